@@ -1,0 +1,141 @@
+/*
+ * globalign_b200 -- C-ABI of the B200 (sm_100a) implementation of globalign's
+ * Gotoh affine-gap Needleman-Wunsch hot path (three-level DP fill + traceback).
+ *
+ * The reference (iamgiddyaboutgit/globalign) is pure Python and has no FFI
+ * layer; the seam this library replaces is the three plain calls inside
+ * find_global_alignment (reference src/globalign/globaligner.py:256-293):
+ *
+ *     make_dp_array      globaligner.py:756-821   boundary row/column
+ *     dp_array_forward   globaligner.py:366-392   fill (cell: :317-363)
+ *     dp_array_backward  globaligner.py:395-593   traceback (tie table :595-685)
+ *
+ * A maintainer of the reference binds these entry points with ctypes (see
+ * INTEGRATION.md for the stub).  All functions return 0 on success or a
+ * negative GA_E_* code; ga_last_error() gives the message.  No function
+ * throws, allocates memory that the caller must free, or takes torch types.
+ *
+ * Conventions
+ *   - Sequences are "lowered": one uint8 letter index (0 .. A-1) per residue,
+ *     pairs concatenated, CSR offsets (int64, n_pairs+1 entries, in letters).
+ *   - The scheme is a dense costing matrix (ga_set_scheme), exactly the
+ *     reference's costing_mat with its "-" row/column split out:
+ *         sub[a*A+b] = costing_mat[a][b]
+ *         gap_h[b]   = costing_mat["-"][b]   horizontal step = gap in seq_1 (level 1)
+ *         gap_v[a]   = costing_mat[a]["-"]   vertical step   = gap in seq_2 (level 2)
+ *         gap_open   = gap_open_cost, max_cost = get_max_val(costing_mat)
+ *   - ops: the alignment as 2-bit operations in WALK order (last alignment
+ *     column first, as dp_array_backward produces them before its final
+ *     reverse): 0 = match/mismatch column, 1 = gap in seq_1, 2 = gap in seq_2.
+ *     Four ops per byte, op k of a pair in bits 2*(k%4) of byte k/4 of that
+ *     pair's slice.  Pair p's slice starts at byte ops_off[p] and must hold
+ *     ceil((m_p+n_p)/4) bytes rounded up to a multiple of 4.
+ *   - Ties are broken in the reference's canonical order (first option listed
+ *     in cost_ranks_dispatcher: level 0, then 1, then 2).
+ *   - status[p]: 0 ok; 1 = the reference's walk would leave the table for this
+ *     pair (only possible when max(m,n) <= gap_open_cost; the reference raises
+ *     IndexError or wraps around there) -- cost is still exact, ops undefined.
+ */
+#ifndef GLOBALIGN_B200_H
+#define GLOBALIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ga_ctx ga_ctx;
+
+enum {
+    GA_OK = 0,
+    GA_E_CUDA = -1,        /* a CUDA runtime call failed */
+    GA_E_ARG = -2,         /* invalid argument */
+    GA_E_RANGE = -3,       /* costs could overflow int32 for these lengths */
+    GA_E_NOMEM = -4,       /* device scratch budget exceeded */
+    GA_E_STATE = -5        /* call order (no scheme / no plan) */
+};
+
+/* flags for ga_align_batch / ga_plan_batch */
+enum {
+    GA_F_DEFAULT = 0,
+    GA_F_FORCE_GENERIC = 1,   /* never use the packed 16-bit kernel */
+    GA_F_COST_ONLY = 2        /* skip the traceback walk (ops / ops_len untouched) */
+};
+
+/* phases reported by ga_get_timing (milliseconds, CUDA events on the ctx stream) */
+enum { GA_T_H2D = 0, GA_T_FILL = 1, GA_T_WALK = 2, GA_T_D2H = 3, GA_T_TOTAL = 4, GA_T_COUNT = 5 };
+
+int ga_version(void);
+int ga_device_count(int *count);
+
+/* One context per (host thread, device).  Calls on a context are serialised by
+ * the caller.  The context owns only scratch (direction codes, plan, staging). */
+int ga_ctx_create(int device, ga_ctx **ctx);
+int ga_ctx_destroy(ga_ctx *ctx);
+const char *ga_last_error(const ga_ctx *ctx);
+
+/* Launch on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream);
+ * NULL/0 = the context's own stream. */
+int ga_ctx_set_stream(ga_ctx *ctx, void *cuda_stream);
+/* Cap on library-owned device scratch in bytes (default 64 GiB); batches whose
+ * direction codes exceed it are processed in chunks. */
+int ga_ctx_set_scratch_limit(ga_ctx *ctx, int64_t bytes);
+
+/* Replaces: the costing_mat / gap_open_cost arguments of make_dp_array,
+ * dp_array_forward, dp_array_backward (globaligner.py:260-287). */
+int ga_set_scheme(ga_ctx *ctx, int A, const int32_t *sub, const int32_t *gap_h,
+                  const int32_t *gap_v, int32_t gap_open, int32_t max_cost);
+
+/* Whole hot path for a batch of pairs, host buffers in, host buffers out
+ * (H2D and D2H inside).  Replaces, per pair, make_dp_array + dp_array_forward +
+ * dp_array_backward.  out_ops may be NULL with GA_F_COST_ONLY. */
+int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off, const uint8_t *s2,
+                   const int64_t *s2_off, int64_t n_pairs, int32_t *out_cost, uint8_t *out_ops,
+                   const int64_t *out_ops_off, int32_t *out_ops_len, int32_t *out_status,
+                   uint32_t flags);
+
+/* Same work on DEVICE-resident buffers, split into planning (host side: reads
+ * the two offset arrays, sizes scratch, uploads tile metadata) and running
+ * (only kernels; asynchronous on the ctx stream).  d_* are device pointers the
+ * caller owns; offsets are passed both as host (for planning) and device
+ * (for the kernels) copies. */
+int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
+                  const int64_t *out_ops_off, uint32_t flags);
+int ga_run_batch(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_off, const uint8_t *d_s2,
+                 const int64_t *d_s2_off, int32_t *d_out_cost, uint8_t *d_out_ops,
+                 const int64_t *d_out_ops_off, int32_t *d_out_ops_len, int32_t *d_out_status);
+int ga_sync(ga_ctx *ctx);
+
+/* Facts about the current plan: kernel name, number of kernel launches one
+ * ga_run_batch makes, direction-code bytes written per run, cells per run. */
+typedef struct {
+    char fill_kernel[64];
+    int32_t rows_per_lane, lanes_per_group, packed16;
+    int32_t launches_per_run;
+    int64_t code_bytes;
+    int64_t cells;
+    int64_t n_chunks;
+} ga_plan_info;
+int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info);
+
+/* CUDA-event milliseconds of the last ga_align_batch / ga_run_batch per phase. */
+int ga_get_timing(ga_ctx *ctx, float *ms /* GA_T_COUNT entries */);
+
+/* Debug / parity aid: the full (m+1) x (n+1) x 3 int32 value table of ONE pair,
+ * i.e. what dp_array_forward leaves in dp_array (globaligner.py:366-392).  If
+ * keep_boundary != 0, row 0 and column 0 of `table` (host, in/out) are used as
+ * given instead of make_dp_array's values -- the reference's own
+ * test_dp_array_forward passes hand-written boundary values. */
+int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                   int keep_boundary, int32_t *table);
+
+/* Integer-ALU roofline microbenchmark: measured giga-ops/s of dependent-chain-
+ * free int32 add / min (mode 0), packed s16x2 add / min3 (mode 1), and the
+ * fill kernel's own instruction mix (mode 2). */
+int ga_alu_peak(ga_ctx *ctx, int mode, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLOBALIGN_B200_H */
