@@ -1,0 +1,404 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: GCUPS with traceback (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+A "step" is one pass of the hot path (fill + direction-code store + traceback walk)
+over one batch of synthetic pairs of the BASELINE shape.  Default workload:
+BASELINE.json configs[1] (1,000,000 DNA pairs, 150 x 150) per GPU; with N > 1 every
+rank aligns its own shard of N x 1,000,000 pairs (pairs are independent: no
+collective on the data path, "scaling": "weak").
+
+`value`   device-resident inputs -> device-resident cost + packed ops, CUDA events on the
+          launching stream, barrier + synchronize on both sides, max over ranks.
+`e2e`     the same work through the public host-buffer call (ga_align_batch): pinned host
+          inputs, H2D, planning, kernels, D2H of costs/ops/lengths/status, all timed.
+`roofline`     fill kernel vs the integer-ALU roofline (BASELINE metric), from its CUDA-event
+               duration (recorded by the library on the launching stream).
+`roofline_hbm` direction-code store vs the measured HBM peak (MEASURED_PEAKS.json).
+`cpu_baseline` the C oracle port on the host cores, on a bounded sample (rank 0, N = 1).
+`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel
+          to the GPU box; its restatement can), with all host threads.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from globalign_b200 import synth  # noqa: E402
+
+METRIC = "GCUPS w/ traceback"
+UNIT = "GCUPS"
+OPS_PER_CELL = 24          # SURVEY.md 8d contract figure: int32 ops per cell, fill with codes
+CODE_BYTES_PER_CELL = 0.75  # 3 x 2 bit
+NOMINAL_INT32_TOPS = 148 * 64 * 1.965e9 / 1e12     # 18.6 Tops/s
+
+DESCR = {
+    "cfg2": "1M synthetic DNA short-read pairs 150 bp x 150 bp with traceback (BASELINE configs[1])",
+    "cfg3": "100k protein pairs 300-1000 aa, BLOSUM62, gap_open_cost=10 (BASELINE configs[2])",
+    "cfg5": "10M DNA pairs 250 bp x 250 bp sharded across the GPUs (BASELINE configs[4])",
+}
+DEFAULT_PAIRS = {"cfg2": 1_000_000, "cfg3": 100_000, "cfg5": 10_000_000}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(DESCR))
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: the BASELINE size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4)
+                          if r[4 + k].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def oracle_dense(dense):
+    from oracle import c_oracle
+    d = c_oracle.Dense.__new__(c_oracle.Dense)
+    d.A, d.sub, d.gap_h, d.gap_v, d.o, d.max_cost = (dense.A, dense.sub, dense.gap_h, dense.gap_v,
+                                                     dense.gap_open, dense.max_cost)
+    return d
+
+
+def cpu_port_gcups(batch, dense, remap, target_s: float = 12.0, threads: int | None = None):
+    """C oracle (port of the reference's path) on the host cores, bounded sample."""
+    from oracle import c_oracle
+    threads = threads or os.cpu_count() or 1
+    d = oracle_dense(dense)
+    n_probe = min(batch.n_pairs, 64 * threads)
+    sub = batch.head(n_probe)
+    t0 = time.perf_counter()
+    c_oracle.align_batch(remap[sub.s1], sub.off1, remap[sub.s2], sub.off2, d, threads)
+    dt = time.perf_counter() - t0
+    rate = sub.cells() / max(dt, 1e-9)
+    n = int(min(batch.n_pairs, max(n_probe, target_s * rate / (batch.cells() / batch.n_pairs))))
+    sub = batch.head(n)
+    t0 = time.perf_counter()
+    c_oracle.align_batch(remap[sub.s1], sub.off1, remap[sub.s2], sub.off2, d, threads)
+    dt = time.perf_counter() - t0
+    return sub.cells() / dt / 1e9, n, dt, threads
+
+
+def python_port_mcups(batch, scheme, n: int = 6):
+    """The pure-Python restatement (same data structures as the reference), 1 core."""
+    from oracle import py_oracle
+    t0 = time.perf_counter()
+    cells = 0
+    for k in range(min(n, batch.n_pairs)):
+        s1, s2 = batch.pair(k)
+        sm, cm = scheme.matrices_for(s1, s2)
+        py_oracle.align(s1, s2, cm, scheme.gap_open_cost)
+        cells += len(s1) * len(s2)
+    return cells / (time.perf_counter() - t0) / 1e6
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from globalign_b200.batch import Scheme
+    name = args.workload
+    scheme = Scheme(**synth.SCHEMES[name])
+    threads = os.cpu_count() or 1
+    per_pair = {"cfg2": 22500, "cfg3": 450000, "cfg5": 62500}[name]
+    n_sample = int(min(DEFAULT_PAIRS[name], max(256, 4e9 / per_pair)))       # ~4e9 cells per step
+    batch = synth.workload(name, n_pairs=n_sample)
+    dense = scheme.dense_for(sorted(batch.alphabet))
+    remap = np.array([dense.index[ch] for ch in batch.alphabet], dtype=np.uint8)
+    from oracle import c_oracle
+    d = oracle_dense(dense)
+    s1, s2 = remap[batch.s1], remap[batch.s2]
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        c_oracle.align_batch(s1, batch.off1, s2, batch.off2, d, threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = batch.cells() / (ms / 1e3) / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": DESCR[name], "sample": f"first {n_sample} pairs per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {n_sample} pairs of {name}, C restatement of the reference's "
+                                   f"fill + value-comparing traceback (oracle/ga_oracle.c), pthreads"},
+        "python_port_mcups_per_core": python_port_mcups(batch, scheme),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from globalign_b200 import _native
+    from globalign_b200.batch import Scheme
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: globalign_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    name = args.workload
+    n_total = args.pairs * world if args.pairs else DEFAULT_PAIRS[name] * (world if name != "cfg5" else 1)
+    scaling = "strong" if (name == "cfg5" and not args.pairs) else "weak"
+    per_rank = n_total // world
+    blocks_per_rank = -(-per_rank // synth._BLOCK)
+    if name == "cfg3":
+        batch = synth.protein_varlen(per_rank * world, 3000).slice(rank * per_rank, (rank + 1) * per_rank) \
+            if world > 1 else synth.workload(name, n_pairs=per_rank)
+    else:
+        batch = synth.workload(name, n_pairs=per_rank, first_block=rank * blocks_per_rank)
+    scheme = Scheme(**synth.SCHEMES[name])
+    dense = scheme.dense_for(sorted(batch.alphabet))
+    remap = np.array([dense.index[ch] for ch in batch.alphabet], dtype=np.uint8)
+    s1h = remap[batch.s1]
+    s2h = remap[batch.s2]
+    cells = batch.cells()
+
+    ctx = _native.Context(local_rank)
+    ctx.set_scheme(dense)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ops_off_h = _native.ops_offsets(batch.off1, batch.off2)
+
+    # ---- device-resident buffers
+    d_s1 = torch.from_numpy(s1h).to(dev)
+    d_s2 = torch.from_numpy(s2h).to(dev)
+    d_off1 = torch.from_numpy(batch.off1).to(dev)
+    d_off2 = torch.from_numpy(batch.off2).to(dev)
+    d_opsoff = torch.from_numpy(ops_off_h).to(dev)
+    n = batch.n_pairs
+    d_cost = torch.empty(n, dtype=torch.int32, device=dev)
+    d_len = torch.empty(n, dtype=torch.int32, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    d_ops = torch.empty(int(ops_off_h[-1]) + 16, dtype=torch.uint8, device=dev)
+    info = ctx.plan_batch(batch.off1, batch.off2, ops_off_h)
+
+    def step_device():
+        ctx.run_batch(d_s1.data_ptr(), d_off1.data_ptr(), d_s2.data_ptr(), d_off2.data_ptr(),
+                      d_cost.data_ptr(), d_ops.data_ptr(), d_opsoff.data_ptr(), d_len.data_ptr(),
+                      d_status.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fill_ms, walk_ms = [], []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    # per-kernel durations (library CUDA events on the same stream) of the last timed step
+    t = ctx.timing()
+    fill_ms.append(t["fill"])
+    walk_ms.append(t["walk"])
+    # a few separately timed steps for the per-kernel average
+    for _ in range(min(3, args.steps)):
+        step_device()
+        t = ctx.timing()
+        fill_ms.append(t["fill"])
+        walk_ms.append(t["walk"])
+    dev_cost = d_cost.cpu().numpy()
+
+    # ---- end to end through the host-buffer call, pinned host memory
+    def pinned(a):
+        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return tt, tt.numpy()
+    keep = []
+    hb = []
+    for a in (s1h, batch.off1, s2h, batch.off2):
+        tt, v = pinned(a)
+        keep.append(tt)
+        hb.append(v)
+    outs = []
+    for shape, dt in ((n, np.int32), (int(ops_off_h[-1]), np.uint8), (n + 1, np.int64), (n, np.int32), (n, np.int32)):
+        tt = torch.empty(shape, dtype=getattr(torch, np.dtype(dt).name)).pin_memory()
+        keep.append(tt)
+        outs.append(tt.numpy())
+    outs[2][:] = ops_off_h
+    h2d = s1h.nbytes + s2h.nbytes + 2 * batch.off1.nbytes + ops_off_h.nbytes
+    d2h = outs[0].nbytes + outs[1].nbytes + outs[3].nbytes + outs[4].nbytes
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        ctx.align_batch(hb[0], hb[1], hb[2], hb[3], out=tuple(outs))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.align_batch(hb[0], hb[1], hb[2], hb[3], out=tuple(outs))
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_phase = ctx.timing()
+    assert np.array_equal(outs[0], dev_cost), "device-resident and host-buffer paths disagree"
+
+    # ---- reduce over ranks: max time, sum of cells
+    vals = torch.tensor([dev_ms / args.steps, e2e_s * 1e3, float(cells)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        step_ms, e2e_ms, total_cells = mx[0].item(), mx[1].item(), sm[2].item()
+    else:
+        step_ms, e2e_ms, total_cells = vals[0].item(), vals[1].item(), float(cells)
+    if rank != 0:
+        return
+
+    value = total_cells / (step_ms / 1e3) / 1e9
+    e2e_value = total_cells / (e2e_ms / 1e3) / 1e9
+    fms = sum(fill_ms) / len(fill_ms)
+    wms = sum(walk_ms) / len(walk_ms)
+    fill_gcups = cells / (fms / 1e3) / 1e9
+    hbm_peak, hbm_src = peaks()
+    try:
+        int32_measured = ctx.alu_peak(0) / 1e3          # Tops/s, IADD chains
+        mix_measured = ctx.alu_peak(5) / 1e3            # Tinstr/s on the packed cell's own mix
+        vimnmx3 = ctx.alu_peak(1) / 1e3
+    except Exception:
+        int32_measured = mix_measured = vimnmx3 = None
+    achieved_tops = fill_gcups * 1e9 * OPS_PER_CELL / 1e12
+    peak_tops = int32_measured or NOMINAL_INT32_TOPS
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "s16x2" if info["packed16"] else "int32", "data": "synthetic",
+        "config": {"workload": DESCR[name], "pairs_per_gpu": n, "cells_per_gpu": cells,
+                   "l2": "inputs + direction codes (%.1f GB per step) are far larger than the 126 MB L2"
+                         % (info["code_bytes"] / 1e9),
+                   "fill_kernel": info["fill_kernel"], "chunks": info["n_chunks"]},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms,
+                "phases_ms": {k: round(v, 3) for k, v in e2e_phase.items()}},
+        "gpu_launches": int(info["launches_per_run"]) * args.steps,
+        "kernels_ms": {"fill": fms, "walk": wms},
+        "roofline": {"bound": "int_alu", "kernel": info["fill_kernel"],
+                     "achieved": achieved_tops, "peak": peak_tops, "unit": "Tops/s",
+                     "frac": achieved_tops / peak_tops,
+                     "peak_source": "measured in this run (ga_alu_peak mode 0: int32 IADD chains)"
+                     if int32_measured else "nominal 148 SM x 64 lanes x 1.965 GHz",
+                     "frac_of_nominal_18.6": achieved_tops / NOMINAL_INT32_TOPS,
+                     "ops_per_cell": OPS_PER_CELL, "fill_gcups": fill_gcups,
+                     "measured_mix_tinstr_s": mix_measured, "measured_vimnmx3_s16x2_tinstr_s": vimnmx3,
+                     "traffic": None},
+        "roofline_hbm": {"bound": "hbm", "kernel": info["fill_kernel"] + " (direction-code store)",
+                         "achieved": cells * CODE_BYTES_PER_CELL / (fms / 1e3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": cells * CODE_BYTES_PER_CELL / (fms / 1e3) / 1e9 / hbm_peak,
+                         "peak_source": hbm_src, "stored_bytes_per_step": info["code_bytes"], "traffic": None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        g, ns, dt, th = cpu_port_gcups(batch, dense, remap)
+        line["cpu_baseline"] = {
+            "value": g, "unit": UNIT, "cores": th, "kind": "port",
+            "sample": f"first {ns} pairs of {name} ({dt:.1f} s), C restatement of the reference's fill + "
+                      f"value-comparing traceback (oracle/ga_oracle.c), pthreads"}
+        line["python_port_mcups_per_core"] = python_port_mcups(batch, scheme)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,240 @@
+"""ctypes binding of libglobalign_b200.so (the C-ABI in include/globalign_b200.h).
+
+There is no CPU fallback: importing this module is cheap, but the first call
+that needs the library raises ``NativeLibraryError`` if the shared object has
+not been built (``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C globalign_b200/csrc``), and any entry point that computes raises if no
+CUDA device is present.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "libglobalign_b200.so"
+
+GA_F_DEFAULT = 0
+GA_F_FORCE_GENERIC = 1
+GA_F_COST_ONLY = 2
+T_H2D, T_FILL, T_WALK, T_D2H, T_TOTAL, T_COUNT = 0, 1, 2, 3, 4, 5
+
+#: every symbol include/globalign_b200.h declares (checked by the CPU tests)
+EXPORTS = (
+    "ga_version", "ga_device_count", "ga_ctx_create", "ga_ctx_destroy", "ga_last_error",
+    "ga_ctx_set_stream", "ga_ctx_set_scratch_limit", "ga_set_scheme", "ga_align_batch",
+    "ga_plan_batch", "ga_run_batch", "ga_sync", "ga_get_plan_info", "ga_get_timing",
+    "ga_fill_values", "ga_alu_peak",
+)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("fill_kernel", C.c_char * 64), ("rows_per_lane", C.c_int32),
+                ("lanes_per_group", C.c_int32), ("packed16", C.c_int32),
+                ("launches_per_run", C.c_int32), ("code_bytes", C.c_int64),
+                ("cells", C.c_int64), ("n_chunks", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            f"(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i64, i32, u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32
+    L.ga_version.restype = C.c_int
+    L.ga_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.ga_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.ga_ctx_destroy.argtypes = [vp]
+    L.ga_last_error.argtypes = [vp]
+    L.ga_last_error.restype = C.c_char_p
+    L.ga_ctx_set_stream.argtypes = [vp, vp]
+    L.ga_ctx_set_scratch_limit.argtypes = [vp, i64]
+    L.ga_set_scheme.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32]
+    L.ga_align_batch.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, u32]
+    L.ga_plan_batch.argtypes = [vp, vp, vp, i64, vp, u32]
+    L.ga_run_batch.argtypes = [vp] + [vp] * 9
+    L.ga_sync.argtypes = [vp]
+    L.ga_get_plan_info.argtypes = [vp, C.POINTER(PlanInfo)]
+    L.ga_get_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ga_fill_values.argtypes = [vp, vp, i64, vp, i64, C.c_int, vp]
+    L.ga_alu_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    for name in EXPORTS:
+        if name not in ("ga_last_error",):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One ga_ctx (device + stream + scratch).  Not thread-safe by design."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        n = C.c_int(0)
+        rc = self._L.ga_device_count(C.byref(n))
+        if rc != 0 or n.value <= 0:
+            raise NativeLibraryError("no CUDA device available: globalign_b200 has no CPU fallback")
+        h = C.c_void_p()
+        rc = self._L.ga_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise NativeLibraryError(f"ga_ctx_create(device={device}) failed with {rc}")
+        self._h = h
+        self.device = int(device)
+        self._scheme_key = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ga_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._L.ga_last_error(self._h).decode("utf-8", "replace")
+            exc = {-3: OverflowError, -4: MemoryError}.get(rc, RuntimeError)
+            raise exc(f"globalign_b200 native error {rc}: {msg}")
+
+    # -- configuration
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._L.ga_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_scratch_limit(self, nbytes: int):
+        self._check(self._L.ga_ctx_set_scratch_limit(self._h, int(nbytes)))
+
+    def set_scheme(self, dense):
+        """`dense`: a lowering.DenseScheme."""
+        key = dense.key()
+        if key == self._scheme_key:
+            return
+        self._check(self._L.ga_set_scheme(self._h, dense.A, _ptr(dense.sub), _ptr(dense.gap_h),
+                                          _ptr(dense.gap_v), dense.gap_open, dense.max_cost))
+        self._scheme_key = key
+
+    # -- host-buffer entry point
+    def align_batch(self, s1, off1, s2, off2, flags: int = 0, out=None):
+        """-> (cost int32[n], ops uint8[...], ops_off int64[n+1], ops_len int32[n], status int32[n]).
+
+        `out`: optional preallocated (cost, ops, ops_off, ops_len, status) arrays
+        (e.g. views of pinned memory) to write into instead of allocating."""
+        n = len(off1) - 1
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        off1 = np.ascontiguousarray(off1, dtype=np.int64)
+        off2 = np.ascontiguousarray(off2, dtype=np.int64)
+        if flags & GA_F_COST_ONLY:
+            cost = np.empty(n, dtype=np.int32) if out is None else out[0]
+            self._check(self._L.ga_align_batch(self._h, _ptr(s1), _ptr(off1), _ptr(s2), _ptr(off2), n,
+                                               _ptr(cost), None, None, None, None, flags))
+            return cost, None, None, None, None
+        if out is None:
+            ops_off = ops_offsets(off1, off2)
+            cost = np.empty(n, dtype=np.int32)
+            ops = np.empty(int(ops_off[-1]), dtype=np.uint8)
+            ops_len = np.empty(n, dtype=np.int32)
+            status = np.empty(n, dtype=np.int32)
+        else:
+            cost, ops, ops_off, ops_len, status = out
+        self._check(self._L.ga_align_batch(self._h, _ptr(s1), _ptr(off1), _ptr(s2), _ptr(off2), n,
+                                           _ptr(cost), _ptr(ops), _ptr(ops_off), _ptr(ops_len),
+                                           _ptr(status), flags))
+        return cost, ops, ops_off, ops_len, status
+
+    # -- device-buffer entry points (pointers are ints, e.g. torch.Tensor.data_ptr())
+    def plan_batch(self, off1, off2, ops_off=None, flags: int = 0):
+        off1 = np.ascontiguousarray(off1, dtype=np.int64)
+        off2 = np.ascontiguousarray(off2, dtype=np.int64)
+        self._check(self._L.ga_plan_batch(self._h, _ptr(off1), _ptr(off2), len(off1) - 1,
+                                          _ptr(ops_off), flags))
+        return self.plan_info()
+
+    def run_batch(self, d_s1, d_off1, d_s2, d_off2, d_cost, d_ops, d_ops_off, d_len, d_status):
+        self._check(self._L.ga_run_batch(self._h, *[C.c_void_p(int(x or 0)) for x in
+                                                    (d_s1, d_off1, d_s2, d_off2, d_cost, d_ops,
+                                                     d_ops_off, d_len, d_status)]))
+
+    def sync(self):
+        self._check(self._L.ga_sync(self._h))
+
+    def plan_info(self) -> dict:
+        info = PlanInfo()
+        self._check(self._L.ga_get_plan_info(self._h, C.byref(info)))
+        return dict(fill_kernel=info.fill_kernel.decode(), rows_per_lane=info.rows_per_lane,
+                    lanes_per_group=info.lanes_per_group, packed16=bool(info.packed16),
+                    launches_per_run=info.launches_per_run, code_bytes=info.code_bytes,
+                    cells=info.cells, n_chunks=info.n_chunks)
+
+    def timing(self) -> dict:
+        ms = (C.c_float * T_COUNT)()
+        self._check(self._L.ga_get_timing(self._h, ms))
+        return dict(h2d=ms[T_H2D], fill=ms[T_FILL], walk=ms[T_WALK], d2h=ms[T_D2H], total=ms[T_TOTAL])
+
+    def fill_values(self, s1, s2, table, keep_boundary: bool):
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        assert table.dtype == np.int32 and table.flags.c_contiguous
+        self._check(self._L.ga_fill_values(self._h, _ptr(s1), len(s1), _ptr(s2), len(s2),
+                                           1 if keep_boundary else 0, _ptr(table)))
+        return table
+
+    def alu_peak(self, mode: int) -> float:
+        g = C.c_double(0.0)
+        self._check(self._L.ga_alu_peak(self._h, int(mode), C.byref(g)))
+        return g.value
+
+
+def ops_offsets(off1, off2) -> np.ndarray:
+    """Byte offsets of each pair's packed-ops slice: ceil((m+n)/4) rounded up to 4."""
+    lens = (np.diff(off1) + np.diff(off2)).astype(np.int64)
+    nbytes = (((lens + 3) // 4) + 3) // 4 * 4
+    out = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(nbytes, out=out[1:])
+    return out
+
+
+def unpack_ops(ops: np.ndarray, start: int, count: int) -> np.ndarray:
+    """2-bit ops of one pair (walk order) as a uint8 array of 0/1/2."""
+    nbytes = (count + 3) // 4
+    b = ops[start:start + nbytes]
+    out = np.empty(nbytes * 4, dtype=np.uint8)
+    out[0::4] = b & 3
+    out[1::4] = (b >> 2) & 3
+    out[2::4] = (b >> 4) & 3
+    out[3::4] = (b >> 6) & 3
+    return out[:count]
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

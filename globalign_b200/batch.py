@@ -1,0 +1,179 @@
+"""Batched alignment: many pairs, one scheme, one GPU call.
+
+The reference aligns exactly one pair per call (globaligner.py:132-314); the
+BASELINE workloads (10^5 .. 10^7 pairs) need a batched entry point.  It keeps the
+reference's scheme keyword arguments and returns results that materialise the
+reference's ``AlignmentResults`` lazily (building 10^6 nested dicts eagerly would
+cost far more than the alignment itself).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native, start
+from .conclude import AlignmentResults, final_cost_to_score
+from .lowering import DenseScheme
+
+GAP = "-"
+
+
+class ReferenceUndefinedError(RuntimeError):
+    """The reference's traceback would leave the DP table for this input (it
+    raises IndexError or silently wraps to negative indices).  Only possible when
+    max(len(seq_1), len(seq_2)) <= gap_open_cost."""
+
+
+def render(ops: np.ndarray, seq_1: str, seq_2: str):
+    """Walk-order ops (0 diag, 1 gap in seq_1, 2 gap in seq_2) -> the three
+    strings of the reference's emitters (globaligner.py:688-753, reversed :584-593)."""
+    fwd = ops[::-1]
+    take1 = fwd != 1                     # columns that consume a seq_1 letter
+    take2 = fwd != 2
+    a = np.frombuffer(seq_1.encode("utf-32-le"), dtype=np.uint32)
+    b = np.frombuffer(seq_2.encode("utf-32-le"), dtype=np.uint32)
+    top = np.full(len(fwd), ord(GAP), dtype=np.uint32)
+    bot = np.full(len(fwd), ord(GAP), dtype=np.uint32)
+    top[take1] = a
+    bot[take2] = b
+    mid = np.full(len(fwd), ord(" "), dtype=np.uint32)
+    diag = fwd == 0
+    mid[diag] = np.where(top[diag] == bot[diag], ord("|"), ord("*"))
+    dec = lambda x: x.tobytes().decode("utf-32-le")
+    return dec(top), dec(mid), dec(bot)
+
+
+class BatchAlignment:
+    """Packed results of a batch; ``batch[k]`` builds the k-th AlignmentResults."""
+
+    def __init__(self, seqs_1, seqs_2, cost, ops, ops_off, ops_len, status, scheme):
+        self.seqs_1, self.seqs_2 = seqs_1, seqs_2
+        self.cost, self.ops, self.ops_off, self.ops_len, self.status = cost, ops, ops_off, ops_len, status
+        self._scheme = scheme
+        m = np.fromiter((len(s) for s in seqs_1), dtype=np.int64, count=len(seqs_1))
+        n = np.fromiter((len(s) for s in seqs_2), dtype=np.int64, count=len(seqs_2))
+        self.score = final_cost_to_score(cost.astype(np.int64), m, n, scheme.max_score)
+
+    def __len__(self):
+        return len(self.cost)
+
+    def ops_of(self, k: int) -> np.ndarray:
+        return _native.unpack_ops(self.ops, int(self.ops_off[k]), int(self.ops_len[k]))
+
+    def __getitem__(self, k: int) -> AlignmentResults:
+        if self.status[k] != 0:
+            raise ReferenceUndefinedError(
+                f"pair {k}: the reference's traceback leaves the DP table for this input "
+                f"(max(m, n) <= gap_open_cost)")
+        s1, s2 = self.seqs_1[k], self.seqs_2[k]
+        top, mid, bot = render(self.ops_of(k), s1, s2)
+        scoring_mat, costing_mat = self._scheme.matrices_for(s1, s2)
+        return AlignmentResults(top, mid, bot, int(self.cost[k]), int(self.score[k]), scoring_mat,
+                                costing_mat, self._scheme.gap_open_score, self._scheme.gap_open_cost,
+                                None)
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+class Scheme:
+    """A resolved scoring/costing scheme, independent of any particular pair."""
+
+    def __init__(self, scoring_mat_name=None, scoring_mat_path=None, match_score=None,
+                 mismatch_score=None, mismatch_cost=None, gap_open_score=None, gap_open_cost=None,
+                 gap_extension_score=None, gap_extension_cost=None):
+        self.branch, self.scoring, self.costing = start.resolve_scheme_options(
+            scoring_mat_name, scoring_mat_path, match_score, mismatch_score, mismatch_cost,
+            gap_open_score, gap_open_cost, gap_extension_score, gap_extension_cost)
+        self.gap_open_score = self.scoring.gap_open_score
+        self.gap_open_cost = self.costing.gap_open_cost
+        if self.branch in ("name", "path"):
+            self.scoring_mat = start.load_matrix_scheme(self.branch, scoring_mat_name, scoring_mat_path)
+            self.costing_mat = start.scoring_mat_to_costing_mat(
+                self.scoring_mat, max_score=start.get_max_val(self.scoring_mat))
+            self.max_score = start.get_max_val(self.scoring_mat)
+        else:
+            self.scoring_mat = self.costing_mat = None
+            # simple schemes: max of the scoring matrix is the match score
+            # (the "-","-" corner and the diagonal; start.py:431-449, 559-612)
+            self.max_score = self.scoring.match_score
+
+    def matrices_for(self, seq_1: str, seq_2: str):
+        """The (scoring_mat, costing_mat) the reference would report for this pair:
+        matrix schemes are pair-independent, simple schemes are built over the
+        letters of the pair (start.py:319-343)."""
+        if self.scoring_mat is not None:
+            return self.scoring_mat, self.costing_mat
+        return start.simple_scheme_matrices(self.branch, start.get_common_alphabet(seq_1, seq_2),
+                                            self.scoring, self.costing)
+
+    def dense_for(self, alphabet) -> DenseScheme:
+        """Dense tables over `alphabet` (sorted letters of the whole batch)."""
+        if self.scoring_mat is not None:
+            letters = [k for k in self.costing_mat if k != GAP]
+            missing = set(alphabet).difference(self.scoring_mat.keys())
+            if missing:
+                raise RuntimeError(
+                    f"common_alphabet contains values not in scoring_mat_keys, e.g. {missing}.  "
+                    f"Please check your sequences and your scoring matrix.")
+            return DenseScheme(self.costing_mat, self.gap_open_cost, letters)
+        _, cm = start.simple_scheme_matrices(self.branch, list(alphabet), self.scoring, self.costing)
+        return DenseScheme(cm, self.gap_open_cost)
+
+
+def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=None,
+                           scoring_mat_name=None, scoring_mat_path=None, match_score=None,
+                           mismatch_score=None, mismatch_cost=None, gap_open_score=None,
+                           gap_open_cost=None, gap_extension_score=None, gap_extension_cost=None
+                           ) -> BatchAlignment:
+    """Align seqs_1[k] with seqs_2[k] for every k under one scheme.
+
+    Scheme keywords mean exactly what they mean for ``find_global_alignment``.
+    ``max_seq_len_prod`` defaults to the reference's guard (start.py:213); pass a
+    larger number (or ``float('inf')``) to lift it.
+    """
+    if len(seqs_1) != len(seqs_2) or len(seqs_1) == 0:
+        raise RuntimeError("seqs_1 and seqs_2 must be non-empty and of equal length")
+    limit = start.MAX_SEQ_LEN_PRODUCT if max_seq_len_prod is None else max_seq_len_prod
+    up1, up2 = [], []
+    for s1, s2 in zip(seqs_1, seqs_2):
+        start.check_seq_lengths(s1, s2, limit)
+        if GAP in s1 or GAP in s2:
+            raise RuntimeError(
+                "The current implementation does not allow for '-' characters in the sequences "
+                "because they are used internally for gaps.  Please replace this character in "
+                "your sequences.")
+        up1.append(s1.upper())
+        up2.append(s2.upper())
+    scheme = Scheme(scoring_mat_name, scoring_mat_path, match_score, mismatch_score, mismatch_cost,
+                    gap_open_score, gap_open_cost, gap_extension_score, gap_extension_cost)
+    alphabet = sorted(set().union(*map(set, up1), *map(set, up2)))
+    dense = scheme.dense_for(alphabet)
+    enc1 = [dense.encode(s) for s in up1]
+    enc2 = [dense.encode(s) for s in up2]
+    off1 = np.zeros(len(up1) + 1, dtype=np.int64)
+    off2 = np.zeros(len(up2) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in enc1], out=off1[1:])
+    np.cumsum([len(x) for x in enc2], out=off2[1:])
+    ctx = _native.default_context(device)
+    ctx.set_scheme(dense)
+    cost, ops, ops_off, ops_len, status = ctx.align_batch(
+        np.concatenate(enc1), off1, np.concatenate(enc2), off2)
+    return BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme)
+
+
+def align_encoded(batch, scheme_kwargs: dict, *, device: int = 0, flags: int = 0):
+    """Fast path for already-encoded batches (``synth.PairBatch``-like objects with
+    .alphabet/.s1/.off1/.s2/.off2): no Python strings are touched.
+    -> (cost, ops, ops_off, ops_len, status, Scheme, DenseScheme)"""
+    scheme = Scheme(**scheme_kwargs)
+    dense_any = scheme.dense_for(sorted(batch.alphabet))
+    # re-index the batch's letter codes into the scheme's letter order
+    remap = np.array([dense_any.index[ch] for ch in batch.alphabet], dtype=np.uint8)
+    identity = np.array_equal(remap, np.arange(len(remap), dtype=np.uint8))
+    s1 = batch.s1 if identity else remap[batch.s1]
+    s2 = batch.s2 if identity else remap[batch.s2]
+    ctx = _native.default_context(device)
+    ctx.set_scheme(dense_any)
+    out = ctx.align_batch(s1, batch.off1, s2, batch.off2, flags)
+    return (*out, scheme, dense_any)

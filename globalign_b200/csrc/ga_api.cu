@@ -1,0 +1,702 @@
+// C-ABI of libglobalign_b200.so (see include/globalign_b200.h).
+//
+// Host side: context, scheme upload, planner (pairs -> tiles -> chunks that fit
+// the direction-code scratch), kernel launches on one CUDA stream, CUDA-event
+// timing.  No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/globalign_b200.h"
+#include "ga_fill.cuh"
+#include "ga_walk.cuh"
+
+using namespace ga;
+
+// ------------------------------------------------------------------ kernels registry
+struct KernelCfg {
+    const char *name;
+    LayInfo lay;
+    bool simple;
+    const void *fill_fn;
+    void (*launch_fill)(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
+                        const TileDesc *tiles, int n_tiles, int *counter, const uint8_t *s1,
+                        const long long *off1, const uint8_t *s2, const long long *off2,
+                        uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost);
+    void (*launch_walk)(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, int pair_lo,
+                        int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
+                        const long long *off2, const uint32_t *codes, uint8_t *out_ops,
+                        const long long *ops_off, int *out_len, int *out_status);
+};
+
+template <bool P, bool S, int R, int G>
+static void launch_fill_t(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
+                          const TileDesc *tiles, int n_tiles, int *counter, const uint8_t *s1,
+                          const long long *off1, const uint8_t *s2, const long long *off2,
+                          uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost) {
+    fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, n_tiles, counter, s1, off1, s2, off2,
+                                                     codes, bnd, bnd_stride, sb_stride, out_cost);
+}
+template <bool P, int R, int G>
+static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, int pair_lo,
+                          int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
+                          const long long *off2, const uint32_t *codes, uint8_t *out_ops,
+                          const long long *ops_off, int *out_len, int *out_status) {
+    const int grid = (n_pairs + 127) / 128;
+    walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, pair_lo, n_pairs, s1, off1, s2, off2, codes,
+                                               out_ops, ops_off, out_len, out_status);
+}
+template <bool P, bool S, int R, int G>
+static KernelCfg make_cfg(const char *name) {
+    KernelCfg c;
+    c.name = name;
+    c.lay = lay_info<P, R, G>();
+    c.simple = S;
+    c.fill_fn = (const void *)fill_kernel<P, S, R, G>;
+    c.launch_fill = launch_fill_t<P, S, R, G>;
+    c.launch_walk = launch_walk_t<P, R, G>;
+    return c;
+}
+
+static const std::vector<KernelCfg> &registry() {
+    static const std::vector<KernelCfg> cfgs = {
+        // packed 16-bit, two pairs per register (simple schemes, short reads)
+        make_cfg<true, true, 5, 32>("fill_p16_r5_g32"),
+        make_cfg<true, true, 10, 16>("fill_p16_r10_g16"),
+        make_cfg<true, true, 15, 10>("fill_p16_r15_g10"),
+        make_cfg<true, true, 19, 8>("fill_p16_r19_g8"),
+        make_cfg<true, true, 16, 16>("fill_p16_r16_g16"),
+        make_cfg<true, true, 8, 32>("fill_p16_r8_g32"),
+        make_cfg<true, true, 16, 32>("fill_p16_r16_g32"),
+        // int32, simple schemes (compare instead of table)
+        make_cfg<false, true, 8, 8>("fill_i32s_r8_g8"),
+        make_cfg<false, true, 8, 16>("fill_i32s_r8_g16"),
+        make_cfg<false, true, 8, 32>("fill_i32s_r8_g32"),
+        // int32, table-driven schemes (BLOSUM, custom matrices, per-letter gaps)
+        make_cfg<false, false, 8, 8>("fill_i32t_r8_g8"),
+        make_cfg<false, false, 8, 16>("fill_i32t_r8_g16"),
+        make_cfg<false, false, 8, 32>("fill_i32t_r8_g32"),
+    };
+    return cfgs;
+}
+
+static const KernelCfg *find_cfg(const char *name) {
+    for (const auto &c : registry())
+        if (strcmp(c.name, name) == 0) return &c;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------ context
+struct Chunk {
+    int tile_lo, tile_hi;     // tiles [lo, hi)
+    int pair_lo, pair_hi;     // pairs [lo, hi)
+    long long code_u4;        // uint4 words of direction codes
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ga_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int64_t scratch_limit = (int64_t)64 << 30;
+    int sm_count = 0;
+    // scheme
+    bool have_scheme = false;
+    SchemeDev sc{};
+    bool uniform_gaps = false;
+    DevBuf d_sub4, d_gh4t, d_gv4t, d_gvraw, d_ghraw;
+    // plan
+    bool have_plan = false;
+    const KernelCfg *cfg = nullptr;
+    int64_t n_pairs = 0;
+    std::vector<TileDesc> tiles;
+    std::vector<Chunk> chunks;
+    int sb_stride = 0, bnd_stride = 0, grid = 0;
+    size_t smem = 0;
+    int64_t cells = 0, code_bytes = 0;
+    uint32_t plan_flags = 0;
+    DevBuf d_tiles, d_codes, d_bnd, d_counter;
+    // staging for the host-buffer entry point
+    DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
+    // timing
+    cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> seg;      // per chunk: fill-end, walk-end
+    float ms[GA_T_COUNT] = {};
+    bool timing_valid = false;
+};
+
+static int fail(ga_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, GA_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+static int ensure(ga_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return GA_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = std::max(bytes, (size_t)256);
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return GA_OK;
+}
+
+extern "C" int ga_version(void) { return 100; }
+
+extern "C" int ga_device_count(int *count) {
+    if (!count) return GA_E_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return GA_E_CUDA; }
+    *count = n;
+    return GA_OK;
+}
+
+extern "C" int ga_ctx_create(int device, ga_ctx **out) {
+    if (!out) return GA_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return GA_E_CUDA;
+    ga_ctx *ctx = new ga_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return GA_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    *out = ctx;
+    return GA_OK;
+}
+
+extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
+    if (!ctx) return GA_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->d_sub4, &ctx->d_gh4t, &ctx->d_gv4t, &ctx->d_gvraw, &ctx->d_ghraw,
+                      &ctx->d_tiles, &ctx->d_codes, &ctx->d_bnd, &ctx->d_counter, &ctx->d_s1,
+                      &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
+                      &ctx->d_opsoff, &ctx->d_len, &ctx->d_status})
+        if (b->p) cudaFree(b->p);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->seg) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return GA_OK;
+}
+
+extern "C" const char *ga_last_error(const ga_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int ga_ctx_set_stream(ga_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return GA_E_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return GA_OK;
+}
+
+extern "C" int ga_ctx_set_scratch_limit(ga_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes < (1 << 20)) return fail(ctx, GA_E_ARG, "scratch limit must be >= 1 MiB");
+    ctx->scratch_limit = bytes;
+    ctx->have_plan = false;
+    return GA_OK;
+}
+
+extern "C" int ga_sync(ga_ctx *ctx) {
+    if (!ctx) return GA_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ scheme
+extern "C" int ga_set_scheme(ga_ctx *ctx, int A, const int32_t *sub, const int32_t *gap_h,
+                             const int32_t *gap_v, int32_t gap_open, int32_t max_cost) {
+    if (!ctx) return GA_E_ARG;
+    if (A < 1 || A > 250 || !sub || !gap_h || !gap_v) return fail(ctx, GA_E_ARG, "bad scheme (1 <= A <= 250)");
+    if (gap_open < 0) return fail(ctx, GA_E_ARG, "gap_open must be >= 0");
+    int64_t mx = 0;
+    for (int k = 0; k < A * A; ++k) {
+        if (sub[k] < 0) return fail(ctx, GA_E_ARG, "costs must be non-negative");
+        mx = std::max<int64_t>(mx, sub[k]);
+    }
+    for (int k = 0; k < A; ++k) {
+        if (gap_h[k] < 0 || gap_v[k] < 0) return fail(ctx, GA_E_ARG, "costs must be non-negative");
+        mx = std::max<int64_t>(mx, std::max(gap_h[k], gap_v[k]));
+    }
+    if (max_cost < mx) return fail(ctx, GA_E_ARG, "max_cost is smaller than a matrix entry");
+    if ((int64_t)max_cost > (1 << 24) || gap_open > (1 << 24)) return fail(ctx, GA_E_RANGE, "costs too large");
+    CK(cudaSetDevice(ctx->device));
+    // simple scheme: zero diagonal, one off-diagonal value, one gap cost per direction
+    bool simple = true, uniform = true;
+    int mm = (A > 1) ? sub[1] : 0;
+    for (int a = 0; a < A && simple; ++a)
+        for (int b = 0; b < A; ++b)
+            if (sub[a * A + b] != (a == b ? 0 : mm)) { simple = false; break; }
+    for (int k = 1; k < A; ++k)
+        if (gap_h[k] != gap_h[0] || gap_v[k] != gap_v[0]) uniform = false;
+    simple = simple && uniform;
+    std::vector<int> sub4((size_t)(A + 1) * A, 0), gh4t(A), gv4t(A + 1), gvraw(A + 1), ghraw(A);
+    for (int k = 0; k < A * A; ++k) sub4[k] = 4 * sub[k];
+    for (int k = 0; k < A; ++k) {
+        gh4t[k] = 4 * gap_h[k] + 1;
+        gv4t[k] = 4 * gap_v[k] + 2;
+        gvraw[k] = gap_v[k];
+        ghraw[k] = gap_h[k];
+    }
+    gv4t[A] = 2;
+    gvraw[A] = 0;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_sub4, sub4.size() * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_gh4t, gh4t.size() * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_gv4t, gv4t.size() * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_gvraw, gvraw.size() * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ghraw, ghraw.size() * 4))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->d_sub4.p, sub4.data(), sub4.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_gh4t.p, gh4t.data(), gh4t.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_gv4t.p, gv4t.data(), gv4t.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_gvraw.p, gvraw.data(), gvraw.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ghraw.p, ghraw.data(), ghraw.size() * 4, cudaMemcpyHostToDevice));
+    SchemeDev &sc = ctx->sc;
+    sc.A = A;
+    sc.o = gap_open;
+    sc.max_cost = max_cost;
+    sc.simple = simple ? 1 : 0;
+    sc.mm = mm;
+    sc.gh = gap_h[0];
+    sc.gv = gap_v[0];
+    sc.sub4 = (const int *)ctx->d_sub4.p;
+    sc.gh4t = (const int *)ctx->d_gh4t.p;
+    sc.gv4t = (const int *)ctx->d_gv4t.p;
+    sc.gv_raw = (const int *)ctx->d_gvraw.p;
+    sc.gh_raw = (const int *)ctx->d_ghraw.p;
+    ctx->uniform_gaps = uniform;
+    ctx->have_scheme = true;
+    ctx->have_plan = false;
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ planner
+static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32_t flags) {
+    const SchemeDev &sc = ctx->sc;
+    // largest value any cell (padding included) can take, times 4 plus tag, must fit int16
+    auto fits16 = [&](const KernelCfg *c) {
+        const int band = c->lay.BAND, G = c->lay.G;
+        const long long Mp = ((maxM + band - 1) / band) * (long long)band, Np = maxN + G;
+        const long long big = (long long)(sc.max_cost + 1) * std::max(maxM, maxN);
+        const long long vmax = big + (std::min(Mp, Np) + 2) * sc.max_cost + 3LL * sc.o;
+        return 4 * vmax + 3 < 32767 && 4LL * sc.mm < 65536;
+    };
+    if (const char *force = getenv("GA_FORCE_CFG")) {      // tests and tuning
+        const KernelCfg *c = find_cfg(force);
+        if (!c || (c->simple && !sc.simple) || (c->lay.packed && !fits16(c))) return nullptr;
+        return c;
+    }
+    if (sc.simple) {
+        if (!(flags & GA_F_FORCE_GENERIC)) {
+            const char *pick = maxM <= 160 ? "fill_p16_r10_g16"
+                               : maxM <= 256 ? "fill_p16_r16_g16" : "fill_p16_r16_g32";
+            const KernelCfg *c = find_cfg(pick);
+            if (fits16(c)) return c;
+        }
+        return find_cfg(maxM <= 64 ? "fill_i32s_r8_g8" : maxM <= 128 ? "fill_i32s_r8_g16" : "fill_i32s_r8_g32");
+    }
+    return find_cfg(maxM <= 64 ? "fill_i32t_r8_g8" : maxM <= 128 ? "fill_i32t_r8_g16" : "fill_i32t_r8_g32");
+}
+
+extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off,
+                             int64_t n_pairs, const int64_t *out_ops_off, uint32_t flags) {
+    if (!ctx) return GA_E_ARG;
+    if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
+    if (!s1_off || !s2_off || n_pairs < 1 || n_pairs > 0x7fffff00LL)
+        return fail(ctx, GA_E_ARG, "bad batch (1 <= n_pairs < 2^31)");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_plan = false;
+    for (float &v : ctx->ms) v = 0.f;
+    int maxM = 0, maxN = 0;
+    int64_t cells = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t m = s1_off[p + 1] - s1_off[p], n = s2_off[p + 1] - s2_off[p];
+        if (m < 1 || n < 1) return fail(ctx, GA_E_ARG, "pair %lld has an empty sequence", (long long)p);
+        if (m > (1 << 24) || n > (1 << 15))
+            return fail(ctx, GA_E_ARG, "pair %lld too long for the batched kernels (m <= 2^24, n <= 32768); use ga_align_long", (long long)p);
+        if (out_ops_off && !(flags & GA_F_COST_ONLY)) {
+            const int64_t need = (((m + n + 3) / 4) + 3) & ~(int64_t)3;
+            if ((out_ops_off[p] & 3) || out_ops_off[p + 1] - out_ops_off[p] < need)
+                return fail(ctx, GA_E_ARG, "ops slice of pair %lld is too small or misaligned", (long long)p);
+        }
+        maxM = std::max<int>(maxM, (int)m);
+        maxN = std::max<int>(maxN, (int)n);
+        cells += m * n;
+    }
+    const KernelCfg *cfg = choose_cfg(ctx, maxM, maxN, flags);
+    if (!cfg) return fail(ctx, GA_E_ARG, "no usable kernel configuration (GA_FORCE_CFG names an unknown kernel or one whose value range / scheme kind does not fit)");
+    const LayInfo &L = cfg->lay;
+    {   // int32 range
+        const long long Mp = ((maxM + L.BAND - 1) / L.BAND) * (long long)L.BAND;
+        const long long big = (long long)(ctx->sc.max_cost + 1) * std::max(maxM, maxN);
+        const long long vmax = big + (std::min<long long>(Mp, maxN + L.G) + 2) * ctx->sc.max_cost + 3LL * ctx->sc.o;
+        if (4 * vmax + 3 >= 0x7fffffffLL) return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
+    }
+    if (!cfg->simple && ctx->sc.A > 64)
+        return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
+    // tiles: consecutive groups of PPT pairs
+    const int64_t n_tiles = (n_pairs + L.PPT - 1) / L.PPT;
+    ctx->tiles.resize((size_t)n_tiles);
+    ctx->chunks.clear();
+    const long long limit_u4 = std::max<long long>(ctx->scratch_limit / 16, 1);
+    Chunk cur{0, 0, 0, 0, 0};
+    long long max_chunk_u4 = 0, total_u4 = 0;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        TileDesc &td = ctx->tiles[(size_t)t];
+        const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
+        int M = 0, N = 0;
+        for (int64_t p = lo; p < hi; ++p) {
+            M = std::max<int>(M, (int)(s1_off[p + 1] - s1_off[p]));
+            N = std::max<int>(N, (int)(s2_off[p + 1] - s2_off[p]));
+        }
+        const long long npass = (M + L.BAND - 1) / L.BAND;
+        const long long nTB = (N + L.G - 1 + L.S - 1) / L.S;
+        const long long u4 = npass * nTB * L.NQ * 32;
+        if (u4 > limit_u4) return fail(ctx, GA_E_NOMEM, "one tile needs %lld bytes of direction codes, above the scratch limit", u4 * 16);
+        if (cur.code_u4 + u4 > limit_u4) {
+            cur.tile_hi = (int)t;
+            cur.pair_hi = (int)lo;
+            ctx->chunks.push_back(cur);
+            max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
+            cur = Chunk{(int)t, 0, (int)lo, 0, 0};
+        }
+        td.code_off = cur.code_u4;
+        td.first_pair = (int)lo;
+        td.n_pairs = (int)(hi - lo);
+        td.M = M;
+        td.N = N;
+        cur.code_u4 += u4;
+        total_u4 += u4;
+    }
+    cur.tile_hi = (int)n_tiles;
+    cur.pair_hi = (int)n_pairs;
+    ctx->chunks.push_back(cur);
+    max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
+
+    // launch geometry
+    const int warps = 4;
+    ctx->sb_stride = ((maxN + L.G - 1 + L.S + 1 + 16) + 15) & ~15;
+    ctx->bnd_stride = maxN + 8;
+    const size_t elt = L.packed ? 4 : 1;
+    size_t table = 0;
+    if (!cfg->simple) table = (((size_t)(ctx->sc.A + 1) * ctx->sc.A + ctx->sc.A) * 4 + 15) & ~(size_t)15;
+    ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
+    if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
+    CK(cudaFuncSetAttribute(cfg->fill_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg->fill_fn, 128, ctx->smem));
+    if (per_sm < 1) return fail(ctx, GA_E_ARG, "fill kernel does not fit on an SM");
+    const long long want_blocks = (n_tiles + warps - 1) / warps;
+    ctx->grid = (int)std::min<long long>(want_blocks, (long long)per_sm * ctx->sm_count);
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_codes, (size_t)max_chunk_u4 * 16))) return rc;
+    if ((rc = ensure(ctx, ctx->d_bnd, (size_t)ctx->grid * warps * L.IPW * ctx->bnd_stride * sizeof(int2)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_counter, 256))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->tiles.data(), (size_t)n_tiles * sizeof(TileDesc),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // ctx->tiles may be re-planned by the caller
+    // timing events: 2 per chunk
+    while (ctx->seg.size() < 2 * ctx->chunks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->seg.push_back(e);
+    }
+    ctx->cfg = cfg;
+    ctx->n_pairs = n_pairs;
+    ctx->cells = cells;
+    ctx->code_bytes = total_u4 * 16;
+    ctx->plan_flags = flags;
+    ctx->have_plan = true;
+    return GA_OK;
+}
+
+extern "C" int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info) {
+    if (!ctx || !info || !ctx->have_plan) return GA_E_STATE;
+    memset(info, 0, sizeof *info);
+    snprintf(info->fill_kernel, sizeof info->fill_kernel, "%s", ctx->cfg->name);
+    info->rows_per_lane = ctx->cfg->lay.R;
+    info->lanes_per_group = ctx->cfg->lay.G;
+    info->packed16 = ctx->cfg->lay.packed;
+    info->launches_per_run = (int)ctx->chunks.size() * ((ctx->plan_flags & GA_F_COST_ONLY) ? 1 : 2);
+    info->code_bytes = ctx->code_bytes;
+    info->cells = ctx->cells;
+    info->n_chunks = (int64_t)ctx->chunks.size();
+    return GA_OK;
+}
+
+extern "C" int ga_run_batch(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_off,
+                            const uint8_t *d_s2, const int64_t *d_s2_off, int32_t *d_out_cost,
+                            uint8_t *d_out_ops, const int64_t *d_out_ops_off, int32_t *d_out_ops_len,
+                            int32_t *d_out_status) {
+    if (!ctx) return GA_E_ARG;
+    if (!ctx->have_plan) return fail(ctx, GA_E_STATE, "ga_plan_batch has not been called");
+    const bool cost_only = (ctx->plan_flags & GA_F_COST_ONLY) != 0;
+    if (!d_s1 || !d_s1_off || !d_s2 || !d_s2_off || !d_out_cost ||
+        (!cost_only && (!d_out_ops || !d_out_ops_off || !d_out_ops_len || !d_out_status)))
+        return fail(ctx, GA_E_ARG, "null device buffer");
+    CK(cudaSetDevice(ctx->device));
+    const KernelCfg *cfg = ctx->cfg;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    for (size_t c = 0; c < ctx->chunks.size(); ++c) {
+        const Chunk &ch = ctx->chunks[c];
+        const int n_tiles = ch.tile_hi - ch.tile_lo;
+        CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st));
+        const int grid = std::min(ctx->grid, (n_tiles + 3) / 4);
+        cfg->launch_fill(grid, ctx->smem, st, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo,
+                         n_tiles, (int *)ctx->d_counter.p, d_s1, (const long long *)d_s1_off, d_s2,
+                         (const long long *)d_s2_off, (uint4 *)ctx->d_codes.p, (int2 *)ctx->d_bnd.p,
+                         ctx->bnd_stride, ctx->sb_stride, d_out_cost);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->seg[2 * c], st));
+        if (!cost_only) {
+            cfg->launch_walk(st, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo, ch.pair_lo,
+                             ch.pair_hi - ch.pair_lo, d_s1, (const long long *)d_s1_off, d_s2,
+                             (const long long *)d_s2_off, (const uint32_t *)ctx->d_codes.p, d_out_ops,
+                             (const long long *)d_out_ops_off, d_out_ops_len, d_out_status);
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(ctx->seg[2 * c + 1], st));
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    ctx->timing_valid = true;
+    return GA_OK;
+}
+
+extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return GA_E_ARG;
+    if (!ctx->timing_valid || !ctx->have_plan) return fail(ctx, GA_E_STATE, "nothing has run yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float fill = 0, walk = 0, total = 0;
+    cudaEvent_t prev = ctx->ev[0];
+    for (size_t c = 0; c < ctx->chunks.size(); ++c) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, prev, ctx->seg[2 * c]));
+        CK(cudaEventElapsedTime(&b, ctx->seg[2 * c], ctx->seg[2 * c + 1]));
+        fill += a;
+        walk += b;
+        prev = ctx->seg[2 * c + 1];
+    }
+    CK(cudaEventElapsedTime(&total, ctx->ev[0], ctx->ev[1]));
+    ctx->ms[GA_T_FILL] = fill;
+    ctx->ms[GA_T_WALK] = walk;
+    ctx->ms[GA_T_TOTAL] = ctx->ms[GA_T_H2D] + total + ctx->ms[GA_T_D2H];
+    for (int k = 0; k < GA_T_COUNT; ++k) ms[k] = ctx->ms[k];
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer entry point
+extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off,
+                              const uint8_t *s2, const int64_t *s2_off, int64_t n_pairs,
+                              int32_t *out_cost, uint8_t *out_ops, const int64_t *out_ops_off,
+                              int32_t *out_ops_len, int32_t *out_status, uint32_t flags) {
+    if (!ctx) return GA_E_ARG;
+    const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
+    if (!s1 || !s2 || !s1_off || !s2_off || !out_cost ||
+        (!cost_only && (!out_ops || !out_ops_off || !out_ops_len || !out_status)))
+        return fail(ctx, GA_E_ARG, "null host buffer");
+    int rc = ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const size_t b1 = (size_t)s1_off[n_pairs], b2 = (size_t)s2_off[n_pairs];
+    const size_t offb = (size_t)(n_pairs + 1) * 8;
+    const size_t opsb = cost_only ? 0 : (size_t)out_ops_off[n_pairs];
+    if ((rc = ensure(ctx, ctx->d_s1, b1 + 16)) || (rc = ensure(ctx, ctx->d_s2, b2 + 16)) ||
+        (rc = ensure(ctx, ctx->d_off1, offb)) || (rc = ensure(ctx, ctx->d_off2, offb)) ||
+        (rc = ensure(ctx, ctx->d_cost, (size_t)n_pairs * 4)))
+        return rc;
+    if (!cost_only &&
+        ((rc = ensure(ctx, ctx->d_ops, opsb + 16)) || (rc = ensure(ctx, ctx->d_opsoff, offb)) ||
+         (rc = ensure(ctx, ctx->d_len, (size_t)n_pairs * 4)) ||
+         (rc = ensure(ctx, ctx->d_status, (size_t)n_pairs * 4))))
+        return rc;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaMemcpyAsync(ctx->d_s1.p, s1, b1, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_s2.p, s2, b2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, st));
+    if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    rc = ga_run_batch(ctx, (const uint8_t *)ctx->d_s1.p, (const int64_t *)ctx->d_off1.p,
+                      (const uint8_t *)ctx->d_s2.p, (const int64_t *)ctx->d_off2.p,
+                      (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p,
+                      (const int64_t *)ctx->d_opsoff.p, (int32_t *)ctx->d_len.p,
+                      (int32_t *)ctx->d_status.p);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaMemcpyAsync(out_cost, ctx->d_cost.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    if (!cost_only) {
+        CK(cudaMemcpyAsync(out_ops, ctx->d_ops.p, opsb, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_ops_len, ctx->d_len.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_status, ctx->d_status.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->ms[GA_T_H2D], ctx->ev[2], ctx->ev[3]));
+    CK(cudaEventElapsedTime(&ctx->ms[GA_T_D2H], ctx->ev[4], ctx->ev[5]));
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ debug: full value table
+// What dp_array_forward leaves in dp_array (reference globaligner.py:366-392), for ONE
+// small pair; anti-diagonals in parallel, one block.  Not a performance path.
+__global__ void values_kernel(const SchemeDev sc, const uint8_t *s1, int m, const uint8_t *s2, int n,
+                              int keep_boundary, int *tab) {
+    const int W = n + 1;
+    auto at = [&](int i, int j, int k) -> int & { return tab[((size_t)i * W + j) * 3 + k]; };
+    if (!keep_boundary) {
+        if (threadIdx.x == 0) {
+            const int big = (sc.max_cost + 1) * max(m, n);
+            at(0, 0, 0) = at(0, 0, 1) = at(0, 0, 2) = 0;
+            int run = sc.o;
+            for (int j = 1; j <= n; ++j) { run += sc.gh_raw[s2[j - 1]]; at(0, j, 0) = big; at(0, j, 1) = run; at(0, j, 2) = big; }
+            run = sc.o;
+            for (int i = 1; i <= m; ++i) { run += sc.gv_raw[s1[i - 1]]; at(i, 0, 0) = big; at(i, 0, 1) = big; at(i, 0, 2) = run; }
+        }
+        __syncthreads();
+    }
+    for (int d = 2; d <= m + n; ++d) {
+        const int ilo = max(1, d - n), ihi = min(m, d - 1);
+        for (int i = ilo + threadIdx.x; i <= ihi; i += blockDim.x) {
+            const int j = d - i;
+            const int a = s1[i - 1], b = s2[j - 1];
+            const int o = sc.o;
+            at(i, j, 0) = min(min(at(i - 1, j - 1, 0), at(i - 1, j - 1, 1)), at(i - 1, j - 1, 2)) + sc.sub4[a * sc.A + b] / 4;
+            at(i, j, 1) = min(min(at(i, j - 1, 0) + o, at(i, j - 1, 1)), at(i, j - 1, 2) + o) + sc.gh_raw[b];
+            at(i, j, 2) = min(min(at(i - 1, j, 0) + o, at(i - 1, j, 1) + o), at(i - 1, j, 2)) + sc.gv_raw[a];
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                              int keep_boundary, int32_t *table) {
+    if (!ctx) return GA_E_ARG;
+    if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
+    if (!s1 || !s2 || !table || m < 1 || n < 1 || (m + 1) * (n + 1) > (int64_t)50'000'000)
+        return fail(ctx, GA_E_ARG, "ga_fill_values is for small pairs");
+    CK(cudaSetDevice(ctx->device));
+    const size_t tb = (size_t)(m + 1) * (n + 1) * 3 * 4;
+    uint8_t *d1 = nullptr, *d2 = nullptr;
+    int *dt = nullptr;
+    CK(cudaMalloc(&d1, m));
+    CK(cudaMalloc(&d2, n));
+    CK(cudaMalloc(&dt, tb));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dt, table, tb, cudaMemcpyHostToDevice, st));
+    values_kernel<<<1, 256, 0, st>>>(ctx->sc, d1, (int)m, d2, (int)n, keep_boundary, dt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(table, dt, tb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d1);
+    cudaFree(d2);
+    cudaFree(dt);
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ integer-ALU roofline probe
+// Independent chains, no memory traffic: how many of the fill kernel's instruction
+// kinds the SMs retire per second.  mode 0: IADD;  1: VIMNMX3.S16x2;  2: VIMNMX3 (s32);
+// 3: LOP3;  4: IMAD;  5: the packed fill cell's own mix (20 instructions).
+template <int MODE>
+__global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsigned seed) {
+    unsigned a[8], b[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = seed + threadIdx.x * 7u + k;
+        b[k] = seed * 3u + threadIdx.x + 11u * k;
+        c[k] = seed ^ (threadIdx.x * 5u + k);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (MODE == 0) { a[k] += b[k]; b[k] += a[k]; }
+            else if (MODE == 1) { a[k] = __vimin3_s16x2(a[k], b[k], c[k]); b[k] = __vimin3_s16x2(b[k], c[k], a[k]); }
+            else if (MODE == 2) { a[k] = (unsigned)__vimin3_s32((int)a[k], (int)b[k], (int)c[k]); b[k] = (unsigned)__vimin3_s32((int)b[k], (int)c[k], (int)a[k]); }
+            else if (MODE == 3) { a[k] = (a[k] & b[k]) ^ c[k]; b[k] = (b[k] | c[k]) ^ a[k]; }
+            else if (MODE == 4) { a[k] = a[k] * b[k] + c[k]; b[k] = b[k] * c[k] + a[k]; }
+            else {
+                // one packed cell: a = diag/h, b = L, c = U  (same 20-instruction mix as fill_kernel)
+                const unsigned d0 = __vminu2(a[k] ^ seed, 0x00010001u) * 20u + a[k];
+                const unsigned d1 = b[k] + 0x00090009u, d2 = c[k] + 0x000a000au, e0 = d0 + 0x00280028u;
+                const unsigned hq = __vimin3_s16x2(d0, d1, d2);
+                const unsigned Lq = __vimin3_s16x2(e0, d1, d2 + 0x00280028u);
+                const unsigned Uq = __vimin3_s16x2(e0, d1 + 0x00280028u, d2);
+                seed = seed * 4u + (hq & 0x00030003u);
+                seed = seed * 4u + (Lq & 0x00030003u);
+                seed = seed * 4u + (Uq & 0x00030003u);
+                a[k] = hq & ~0x00030003u; b[k] = Lq & ~0x00030003u; c[k] = Uq & ~0x00030003u;
+            }
+        }
+    }
+    unsigned acc = seed;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= a[k] ^ b[k] ^ c[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+extern "C" int ga_alu_peak(ga_ctx *ctx, int mode, double *gops) {
+    if (!ctx || !gops || mode < 0 || mode > 5) return GA_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    unsigned *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * threads * 4));
+    cudaStream_t st = ctx->stream;
+    auto launch = [&](int it) {
+        switch (mode) {
+            case 0: alu_kernel<0><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+            case 1: alu_kernel<1><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+            case 2: alu_kernel<2><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+            case 3: alu_kernel<3><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+            case 4: alu_kernel<4><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+            default: alu_kernel<5><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+        }
+    };
+    launch(64);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev[6], st));
+        launch(iters);
+        CK(cudaEventRecord(ctx->ev[7], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+        best = std::min(best, ms);
+    }
+    CK(cudaGetLastError());
+    cudaFree(d);
+    const double per_iter = (mode == 5) ? 8.0 * 20.0 : 8.0 * 2.0;   // instructions per thread per iteration
+    *gops = per_iter * iters * (double)blocks * threads / (best * 1e-3) / 1e9;
+    return GA_OK;
+}

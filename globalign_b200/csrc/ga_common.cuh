@@ -1,0 +1,78 @@
+// Shared device-side definitions of the globalign_b200 kernels (sm_100a).
+//
+// Data layout in HBM ("Direction-code layout"):
+//   * sequences: one uint8 letter index per residue, CSR offsets (int64);
+//   * direction codes: for every DP cell three 2-bit codes c0,c1,c2 -- the
+//     first-listed argmin of the three candidates the reference's traceback
+//     ranks at that cell when its successor node is on level 0/1/2
+//     (reference globaligner.py:490-514, tie table :595-685);
+//   * a "tile" is the set of pairs one warp fills together.  The warp's 32
+//     lanes are split into groups of G lanes; each lane owns R consecutive DP
+//     rows; a group sweeps the columns of its pair(s) as an anti-diagonal
+//     wavefront (lane g works on column t-g at step t).  Codes are stored in
+//     that skewed (step, lane) order so that every store instruction of a warp
+//     writes 32 consecutive 128-bit words.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ga {
+
+struct SchemeDev {
+    int A;               // alphabet size (letters 0..A-1)
+    int o;               // gap_open_cost
+    int max_cost;        // largest costing-matrix entry (reference sentinel, globaligner.py:777)
+    int simple;          // 1: sub = (a == b) ? 0 : mm, one gap cost per direction
+    int mm;              // SIMPLE: mismatch cost
+    int gh, gv;          // SIMPLE: horizontal / vertical gap-extension cost
+    const int *sub4;     // TABLE: (A+1)*A ints, 4*cm[a][b]; row A (padding letter) is all zero
+    const int *gh4t;     // TABLE: A ints, 4*cm["-"][b] + 1  (level-1 tag folded in)
+    const int *gv4t;     // TABLE: A+1 ints, 4*cm[a]["-"] + 2 (level-2 tag), entry A = 2
+    const int *gv_raw;   // TABLE: A+1 ints, cm[a]["-"], entry A = 0
+    const int *gh_raw;   // TABLE: A ints
+};
+
+struct TileDesc {
+    long long code_off;  // start of this tile's direction codes, in uint4 units (chunk-relative)
+    int first_pair;      // first pair of the tile
+    int n_pairs;         // pairs in the tile (<= items per warp * pairs per item)
+    int M, N;            // longest seq_1 / seq_2 in the tile
+};
+
+// Compile-time layout of one kernel configuration.
+template <bool PACKED, int R_, int G_>
+struct Lay {
+    static constexpr int R = R_;                       // DP rows per lane
+    static constexpr int G = G_;                       // lanes per group (one item per group)
+    static constexpr int RPW = PACKED ? 8 : 16;        // rows per 32-bit code word (per plane)
+    static constexpr int WPP = (R + RPW - 1) / RPW;    // words per plane per step
+    static constexpr int NW = 3 * WPP;                 // code words per lane per step
+    static constexpr int S = (NW % 4 == 0) ? 1 : ((NW % 2 == 0) ? 2 : 4);  // steps per store block
+    static constexpr int NQ = S * NW / 4;              // 128-bit stores per lane per block
+    static constexpr int IPW = 32 / G;                 // items (lane groups) per warp
+    static constexpr int PPI = PACKED ? 2 : 1;         // pairs per item
+    static constexpr int PPT = IPW * PPI;              // pairs per tile
+    static constexpr int BAND = G * R;                 // DP rows per pass
+};
+
+// Runtime mirror of Lay<> for host-side planning.
+struct LayInfo {
+    int packed, R, G, RPW, WPP, NW, S, NQ, IPW, PPI, PPT, BAND;
+};
+template <bool PACKED, int R, int G>
+inline LayInfo lay_info() {
+    using L = Lay<PACKED, R, G>;
+    return LayInfo{PACKED ? 1 : 0, L::R, L::G, L::RPW, L::WPP, L::NW, L::S, L::NQ, L::IPW,
+                   L::PPI, L::PPT, L::BAND};
+}
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// steps of one pass over a tile whose longest seq_2 has N letters
+__host__ __device__ inline int tile_steps(int N, int G) { return N + G - 1; }
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int PAD_A = 0xFE;   // padding letter for rows past the end of seq_1 (SIMPLE kernels)
+constexpr int PAD_B = 0xFF;   // padding letter for columns past the end of seq_2
+
+}  // namespace ga

@@ -1,0 +1,307 @@
+// K1: batched three-level DP fill + direction-code store (sm_100a).
+//
+// Replaces, for every pair of a batch, the reference's make_dp_array
+// (globaligner.py:756-821), get_next_best_costs (:317-363) and dp_array_forward
+// (:366-392), and produces what dp_array_backward (:395-593) needs instead of
+// the value table: three 2-bit direction codes per cell.
+//
+// One warp fills one tile.  Lanes are split into groups of G; a group owns one
+// item (PACKED: two pairs, one per 16-bit half of every register; otherwise one
+// pair).  Lane g of a group owns DP rows  pass*G*R + g*R + 1 .. + R  and at step
+// t computes column j = t - g + 1 of those rows (anti-diagonal wavefront).  The
+// bottom row of a lane (h = min of the three levels, and U = the level-2
+// candidate for the row below) travels to lane g+1 by warp shuffle; nothing but
+// the letters of seq_2 goes through shared memory.
+//
+// Arithmetic (all integer, exact):  values are kept multiplied by 4; before a
+// three-way minimum the level index (0,1,2) is added in the two low bits, so a
+// single VIMNMX3 returns both the minimum and its first-listed argmin -- ties go
+// to the lowest level, which is the canonical order of the reference's tie
+// table (globaligner.py:599-607).  With D = (d0,d1,d2) the three level values of
+// a cell and o the gap-open cost:
+//     hq = min3(d0, d1|1, d2|2)        -> code c0 (successor on level 0), h
+//     Lq = min3(d0+o, d1|1, (d2|2)+o)  -> code c1 (successor on level 1), L
+//     Uq = min3(d0+o, (d1|1)+o, d2|2)  -> code c2 (successor on level 2), U
+// and the next cells use  d0' = h(diag)+sub, d1' = L(left)+gap_h, d2' = U(up)+gap_v.
+// The boundary row/column use the reference's finite sentinel
+// (max_cost+1)*max(m,n) so every value equals the reference's.
+#pragma once
+#include <type_traits>
+
+#include "ga_common.cuh"
+
+namespace ga {
+
+template <bool PACKED>
+struct VOps;
+
+template <>
+struct VOps<false> {
+    static constexpr unsigned TAGM = 3u;
+    static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
+        return (unsigned)__vimin3_s32((int)a, (int)b, (int)c);
+    }
+    static __device__ __forceinline__ unsigned min2(unsigned a, unsigned b) {
+        return (unsigned)min((int)a, (int)b);
+    }
+    static __device__ __forceinline__ unsigned pk(unsigned lo, unsigned) { return lo; }
+};
+
+template <>
+struct VOps<true> {
+    static constexpr unsigned TAGM = 0x00030003u;
+    static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
+        return __vimin3_s16x2(a, b, c);
+    }
+    static __device__ __forceinline__ unsigned min2(unsigned a, unsigned b) { return __vmins2(a, b); }
+    static __device__ __forceinline__ unsigned pk(unsigned lo, unsigned hi) { return lo | (hi << 16); }
+};
+
+template <bool PACKED, bool SIMPLE, int R, int G>
+__global__ void __launch_bounds__(128)
+fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int n_tiles, int *tile_counter,
+            const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
+            const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
+            uint4 *__restrict__ codes, int2 *bnd, int bnd_stride, int sb_stride,
+            int *__restrict__ out_cost) {
+    using L = Lay<PACKED, R, G>;
+    using V = VOps<PACKED>;
+    using BT = typename std::conditional<PACKED, uint32_t, uint8_t>::type;
+    static_assert(!PACKED || SIMPLE, "the packed 16-bit kernel is for simple schemes");
+    static_assert(G >= 1 && G <= 32 && R >= 1, "bad configuration");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *s_sub = reinterpret_cast<int *>(smem_raw);
+    int *s_gh = s_sub;
+    size_t table_bytes = 0;
+    if (!SIMPLE) {
+        const int n_sub = (sc.A + 1) * sc.A;
+        s_gh = s_sub + n_sub;
+        for (int k = threadIdx.x; k < n_sub; k += blockDim.x) s_sub[k] = sc.sub4[k];
+        for (int k = threadIdx.x; k < sc.A; k += blockDim.x) s_gh[k] = sc.gh4t[k];
+        table_bytes = ((size_t)(n_sub + sc.A) * 4 + 15) & ~(size_t)15;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G;
+    const int g = lane - grp * G;
+    const bool lane_ok = grp < L::IPW;
+    const int my_item = lane_ok ? grp : 0;
+    BT *sb = reinterpret_cast<BT *>(smem_raw + table_bytes) + (size_t)warp * L::IPW * sb_stride;
+    const BT *myb = sb + (size_t)my_item * sb_stride;
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    int2 *my_bnd = bnd + ((size_t)gwarp * L::IPW + my_item) * bnd_stride;
+
+    const unsigned o4 = V::pk(4u * sc.o, 4u * sc.o);
+    const unsigned mm4 = 4u * sc.mm;
+    const unsigned ghTc = V::pk(4u * sc.gh + 1u, 4u * sc.gh + 1u);
+    const unsigned gvTc = V::pk(4u * sc.gv + 2u, 4u * sc.gv + 2u);
+    const unsigned padb = SIMPLE ? (unsigned)PAD_B : 0u;
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= n_tiles) break;
+        const TileDesc td = tiles[tile];
+
+        // ---- the pair(s) of my item
+        const int ia = my_item * L::PPI, ibx = ia + (PACKED ? 1 : 0);
+        const bool haveA = lane_ok && ia < td.n_pairs;
+        const bool haveB = PACKED && lane_ok && ibx < td.n_pairs;
+        const int pA = td.first_pair + min(ia, td.n_pairs - 1);
+        const int pB = td.first_pair + min(ibx, td.n_pairs - 1);
+        const long long a1 = off1[pA], a2 = off2[pA];
+        const int mA = (int)(off1[pA + 1] - a1), nA = (int)(off2[pA + 1] - a2);
+        long long b1 = a1;
+        int mB = mA, nB = nA;
+        if (PACKED) {
+            b1 = off1[pB];
+            mB = (int)(off1[pB + 1] - b1);
+            nB = (int)(off2[pB + 1] - off2[pB]);
+        }
+        const unsigned bigA = (unsigned)(sc.max_cost + 1) * (unsigned)max(mA, nA);
+        const unsigned bigB = (unsigned)(sc.max_cost + 1) * (unsigned)max(mB, nB);
+
+        const int nsteps = td.N + G - 1;
+        const int nTB = (nsteps + L::S - 1) / L::S;
+        const int sb_len = nTB * L::S + 1;
+
+        // ---- stage the seq_2 letters of every item of the tile in shared memory
+        __syncwarp();
+        for (int q = 0; q < L::IPW; ++q) {
+            const int qa = td.first_pair + min(q * L::PPI, td.n_pairs - 1);
+            const int qb = td.first_pair + min(q * L::PPI + (PACKED ? 1 : 0), td.n_pairs - 1);
+            const long long oa = off2[qa], ob = off2[qb];
+            const int na = (int)(off2[qa + 1] - oa), nb = (int)(off2[qb + 1] - ob);
+            BT *row = sb + (size_t)q * sb_stride;
+            for (int c = lane; c < sb_len; c += 32) {
+                const unsigned va = c < na ? (unsigned)s2[oa + c] : padb;
+                if (PACKED) {
+                    const unsigned vb = c < nb ? (unsigned)s2[ob + c] : padb;
+                    row[c] = (BT)(va | (vb << 16));
+                } else {
+                    row[c] = (BT)va;
+                }
+            }
+        }
+        __syncwarp();
+
+        // where the final cell (m, n) of each pair lives
+        const int pmA = (mA - 1) / L::BAND, gmA = ((mA - 1) % L::BAND) / R, rmA = (mA - 1) % R;
+        const int pmB = (mB - 1) / L::BAND, gmB = ((mB - 1) % L::BAND) / R, rmB = (mB - 1) % R;
+        unsigned costA = 0, costB = 0;
+
+        const int npass = (td.M + L::BAND - 1) / L::BAND;
+        int colbase = sc.o;    // TABLE: o + sum of gap_v over the rows of earlier passes
+        for (int p = 0; p < npass; ++p) {
+            const int ib = p * L::BAND + g * R;    // DP row just above my first row
+            unsigned aw[R], gvT[R], hl[R], Lp[R];
+            int colv[R + 1];                       // column-0 value of rows ib .. ib+R (level 2)
+            if (SIMPLE) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = ib + r;
+                    const unsigned la = row < mA ? (unsigned)s1[a1 + row] : (unsigned)PAD_A;
+                    if (PACKED) {
+                        const unsigned lb = row < mB ? (unsigned)s1[b1 + row] : (unsigned)PAD_A;
+                        aw[r] = la | (lb << 16);
+                    } else {
+                        aw[r] = la;
+                    }
+                    gvT[r] = gvTc;
+                }
+#pragma unroll
+                for (int r = 0; r <= R; ++r) colv[r] = sc.o + sc.gv * (ib + r);
+            } else {
+                int mine = 0, gvr[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = ib + r;
+                    const int a = row < mA ? (int)s1[a1 + row] : sc.A;
+                    aw[r] = (unsigned)(a * sc.A);
+                    gvT[r] = (unsigned)sc.gv4t[a];
+                    gvr[r] = sc.gv_raw[a];
+                    mine += gvr[r];
+                }
+                int incl = mine;                   // inclusive scan over the lanes of my group
+#pragma unroll
+                for (int d = 1; d < G; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, d);
+                    if (g >= d) incl += v;
+                }
+                const int band_total = __shfl_sync(FULL, incl, grp * G + G - 1);
+                colv[0] = colbase + incl - mine;
+#pragma unroll
+                for (int r = 0; r < R; ++r) colv[r + 1] = colv[r] + gvr[r];
+                colbase += band_total;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned c = (unsigned)colv[r + 1];
+                hl[r] = V::pk(min(bigA, c), min(bigB, c)) << 2;                // min(D(i,0))
+                Lp[r] = V::pk(min(bigA, c + sc.o), min(bigB, c + sc.o)) << 2;  // level-1 candidate
+            }
+            unsigned rh_prev = 0;                  // h(ib, 0): diagonal input of my first row at j = 1
+            if (ib != 0) rh_prev = V::pk(min(bigA, (unsigned)colv[0]), min(bigB, (unsigned)colv[0])) << 2;
+
+            unsigned hb = 0, ub = 0, bv = 0;
+            int rowj = sc.o;                       // TABLE: running row-0 value (pass 0, lane g == 0)
+            int2 nxt = make_int2(0, 0);
+            if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
+            uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::NQ * 32) + lane;
+
+            for (int tb = 0; tb < nTB; ++tb) {
+                unsigned stg[L::S * L::NW];
+#pragma unroll
+                for (int u = 0; u < L::S; ++u) {
+                    const int t = tb * L::S + u;
+                    const int j = t - g + 1;
+                    unsigned rh = __shfl_up_sync(FULL, hb, 1);
+                    unsigned ru = __shfl_up_sync(FULL, ub, 1);
+                    unsigned bin = __shfl_up_sync(FULL, bv, 1);
+                    const unsigned bnew = (unsigned)myb[t];
+                    if (g == 0) {
+                        bin = bnew;
+                        if (p == 0) {
+                            unsigned rj;           // row-0 value at column t+1 (level 1)
+                            if (SIMPLE) {
+                                rj = (unsigned)(sc.o + sc.gh * (t + 1));
+                            } else {
+                                rowj += sc.gh_raw[bnew];
+                                rj = (unsigned)rowj;
+                            }
+                            rh = V::pk(min(bigA, rj), min(bigB, rj)) << 2;
+                            ru = V::pk(min(bigA, rj + sc.o), min(bigB, rj + sc.o)) << 2;
+                        } else {
+                            rh = (unsigned)nxt.x;
+                            ru = (unsigned)nxt.y;
+                            nxt = __ldcg(my_bnd + min(t + 2, td.N));
+                        }
+                    }
+                    bv = bin;
+#pragma unroll
+                    for (int x = 0; x < L::NW; ++x) stg[u * L::NW + x] = 0u;
+                    if (lane_ok && j >= 1 && j <= td.N) {
+                        unsigned diag = rh_prev, up = ru;
+                        rh_prev = rh;
+                        const unsigned ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
+                        unsigned acc[L::NW];
+#pragma unroll
+                        for (int x = 0; x < L::NW; ++x) acc[x] = 0u;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            unsigned d0;
+                            if (PACKED) {
+                                d0 = __vminu2(aw[r] ^ bv, 0x00010001u) * mm4 + diag;
+                            } else if (SIMPLE) {
+                                d0 = diag + (aw[r] != bv ? mm4 : 0u);
+                            } else {
+                                d0 = diag + (unsigned)s_sub[aw[r] + bv];
+                            }
+                            const unsigned d1 = Lp[r] + ghT;
+                            const unsigned d2 = up + gvT[r];
+                            const unsigned e0 = d0 + o4;
+                            const unsigned hq = V::min3(d0, d1, d2);
+                            const unsigned Lq = V::min3(e0, d1, d2 + o4);
+                            const unsigned Uq = V::min3(e0, d1 + o4, d2);
+                            const int w = r / L::RPW;
+                            acc[w] = acc[w] * 4u + (hq & V::TAGM);
+                            acc[L::WPP + w] = acc[L::WPP + w] * 4u + (Lq & V::TAGM);
+                            acc[2 * L::WPP + w] = acc[2 * L::WPP + w] * 4u + (Uq & V::TAGM);
+                            diag = hl[r];
+                            hl[r] = hq & ~V::TAGM;
+                            Lp[r] = Lq & ~V::TAGM;
+                            up = Uq & ~V::TAGM;
+                        }
+                        hb = hl[R - 1];
+                        ub = up;
+#pragma unroll
+                        for (int x = 0; x < L::NW; ++x) stg[u * L::NW + x] = acc[x];
+                        if (G * R < td.M && g == G - 1 && p + 1 < npass)
+                            __stcg(my_bnd + j, make_int2((int)hb, (int)ub));
+                        if (j == nA && p == pmA && g == gmA) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                if (r == rmA) costA = hl[r];
+                        }
+                        if (PACKED && j == nB && p == pmB && g == gmB) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                if (r == rmB) costB = hl[r];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < L::NQ; ++q)
+                    cbase[(size_t)(tb * L::NQ + q) * 32] =
+                        make_uint4(stg[4 * q], stg[4 * q + 1], stg[4 * q + 2], stg[4 * q + 3]);
+            }
+            __syncwarp();
+        }
+        if (haveA && g == gmA) out_cost[pA] = (int)((PACKED ? (costA & 0xFFFFu) : costA) >> 2);
+        if (haveB && g == gmB) out_cost[pB] = (int)((costB >> 16) >> 2);
+    }
+}
+
+}  // namespace ga

@@ -1,0 +1,121 @@
+// K4: traceback walk over the direction codes (sm_100a).
+//
+// Replaces the reference's dp_array_backward (globaligner.py:395-593),
+// cost_ranks_dispatcher (:595-685, canonical = first listed option) and the four
+// take_* emitters (:688-753).  One thread walks one pair: at cell (i, j) with
+// the successor node on level L it reads the 2-bit code c_L(i, j), emits it as
+// the operation, moves, and sets L to it.  Reaching row 0 / column 0 ends the
+// walk with a run of gap operations (:542-581).  Operations are emitted in walk
+// order, 16 per 32-bit word.
+//
+// The only boundary cell the reference ever *ranks* is the one reached by the
+// very first move when m == 1 or n == 1 (:460 tests just (0,0)); that cell is
+// re-ranked here from its closed-form values with the reference's finite
+// sentinel, and if the reference would not pick the boundary-consistent level
+// (it would then index with -1) the pair is flagged status = 1.
+#pragma once
+#include "ga_common.cuh"
+
+namespace ga {
+
+__device__ __forceinline__ int first_min3(long long v0, long long v1, long long v2) {
+    int k = 0;
+    long long best = v0;
+    if (v1 < best) { best = v1; k = 1; }
+    if (v2 < best) { k = 2; }
+    return k;
+}
+
+template <bool PACKED, int R, int G>
+__global__ void __launch_bounds__(128)
+walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int pair_lo, int n_pairs,
+            const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
+            const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
+            const uint32_t *__restrict__ codes, uint8_t *__restrict__ out_ops,
+            const long long *__restrict__ ops_off, int *__restrict__ out_len,
+            int *__restrict__ out_status) {
+    using L = Lay<PACKED, R, G>;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const int p = pair_lo + k;                 // global pair index
+    const int tile = k / L::PPT;               // tiles hold PPT consecutive pairs of the chunk
+    const int within = k - tile * L::PPT;
+    const int item = within / L::PPI;
+    const int half = within - item * L::PPI;
+    const TileDesc td = tiles[tile];
+    const long long a1 = off1[p], a2 = off2[p];
+    const int m = (int)(off1[p + 1] - a1), n = (int)(off2[p + 1] - a2);
+    const int nsteps = td.N + G - 1;
+    const int nTB = (nsteps + L::S - 1) / L::S;
+    const uint32_t *cw = codes + 4 * td.code_off;
+    const int lane0 = item * G;
+    const int hshift = (PACKED && half) ? 16 : 0;
+
+    uint32_t *ow = reinterpret_cast<uint32_t *>(out_ops + ops_off[p]);
+    uint32_t word = 0;
+    int nops = 0;
+    auto emit = [&](int op) {
+        word |= (uint32_t)op << (2 * (nops & 15));
+        if ((++nops & 15) == 0) { ow[(nops >> 4) - 1] = word; word = 0; }
+    };
+    auto code_at = [&](int i, int j, int level) -> int {
+        const int row = i - 1;
+        const int pass = row / L::BAND;
+        const int rem = row - pass * L::BAND;
+        const int g = rem / R;
+        const int r = rem - g * R;
+        const int t = (j - 1) + g;
+        const int tb = t / L::S, u = t - tb * L::S;
+        const int w = r / L::RPW;
+        const int flat = u * L::NW + level * L::WPP + w;
+        const size_t chunk = ((size_t)pass * nTB + tb) * L::NQ + (flat >> 2);
+        const uint32_t cword = cw[(chunk * 32 + lane0 + g) * 4 + (flat & 3)];
+        const int rows_in_word = min(L::RPW, R - w * L::RPW);
+        const int sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
+        return (int)((cword >> sh) & 3u);
+    };
+
+    int i = m, j = n, level = 0, status = 0;
+    // first move (globaligner.py:425-458)
+    int op = code_at(i, j, level);
+    emit(op);
+    if (op == 0) { --i; --j; } else if (op == 1) { --j; } else { --i; }
+    level = op;
+    if (!(i == 0 && j == 0)) {
+        if (i == 0 || j == 0) {
+            // boundary cell ranked once by the reference (m == 1 or n == 1)
+            const long long big = (long long)(sc.max_cost + 1) * max(m, n);
+            long long v0 = big, v1 = big, v2 = big;
+            int want;
+            if (i == 0) {
+                long long row = sc.o;
+                for (int c = 0; c < j; ++c) row += sc.simple ? sc.gh : sc.gh_raw[s2[a2 + c]];
+                v1 = row;
+                want = 1;
+            } else {
+                long long col = sc.o;
+                for (int c = 0; c < i; ++c) col += sc.simple ? sc.gv : sc.gv_raw[s1[a1 + c]];
+                v2 = col;
+                want = 2;
+            }
+            if (level == 1) { v0 += sc.o; v2 += sc.o; }
+            else if (level == 2) { v0 += sc.o; v1 += sc.o; }
+            if (first_min3(v0, v1, v2) != want) status = 1;
+        }
+        if (status == 0) {
+            while (i > 0 && j > 0) {
+                op = code_at(i, j, level);
+                emit(op);
+                if (op == 0) { --i; --j; } else if (op == 1) { --j; } else { --i; }
+                level = op;
+            }
+            for (; j > 0; --j) emit(1);       // row 0: gaps in seq_1 (:542-561)
+            for (; i > 0; --i) emit(2);       // column 0: gaps in seq_2 (:562-581)
+        }
+    }
+    if (nops & 15) ow[nops >> 4] = word;
+    out_len[p] = nops;
+    out_status[p] = status;
+}
+
+}  // namespace ga

@@ -1,0 +1,157 @@
+"""Drop-in for the reference's ``globalign.globaligner`` on the GPU hot path.
+
+``find_global_alignment`` keeps the reference's name, its 13 keyword arguments,
+defaults, exceptions and return type (globaligner.py:132-314).  What changes is
+the seam at :256-293: instead of make_dp_array -> dp_array_forward ->
+dp_array_backward over a Python list of tuples, the pair goes through the C-ABI
+(``ga_align_batch``) to the sm_100a kernels.  The three seam functions are also
+exported with the reference's signatures for callers/tests that use them
+directly; they run on the GPU as well (``ga_fill_values`` / ``ga_align_batch``).
+There is no CPU implementation in this package.
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+from . import _native
+from .batch import ReferenceUndefinedError, render
+from .conclude import AlignmentResults, final_cost_to_score
+from .lowering import DenseScheme
+from .start import get_max_val, make_matrix, validate_and_transform_args
+
+__all__ = ["find_global_alignment", "make_dp_array", "dp_array_forward", "dp_array_backward", "main"]
+
+
+def _align_one(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: int, device: int = 0):
+    dense = DenseScheme(costing_mat, gap_open_cost)
+    ctx = _native.default_context(device)
+    ctx.set_scheme(dense)
+    s1, s2 = dense.encode(seq_1), dense.encode(seq_2)
+    m, n = len(s1), len(s2)
+    cost, ops, ops_off, ops_len, status = ctx.align_batch(
+        s1, np.array([0, m], dtype=np.int64), s2, np.array([0, n], dtype=np.int64))
+    if status[0] != 0:
+        raise ReferenceUndefinedError(
+            "the reference's traceback leaves the DP table for this input "
+            "(max(len(seq_1), len(seq_2)) <= gap_open_cost): it raises IndexError or wraps "
+            "to negative indices there")
+    return _native.unpack_ops(ops, 0, int(ops_len[0])), int(cost[0])
+
+
+def find_global_alignment(
+    input_fasta: str | Path = None,
+    output: str | Path = None,
+    seq_1: str = None,
+    seq_2: str = None,
+    scoring_mat_name: str = None,
+    scoring_mat_path: str | Path = None,
+    match_score: str | int = None,
+    mismatch_score: str | int = None,
+    mismatch_cost: str | int = None,
+    gap_open_score: str | int = None,
+    gap_open_cost: str | int = None,
+    gap_extension_score: str | int = None,
+    gap_extension_cost: str | int = None,
+) -> AlignmentResults:
+    """Optimal global alignment of two sequences (affine gaps, three-level DP).
+
+    Arguments, defaults and errors are those of the reference
+    (globaligner.py:147-215); ties between co-optimal alignments are broken in
+    the reference's canonical order (match/mismatch, then gap in seq_1, then gap
+    in seq_2).
+    """
+    (seq_1, seq_2, scoring_mat, costing_mat, gap_open_score, gap_open_cost,
+     output) = validate_and_transform_args(
+        input_fasta, output, seq_1, seq_2, scoring_mat_name, scoring_mat_path, match_score,
+        mismatch_score, mismatch_cost, gap_open_score, gap_open_cost, gap_extension_score,
+        gap_extension_cost)
+    ops, cost = _align_one(seq_1, seq_2, costing_mat, gap_open_cost)
+    seq_1_aligned, middle_part, seq_2_aligned = render(ops, seq_1, seq_2)
+    score = final_cost_to_score(cost=cost, m=len(seq_1), n=len(seq_2),
+                                max_score=get_max_val(scoring_mat))
+    return AlignmentResults(seq_1_aligned, middle_part, seq_2_aligned, cost, score, scoring_mat,
+                            costing_mat, gap_open_score, gap_open_cost, output)
+
+
+# ---------------------------------------------------------------------------
+# the seam functions, reference signatures (globaligner.py:756, :366, :395)
+# ---------------------------------------------------------------------------
+def make_dp_array(seq_1: str, seq_2: str, costing_mat: dict, max_cost: int, gap_open_cost: int):
+    """(m+1) x (n+1) nested list, boundary row/column set, interior ``None``."""
+    m, n = len(seq_1), len(seq_2)
+    dp = make_matrix(num_rows=m + 1, num_cols=n + 1, fill_val=None)
+    big = (max_cost + 1) * max(m, n)
+    dp[0][0] = (0, 0, 0)
+    run = gap_open_cost
+    for j in range(1, n + 1):
+        run += costing_mat["-"][seq_2[j - 1]]
+        dp[0][j] = (big, run, big)
+    if n == 0:
+        return dp
+    run = gap_open_cost
+    for i in range(1, m + 1):
+        run += costing_mat[seq_1[i - 1]]["-"]
+        dp[i][0] = (big, big, run)
+    return dp
+
+
+def dp_array_forward(dp_array, seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost):
+    """Fill ``dp_array`` in place on the GPU, starting from the boundary row and
+    column already present in it (as the reference's own test does)."""
+    dense = DenseScheme(costing_mat, gap_open_cost)
+    ctx = _native.default_context(0)
+    ctx.set_scheme(dense)
+    m, n = len(seq_1), len(seq_2)
+    table = np.zeros((m + 1, n + 1, 3), dtype=np.int32)
+    for j in range(n + 1):
+        table[0, j] = dp_array[0][j]
+    for i in range(m + 1):
+        table[i, 0] = dp_array[i][0]
+    ctx.fill_values(dense.encode(seq_1), dense.encode(seq_2), table, keep_boundary=True)
+    for i in range(1, m + 1):
+        row = dp_array[i]
+        for j in range(1, n + 1):
+            row[j] = tuple(int(v) for v in table[i, j])
+    return None
+
+
+def dp_array_backward(dp_array, seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: int):
+    """-> (seq_1_aligned, middle_part, seq_2_aligned, cost).  The walk runs on the
+    GPU over direction codes recomputed from the sequences; ``dp_array`` is only
+    consulted for its corner value (the cost), exactly what a table filled by
+    ``dp_array_forward`` from ``make_dp_array`` holds."""
+    ops, cost = _align_one(seq_1, seq_2, costing_mat, gap_open_cost)
+    if dp_array is not None and dp_array[len(seq_1)][len(seq_2)] is not None:
+        if min(dp_array[len(seq_1)][len(seq_2)]) != cost:
+            raise RuntimeError("dp_array was not produced by make_dp_array + dp_array_forward "
+                               "for these sequences and costs")
+    top, mid, bot = render(ops, seq_1, seq_2)
+    return top, mid, bot, cost
+
+
+def main(argv=None):
+    """Command line with the reference's flags (globaligner.py:23-129)."""
+    import argparse
+
+    p = argparse.ArgumentParser(
+        description="Perform optimal global alignment of two nucleotide or amino acid sequences.")
+    p.add_argument("-i", "--input_fasta", required=False)
+    p.add_argument("-o", "--output", required=False)
+    p.add_argument("--seq_1", required=False)
+    p.add_argument("--seq_2", required=False)
+    p.add_argument("--scoring_mat_name", required=False, choices=["BLOSUM50", "BLOSUM62"])
+    p.add_argument("--scoring_mat_path", required=False)
+    for name in ("match_score", "mismatch_score", "mismatch_cost", "gap_open_score", "gap_open_cost",
+                 "gap_extension_score", "gap_extension_cost"):
+        p.add_argument(f"--{name}", required=False)
+    args = p.parse_args(argv)
+    find_global_alignment(**vars(args)).write()
+    return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

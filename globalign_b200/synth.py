@@ -86,16 +86,18 @@ def _mutate_fixed(rng, s1: np.ndarray, n_letters: int, p_sub: float, p_ins: floa
 _BLOCK = 4096      # pairs per independently seeded block (keeps prefixes stable)
 
 
-def dna_fixed(n_pairs: int, length: int, seed: int, p_sub=0.08, p_ins=0.01, p_del=0.01) -> PairBatch:
+def dna_fixed(n_pairs: int, length: int, seed: int, p_sub=0.08, p_ins=0.01, p_del=0.01,
+              first_block: int = 0) -> PairBatch:
     """Configs 2 and 5: `n_pairs` DNA pairs, both of exactly `length` letters.
 
     Pairs are drawn in blocks of 4096 from ``default_rng([seed, block])`` so the
-    first k pairs do not depend on n_pairs (CPU samples are prefixes)."""
+    first k pairs do not depend on n_pairs (CPU samples are prefixes).  `first_block`
+    skips that many blocks: rank r of a sharded run generates only its own shard."""
     s1 = np.empty((n_pairs, length), dtype=np.uint8)
     s2 = np.empty((n_pairs, length), dtype=np.uint8)
     for blk, lo in enumerate(range(0, n_pairs, _BLOCK)):
         hi = min(n_pairs, lo + _BLOCK)
-        rng = np.random.default_rng([seed, blk])
+        rng = np.random.default_rng([seed, first_block + blk])
         a = rng.integers(0, 4, size=(_BLOCK, length), dtype=np.uint8)
         b = _mutate_fixed(rng, a, 4, p_sub, p_ins, p_del)
         s1[lo:hi] = a[: hi - lo]
@@ -175,17 +177,17 @@ def concat(parts: list[PairBatch]) -> PairBatch:
 
 #: name -> (builder, human description).  Sizes are the BASELINE.json ones;
 #: every builder accepts n_pairs / length overrides for bounded samples.
-def workload(name: str, n_pairs: int | None = None) -> PairBatch:
+def workload(name: str, n_pairs: int | None = None, first_block: int = 0) -> PairBatch:
     if name == "cfg1":
         return dna_single(1000, 1001, 1002)
     if name == "cfg2":
-        return dna_fixed(n_pairs or 1_000_000, 150, 2000)
+        return dna_fixed(n_pairs or 1_000_000, 150, 2000, first_block=first_block)
     if name == "cfg3":
         return protein_varlen(n_pairs or 100_000, 3000)
     if name == "cfg4":
         return dna_single(100_000, 4001, 4002)
     if name == "cfg5":
-        return dna_fixed(n_pairs or 10_000_000, 250, 5000)
+        return dna_fixed(n_pairs or 10_000_000, 250, 5000, first_block=first_block)
     raise ValueError(f"unknown workload {name!r}")
 
 

@@ -28,8 +28,9 @@
  *     column first, as dp_array_backward produces them before its final
  *     reverse): 0 = match/mismatch column, 1 = gap in seq_1, 2 = gap in seq_2.
  *     Four ops per byte, op k of a pair in bits 2*(k%4) of byte k/4 of that
- *     pair's slice.  Pair p's slice starts at byte ops_off[p] and must hold
- *     ceil((m_p+n_p)/4) bytes rounded up to a multiple of 4.
+ *     pair's slice.  ops_off has n_pairs+1 entries (multiples of 4); pair p's slice is
+ *     [ops_off[p], ops_off[p+1]) and must hold ceil((m_p+n_p)/4) bytes rounded up to a
+ *     multiple of 4.
  *   - Ties are broken in the reference's canonical order (first option listed
  *     in cost_ranks_dispatcher: level 0, then 1, then 2).
  *   - status[p]: 0 ok; 1 = the reference's walk would leave the table for this

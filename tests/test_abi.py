@@ -1,0 +1,54 @@
+"""The C-ABI shared library: builds for sm_100a, loads on a CPU-only box, exports every symbol
+include/globalign_b200.h declares, and fails loudly without a GPU (no CPU fallback)."""
+import re
+from pathlib import Path
+
+import pytest
+
+import __graft_entry__ as entry
+from globalign_b200 import _native
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def built():
+    entry.build()
+    return _native.lib()
+
+
+def test_header_symbols_are_exported(built):
+    header = (ROOT / "include" / "globalign_b200.h").read_text()
+    declared = set(re.findall(r"\b(ga_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(built, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.EXPORTS)
+    assert built.ga_version() >= 100
+
+
+def test_library_is_sm100a_only(built):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback():
+    import ctypes as C
+    n = C.c_int(0)
+    _native.lib().ga_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.NativeLibraryError):
+        _native.Context(0)
+    from globalign_b200.globaligner import find_global_alignment
+    with pytest.raises(_native.NativeLibraryError):
+        find_global_alignment(seq_1="ACGT", seq_2="AGT")
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "globalign_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p
+    for p in (ROOT / "globalign_b200" / "csrc").glob("*"):
+        assert "oracle" not in p.read_text().lower() or p.name == "Makefile", p

