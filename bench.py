@@ -43,7 +43,7 @@ from globalign_b200 import synth  # noqa: E402
 METRIC = "GCUPS w/ traceback"
 UNIT = "GCUPS"
 OPS_PER_CELL = 24          # SURVEY.md 8d contract figure: int32 ops per cell, fill with codes
-CODE_BYTES_PER_CELL = 0.75  # 3 x 2 bit
+CODE_BYTES_PER_CELL = 0.5   # 2 bits (level-0 argmin) + 1 + 1 (gap-level take bits), DESIGN.md
 NOMINAL_INT32_TOPS = 148 * 64 * 1.965e9 / 1e12     # 18.6 Tops/s
 
 DESCR = {
@@ -57,8 +57,8 @@ DEFAULT_PAIRS = {"cfg2": 1_000_000, "cfg3": 100_000, "cfg5": 10_000_000}
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(DESCR))
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: the BASELINE size)")
@@ -98,24 +98,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t_lo: float, t_hi: float) -> dict:
+        """Median SM clock / active throttle reasons of the samples taken in [t_lo, t_hi]
+        (the timed region); if the region was shorter than the sampling period, of the
+        samples taken while the GPU was busy just before it (warm-up)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        good = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        win = [r for t, r in good if t_lo <= t <= t_hi + 0.05]
+        scope = "timed region"
+        if not win:
+            win = [r for t, r in good if t_lo - 1.0 <= t <= t_hi + 0.2]
+            scope = "timed region +-1 s"
+        sm = [float(r[1]) for r in win]
+        mx = [float(r[2]) for r in win]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4)
-                          if r[4 + k].lower().startswith("active")})
+        reasons = sorted({names[k] for r in win for k in range(4) if r[4 + k].lower().startswith("active")})
+        pw = [float(r[3]) for r in win if r[3].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "scope": scope,
+                "reasons": reasons}
 
 
 def oracle_dense(dense):
@@ -229,7 +239,10 @@ def run_ours(args, rank, world, local_rank):
 
     ctx = _native.Context(local_rank)
     ctx.set_scheme(dense)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) torch stream: the library launches on it and the
+    # torch.cuda.Event pair below brackets exactly those launches
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ops_off_h = _native.ops_offsets(batch.off1, batch.off2)
 
@@ -256,32 +269,36 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.3)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fill_ms, walk_ms = [], []
     barrier()
+    t_lo = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    t_hi = time.perf_counter()
+    clocks = sampler.stop(t_lo, t_hi)
     dev_ms = ev0.elapsed_time(ev1)
-    # per-kernel durations (library CUDA events on the same stream) of the last timed step
-    t = ctx.timing()
-    fill_ms.append(t["fill"])
-    walk_ms.append(t["walk"])
-    # a few separately timed steps for the per-kernel average
-    for _ in range(min(3, args.steps)):
+    wall_ms = (t_hi - t_lo) * 1e3
+    dev_cost = d_cost.cpu().numpy()
+    # Per-kernel durations for the roofline: the same work planned with GA_F_SERIAL (one
+    # stream, no fill/walk overlap), library CUDA events on the launching stream.
+    info_serial = ctx.plan_batch(batch.off1, batch.off2, ops_off_h, flags=_native.GA_F_SERIAL)
+    for k in range(2 + min(5, args.steps)):
         step_device()
         t = ctx.timing()
-        fill_ms.append(t["fill"])
-        walk_ms.append(t["walk"])
-    dev_cost = d_cost.cpu().numpy()
+        if k >= 2:
+            fill_ms.append(t["fill"])
+            walk_ms.append(t["walk"])
+    assert np.array_equal(d_cost.cpu().numpy(), dev_cost), "serial and pipelined plans disagree"
 
     # ---- end to end through the host-buffer call, pinned host memory
     def pinned(a):
@@ -347,8 +364,10 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": DESCR[name], "pairs_per_gpu": n, "cells_per_gpu": cells,
                    "l2": "inputs + direction codes (%.1f GB per step) are far larger than the 126 MB L2"
                          % (info["code_bytes"] / 1e9),
-                   "fill_kernel": info["fill_kernel"], "chunks": info["n_chunks"]},
-        "clocks": clocks,
+                   "fill_kernel": info["fill_kernel"], "chunks": info["n_chunks"],
+                   "pipeline": "walk of chunk c overlaps fill of chunk c+1 (2 fill + 2 walk streams); "
+                               "kernels_ms / roofline are from a serial (non-overlapped) plan"},
+        "clocks": clocks, "wall_ms_timed_region": wall_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms,
                 "phases_ms": {k: round(v, 3) for k, v in e2e_phase.items()}},

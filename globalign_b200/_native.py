@@ -19,6 +19,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libglobalign_b200.so"
 GA_F_DEFAULT = 0
 GA_F_FORCE_GENERIC = 1
 GA_F_COST_ONLY = 2
+GA_F_SERIAL = 4
 T_H2D, T_FILL, T_WALK, T_D2H, T_TOTAL, T_COUNT = 0, 1, 2, 3, 4, 5
 
 #: every symbol include/globalign_b200.h declares (checked by the CPU tests)

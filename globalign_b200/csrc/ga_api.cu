@@ -97,6 +97,11 @@ struct Chunk {
     long long code_u4;        // uint4 words of direction codes
 };
 
+// events of one chunk of the pipeline
+struct ChunkEvents {
+    cudaEvent_t in0, in1, f0, f1, w0, w1, out0, out1;
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -105,6 +110,9 @@ struct DevBuf {
 struct ga_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // pipeline streams: two fill streams (alternating chunks, so the tail of one chunk
+    // overlaps the start of the next), two walk streams, copy-in and copy-out
+    cudaStream_t aux[6] = {};
     std::string err;
     int64_t scratch_limit = (int64_t)64 << 30;
     int sm_count = 0;
@@ -123,14 +131,15 @@ struct ga_ctx {
     size_t smem = 0;
     int64_t cells = 0, code_bytes = 0;
     uint32_t plan_flags = 0;
-    DevBuf d_tiles, d_codes, d_bnd, d_counter;
+    bool serial = false;
+    DevBuf d_tiles, d_codes[2], d_bnd[2], d_counter;
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
     // timing
     cudaEvent_t ev[8] = {};
-    std::vector<cudaEvent_t> seg;      // per chunk: fill-end, walk-end
+    std::vector<ChunkEvents> cev;
     float ms[GA_T_COUNT] = {};
-    bool timing_valid = false;
+    bool timing_valid = false, timing_io = false;
 };
 
 static int fail(ga_ctx *c, int code, const char *fmt, ...) {
@@ -185,6 +194,7 @@ extern "C" int ga_ctx_create(int device, ga_ctx **out) {
         return GA_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     *out = ctx;
@@ -196,12 +206,15 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->d_sub4, &ctx->d_gh4t, &ctx->d_gv4t, &ctx->d_gvraw, &ctx->d_ghraw,
-                      &ctx->d_tiles, &ctx->d_codes, &ctx->d_bnd, &ctx->d_counter, &ctx->d_s1,
+                      &ctx->d_tiles, &ctx->d_codes[0], &ctx->d_codes[1], &ctx->d_bnd[0], &ctx->d_bnd[1],
+                      &ctx->d_counter, &ctx->d_s1,
                       &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
                       &ctx->d_opsoff, &ctx->d_len, &ctx->d_status})
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
-    for (auto &e : ctx->seg) cudaEventDestroy(e);
+    for (auto &c : ctx->cev)
+        for (cudaEvent_t e : {c.in0, c.in1, c.f0, c.f1, c.w0, c.w1, c.out0, c.out1}) cudaEventDestroy(e);
+    for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return GA_OK;
@@ -291,6 +304,9 @@ extern "C" int ga_set_scheme(ga_ctx *ctx, int A, const int32_t *sub, const int32
     sc.gv4t = (const int *)ctx->d_gv4t.p;
     sc.gv_raw = (const int *)ctx->d_gvraw.p;
     sc.gh_raw = (const int *)ctx->d_ghraw.p;
+    sc.k_one = 1u;
+    sc.k_four = 4u;
+    sc.k_minus_one = 0xffffffffu;
     ctx->uniform_gaps = uniform;
     ctx->have_scheme = true;
     ctx->have_plan = false;
@@ -315,7 +331,9 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
     }
     if (sc.simple) {
         if (!(flags & GA_F_FORCE_GENERIC)) {
-            const char *pick = maxM <= 160 ? "fill_p16_r10_g16"
+            // measured on B200 (tools/tune_cfgs.py): r19_g8 > r15_g10 > r10_g16 for 150-row reads
+            const char *pick = maxM <= 152 ? "fill_p16_r19_g8"
+                               : maxM <= 160 ? "fill_p16_r10_g16"
                                : maxM <= 256 ? "fill_p16_r16_g16" : "fill_p16_r16_g32";
             const KernelCfg *c = find_cfg(pick);
             if (fits16(c)) return c;
@@ -365,9 +383,8 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     const int64_t n_tiles = (n_pairs + L.PPT - 1) / L.PPT;
     ctx->tiles.resize((size_t)n_tiles);
     ctx->chunks.clear();
-    const long long limit_u4 = std::max<long long>(ctx->scratch_limit / 16, 1);
-    Chunk cur{0, 0, 0, 0, 0};
-    long long max_chunk_u4 = 0, total_u4 = 0;
+    std::vector<long long> tile_u4((size_t)n_tiles);
+    long long total_u4 = 0, biggest = 0;
     for (int64_t t = 0; t < n_tiles; ++t) {
         TileDesc &td = ctx->tiles[(size_t)t];
         const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
@@ -378,22 +395,40 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
         }
         const long long npass = (M + L.BAND - 1) / L.BAND;
         const long long nTB = (N + L.G - 1 + L.S - 1) / L.S;
-        const long long u4 = npass * nTB * L.NQ * 32;
-        if (u4 > limit_u4) return fail(ctx, GA_E_NOMEM, "one tile needs %lld bytes of direction codes, above the scratch limit", u4 * 16);
-        if (cur.code_u4 + u4 > limit_u4) {
-            cur.tile_hi = (int)t;
-            cur.pair_hi = (int)lo;
-            ctx->chunks.push_back(cur);
-            max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
-            cur = Chunk{(int)t, 0, (int)lo, 0, 0};
-        }
-        td.code_off = cur.code_u4;
+        tile_u4[(size_t)t] = npass * nTB * L.NQ * 32;
+        total_u4 += tile_u4[(size_t)t];
+        biggest = std::max(biggest, tile_u4[(size_t)t]);
         td.first_pair = (int)lo;
         td.n_pairs = (int)(hi - lo);
         td.M = M;
         td.N = N;
+    }
+    // Chunks: the direction codes of a chunk live in one of two scratch buffers, so
+    // the walk of chunk c overlaps the fill of chunk c+1.  Large batches are cut into
+    // ~4 chunks (more if the scratch limit requires); GA_F_SERIAL keeps one stream
+    // and as few chunks as the limit allows.
+    const bool serial = (flags & GA_F_SERIAL) != 0;
+    const long long hard_u4 = std::max<long long>((serial ? ctx->scratch_limit : ctx->scratch_limit / 2) / 16, 1);
+    if (biggest > hard_u4)
+        return fail(ctx, GA_E_NOMEM, "one tile needs %lld bytes of direction codes, above the scratch limit", biggest * 16);
+    long long limit_u4 = hard_u4;
+    if (!serial) {
+        const long long min_u4 = ((long long)1 << 30) / 16;            // do not cut below 1 GiB of codes
+        limit_u4 = std::min(hard_u4, std::max(min_u4, (total_u4 + 3) / 4));
+    }
+    Chunk cur{0, 0, 0, 0, 0};
+    long long max_chunk_u4 = 0;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const long long u4 = tile_u4[(size_t)t];
+        if (cur.code_u4 + u4 > limit_u4 && cur.code_u4 > 0) {
+            cur.tile_hi = (int)t;
+            cur.pair_hi = (int)(t * L.PPT);
+            ctx->chunks.push_back(cur);
+            max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
+            cur = Chunk{(int)t, 0, (int)(t * L.PPT), 0, 0};
+        }
+        ctx->tiles[(size_t)t].code_off = cur.code_u4;
         cur.code_u4 += u4;
-        total_u4 += u4;
     }
     cur.tile_hi = (int)n_tiles;
     cur.pair_hi = (int)n_pairs;
@@ -417,23 +452,26 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     ctx->grid = (int)std::min<long long>(want_blocks, (long long)per_sm * ctx->sm_count);
     int rc;
     if ((rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
-    if ((rc = ensure(ctx, ctx->d_codes, (size_t)max_chunk_u4 * 16))) return rc;
-    if ((rc = ensure(ctx, ctx->d_bnd, (size_t)ctx->grid * warps * L.IPW * ctx->bnd_stride * sizeof(int2)))) return rc;
-    if ((rc = ensure(ctx, ctx->d_counter, 256))) return rc;
+    const int n_bufs = (serial || ctx->chunks.size() == 1) ? 1 : 2;
+    for (int b = 0; b < n_bufs; ++b) {
+        if ((rc = ensure(ctx, ctx->d_codes[b], (size_t)max_chunk_u4 * 16))) return rc;
+        if ((rc = ensure(ctx, ctx->d_bnd[b], (size_t)ctx->grid * warps * L.IPW * ctx->bnd_stride * sizeof(int2)))) return rc;
+    }
+    if ((rc = ensure(ctx, ctx->d_counter, ctx->chunks.size() * sizeof(int) + 256))) return rc;
     CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->tiles.data(), (size_t)n_tiles * sizeof(TileDesc),
                        cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));      // ctx->tiles may be re-planned by the caller
-    // timing events: 2 per chunk
-    while (ctx->seg.size() < 2 * ctx->chunks.size()) {
-        cudaEvent_t e;
-        CK(cudaEventCreate(&e));
-        ctx->seg.push_back(e);
+    while (ctx->cev.size() < ctx->chunks.size()) {
+        ChunkEvents c;
+        for (cudaEvent_t *e : {&c.in0, &c.in1, &c.f0, &c.f1, &c.w0, &c.w1, &c.out0, &c.out1}) CK(cudaEventCreate(e));
+        ctx->cev.push_back(c);
     }
     ctx->cfg = cfg;
     ctx->n_pairs = n_pairs;
     ctx->cells = cells;
     ctx->code_bytes = total_u4 * 16;
     ctx->plan_flags = flags;
+    ctx->serial = serial;
     ctx->have_plan = true;
     return GA_OK;
 }
@@ -452,6 +490,93 @@ extern "C" int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info) {
     return GA_OK;
 }
 
+// Host buffers of the host-buffer entry point (null for ga_run_batch).
+struct HostIO {
+    const uint8_t *s1 = nullptr, *s2 = nullptr;
+    const int64_t *off1 = nullptr, *off2 = nullptr, *ops_off = nullptr;
+    int32_t *cost = nullptr, *len = nullptr, *status = nullptr;
+    uint8_t *ops = nullptr;
+};
+
+// The chunk pipeline.  For chunk c (buffers / streams chosen by c & 1):
+//   copy-in (host entry only)  ->  fill  ->  walk  ->  copy-out (host entry only)
+// fill(c) waits for walk(c-2) (it reuses that chunk's code buffer); everything is
+// bracketed by ev[0] / ev[1] on the caller-visible stream, which finally waits for
+// all auxiliary streams.
+static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_off, const uint8_t *d_s2,
+                        const int64_t *d_s2_off, int32_t *d_cost, uint8_t *d_ops, const int64_t *d_ops_off,
+                        int32_t *d_len, int32_t *d_status, const HostIO *io) {
+    const KernelCfg *cfg = ctx->cfg;
+    const bool cost_only = (ctx->plan_flags & GA_F_COST_ONLY) != 0;
+    const bool serial = ctx->serial || ctx->chunks.size() == 1;
+    cudaStream_t main = ctx->stream;
+    const size_t nc = ctx->chunks.size();
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, nc * sizeof(int), main));
+    CK(cudaEventRecord(ctx->ev[0], main));
+    if (!serial || io)
+        for (auto &a : ctx->aux) CK(cudaStreamWaitEvent(a, ctx->ev[0], 0));
+    for (size_t c = 0; c < nc; ++c) {
+        const Chunk &ch = ctx->chunks[c];
+        ChunkEvents &E = ctx->cev[c];
+        const int b = serial ? 0 : (int)(c & 1);
+        cudaStream_t sF = serial ? main : ctx->aux[b], sW = serial ? main : ctx->aux[2 + b];
+        cudaStream_t sIn = ctx->aux[4], sOut = ctx->aux[5];
+        const int n_tiles = ch.tile_hi - ch.tile_lo, np = ch.pair_hi - ch.pair_lo;
+        if (io) {   // this chunk's letters (offset arrays were uploaded up front)
+            const int64_t a0 = io->off1[ch.pair_lo], a1 = io->off1[ch.pair_hi];
+            const int64_t b0 = io->off2[ch.pair_lo], b1 = io->off2[ch.pair_hi];
+            CK(cudaEventRecord(E.in0, sIn));
+            CK(cudaMemcpyAsync((uint8_t *)d_s1 + a0, io->s1 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, sIn));
+            CK(cudaMemcpyAsync((uint8_t *)d_s2 + b0, io->s2 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sIn));
+            CK(cudaEventRecord(E.in1, sIn));
+            CK(cudaStreamWaitEvent(sF, E.in1, 0));
+        }
+        if (!serial && c >= 2) CK(cudaStreamWaitEvent(sF, ctx->cev[c - 2].w1, 0));   // code buffer free
+        CK(cudaEventRecord(E.f0, sF));
+        const int grid = std::min(ctx->grid, (n_tiles + 3) / 4);
+        cfg->launch_fill(grid, ctx->smem, sF, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo,
+                         n_tiles, (int *)ctx->d_counter.p + c, d_s1, (const long long *)d_s1_off, d_s2,
+                         (const long long *)d_s2_off, (uint4 *)ctx->d_codes[b].p, (int2 *)ctx->d_bnd[b].p,
+                         ctx->bnd_stride, ctx->sb_stride, d_cost);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(E.f1, sF));
+        if (sW != sF) CK(cudaStreamWaitEvent(sW, E.f1, 0));
+        CK(cudaEventRecord(E.w0, sW));
+        if (!cost_only) {
+            cfg->launch_walk(sW, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo, ch.pair_lo, np,
+                             d_s1, (const long long *)d_s1_off, d_s2, (const long long *)d_s2_off,
+                             (const uint32_t *)ctx->d_codes[b].p, d_ops, (const long long *)d_ops_off,
+                             d_len, d_status);
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(E.w1, sW));
+        if (io) {
+            CK(cudaStreamWaitEvent(sOut, E.w1, 0));
+            CK(cudaEventRecord(E.out0, sOut));
+            CK(cudaMemcpyAsync(io->cost + ch.pair_lo, d_cost + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
+            if (!cost_only) {
+                const int64_t o0 = io->ops_off[ch.pair_lo], o1 = io->ops_off[ch.pair_hi];
+                CK(cudaMemcpyAsync(io->ops + o0, d_ops + o0, (size_t)(o1 - o0), cudaMemcpyDeviceToHost, sOut));
+                CK(cudaMemcpyAsync(io->len + ch.pair_lo, d_len + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
+                CK(cudaMemcpyAsync(io->status + ch.pair_lo, d_status + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
+            }
+            CK(cudaEventRecord(E.out1, sOut));
+        }
+    }
+    // join: the caller-visible stream waits for the tails of every auxiliary stream
+    if (!serial || io) {
+        for (size_t c = (nc >= 2 ? nc - 2 : 0); c < nc; ++c) {
+            CK(cudaStreamWaitEvent(main, ctx->cev[c].w1, 0));
+            if (io) CK(cudaStreamWaitEvent(main, ctx->cev[c].out1, 0));
+        }
+        if (io && nc > 2) CK(cudaStreamWaitEvent(main, ctx->cev[nc - 1].out1, 0));
+    }
+    CK(cudaEventRecord(ctx->ev[1], main));
+    ctx->timing_valid = true;
+    ctx->timing_io = io != nullptr;
+    return GA_OK;
+}
+
 extern "C" int ga_run_batch(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_off,
                             const uint8_t *d_s2, const int64_t *d_s2_off, int32_t *d_out_cost,
                             uint8_t *d_out_ops, const int64_t *d_out_ops_off, int32_t *d_out_ops_len,
@@ -463,32 +588,8 @@ extern "C" int ga_run_batch(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s
         (!cost_only && (!d_out_ops || !d_out_ops_off || !d_out_ops_len || !d_out_status)))
         return fail(ctx, GA_E_ARG, "null device buffer");
     CK(cudaSetDevice(ctx->device));
-    const KernelCfg *cfg = ctx->cfg;
-    cudaStream_t st = ctx->stream;
-    CK(cudaEventRecord(ctx->ev[0], st));
-    for (size_t c = 0; c < ctx->chunks.size(); ++c) {
-        const Chunk &ch = ctx->chunks[c];
-        const int n_tiles = ch.tile_hi - ch.tile_lo;
-        CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), st));
-        const int grid = std::min(ctx->grid, (n_tiles + 3) / 4);
-        cfg->launch_fill(grid, ctx->smem, st, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo,
-                         n_tiles, (int *)ctx->d_counter.p, d_s1, (const long long *)d_s1_off, d_s2,
-                         (const long long *)d_s2_off, (uint4 *)ctx->d_codes.p, (int2 *)ctx->d_bnd.p,
-                         ctx->bnd_stride, ctx->sb_stride, d_out_cost);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->seg[2 * c], st));
-        if (!cost_only) {
-            cfg->launch_walk(st, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo, ch.pair_lo,
-                             ch.pair_hi - ch.pair_lo, d_s1, (const long long *)d_s1_off, d_s2,
-                             (const long long *)d_s2_off, (const uint32_t *)ctx->d_codes.p, d_out_ops,
-                             (const long long *)d_out_ops_off, d_out_ops_len, d_out_status);
-            CK(cudaGetLastError());
-        }
-        CK(cudaEventRecord(ctx->seg[2 * c + 1], st));
-    }
-    CK(cudaEventRecord(ctx->ev[1], st));
-    ctx->timing_valid = true;
-    return GA_OK;
+    return run_pipeline(ctx, d_s1, d_s1_off, d_s2, d_s2_off, d_out_cost, d_out_ops, d_out_ops_off,
+                        d_out_ops_len, d_out_status, nullptr);
 }
 
 extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
@@ -496,21 +597,28 @@ extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
     if (!ctx->timing_valid || !ctx->have_plan) return fail(ctx, GA_E_STATE, "nothing has run yet");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    float fill = 0, walk = 0, total = 0;
-    cudaEvent_t prev = ctx->ev[0];
+    float fill = 0, walk = 0, h2d = 0, d2h = 0, total = 0;
     for (size_t c = 0; c < ctx->chunks.size(); ++c) {
-        float a = 0, b = 0;
-        CK(cudaEventElapsedTime(&a, prev, ctx->seg[2 * c]));
-        CK(cudaEventElapsedTime(&b, ctx->seg[2 * c], ctx->seg[2 * c + 1]));
-        fill += a;
-        walk += b;
-        prev = ctx->seg[2 * c + 1];
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ctx->cev[c].f0, ctx->cev[c].f1));
+        fill += t;
+        CK(cudaEventElapsedTime(&t, ctx->cev[c].w0, ctx->cev[c].w1));
+        walk += t;
+        if (ctx->timing_io) {
+            CK(cudaEventElapsedTime(&t, ctx->cev[c].in0, ctx->cev[c].in1));
+            h2d += t;
+            CK(cudaEventElapsedTime(&t, ctx->cev[c].out0, ctx->cev[c].out1));
+            d2h += t;
+        }
     }
     CK(cudaEventElapsedTime(&total, ctx->ev[0], ctx->ev[1]));
-    ctx->ms[GA_T_FILL] = fill;
-    ctx->ms[GA_T_WALK] = walk;
-    ctx->ms[GA_T_TOTAL] = ctx->ms[GA_T_H2D] + total + ctx->ms[GA_T_D2H];
-    for (int k = 0; k < GA_T_COUNT; ++k) ms[k] = ctx->ms[k];
+    // per-phase sums; with the pipeline on, phases overlap each other, so they add up
+    // to more than `total` (the bracketing events on the caller-visible stream)
+    ms[GA_T_H2D] = h2d + ctx->ms[GA_T_H2D];
+    ms[GA_T_FILL] = fill;
+    ms[GA_T_WALK] = walk;
+    ms[GA_T_D2H] = d2h;
+    ms[GA_T_TOTAL] = total + ctx->ms[GA_T_H2D];
     return GA_OK;
 }
 
@@ -539,30 +647,22 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
          (rc = ensure(ctx, ctx->d_len, (size_t)n_pairs * 4)) ||
          (rc = ensure(ctx, ctx->d_status, (size_t)n_pairs * 4))))
         return rc;
+    // offset arrays first (every chunk needs them); letters follow chunk by chunk
     CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaMemcpyAsync(ctx->d_s1.p, s1, b1, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_s2.p, s2, b2, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, st));
     if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[3], st));
-    rc = ga_run_batch(ctx, (const uint8_t *)ctx->d_s1.p, (const int64_t *)ctx->d_off1.p,
+    HostIO io;
+    io.s1 = s1; io.s2 = s2; io.off1 = s1_off; io.off2 = s2_off; io.ops_off = out_ops_off;
+    io.cost = out_cost; io.len = out_ops_len; io.status = out_status; io.ops = out_ops;
+    rc = run_pipeline(ctx, (const uint8_t *)ctx->d_s1.p, (const int64_t *)ctx->d_off1.p,
                       (const uint8_t *)ctx->d_s2.p, (const int64_t *)ctx->d_off2.p,
-                      (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p,
-                      (const int64_t *)ctx->d_opsoff.p, (int32_t *)ctx->d_len.p,
-                      (int32_t *)ctx->d_status.p);
+                      (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p, (const int64_t *)ctx->d_opsoff.p,
+                      (int32_t *)ctx->d_len.p, (int32_t *)ctx->d_status.p, &io);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaMemcpyAsync(out_cost, ctx->d_cost.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
-    if (!cost_only) {
-        CK(cudaMemcpyAsync(out_ops, ctx->d_ops.p, opsb, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out_ops_len, ctx->d_len.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out_status, ctx->d_status.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->ms[GA_T_H2D], ctx->ev[2], ctx->ev[3]));
-    CK(cudaEventElapsedTime(&ctx->ms[GA_T_D2H], ctx->ev[4], ctx->ev[5]));
     return GA_OK;
 }
 
@@ -626,9 +726,13 @@ extern "C" int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const u
 }
 
 // ------------------------------------------------------------------ integer-ALU roofline probe
-// Independent chains, no memory traffic: how many of the fill kernel's instruction
-// kinds the SMs retire per second.  mode 0: IADD;  1: VIMNMX3.S16x2;  2: VIMNMX3 (s32);
-// 3: LOP3;  4: IMAD;  5: the packed fill cell's own mix (20 instructions).
+// No memory traffic: how many of the fill kernel's instruction kinds the SMs retire per
+// second.  Throughput modes use 8 independent chains per thread:
+//   0 IADD   1 VIMNMX3.S16x2   2 VIMNMX3 (s32)   3 LOP3   4 IMAD   5 the packed cell's own mix
+//   6 VIADDMNMX.S16x2   7 VIMNMX.U16x2   8 VIADD.16x2 (__vadd2)   9 VIADDMNMX (s32)
+// Latency modes use ONE dependent chain per thread (reported as giga-instr/s; with
+// 8 warps per scheduler resident the rate is issue-limited unless latency > 8 cycles):
+//   10 VIMNMX3.S16x2 chain   11 VIADDMNMX.S16x2 chain   12 IADD chain
 template <int MODE>
 __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsigned seed) {
     unsigned a[8], b[8], c[8];
@@ -638,6 +742,20 @@ __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsi
         b[k] = seed * 3u + threadIdx.x + 11u * k;
         c[k] = seed ^ (threadIdx.x * 5u + k);
     }
+    if (MODE >= 10) {
+        unsigned x = a[0], y = b[0], z = c[0];
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (MODE == 10) x = __vimin3_s16x2(x, y, z) + 1u;
+                else if (MODE == 11) x = __viaddmin_s16x2(x, y, z);
+                else x = x + y;
+                if (MODE == 10) { /* the +1 keeps the chain from collapsing; counted below */ }
+            }
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = x ^ y ^ z;
+        return;
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -646,16 +764,20 @@ __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsi
             else if (MODE == 2) { a[k] = (unsigned)__vimin3_s32((int)a[k], (int)b[k], (int)c[k]); b[k] = (unsigned)__vimin3_s32((int)b[k], (int)c[k], (int)a[k]); }
             else if (MODE == 3) { a[k] = (a[k] & b[k]) ^ c[k]; b[k] = (b[k] | c[k]) ^ a[k]; }
             else if (MODE == 4) { a[k] = a[k] * b[k] + c[k]; b[k] = b[k] * c[k] + a[k]; }
+            else if (MODE == 6) { a[k] = __viaddmin_s16x2(a[k], b[k], c[k]); b[k] = __viaddmin_s16x2(b[k], c[k], a[k]); }
+            else if (MODE == 7) { a[k] = __vminu2(a[k], b[k]); b[k] = __vmaxu2(b[k], c[k] ^ a[k]); }
+            else if (MODE == 8) { a[k] = __vadd2(a[k], b[k]); b[k] = __vadd2(b[k], a[k]); }
+            else if (MODE == 9) { a[k] = (unsigned)__viaddmin_s32((int)a[k], (int)b[k], (int)c[k]); b[k] = (unsigned)__viaddmin_s32((int)b[k], (int)c[k], (int)a[k]); }
             else {
-                // one packed cell: a = diag/h, b = L, c = U  (same 20-instruction mix as fill_kernel)
+                // one packed cell: a = diag/h, b = L, c = U  (same instruction mix as fill_kernel)
                 const unsigned d0 = __vminu2(a[k] ^ seed, 0x00010001u) * 20u + a[k];
-                const unsigned d1 = b[k] + 0x00090009u, d2 = c[k] + 0x000a000au, e0 = d0 + 0x00280028u;
+                const unsigned d1 = b[k] + 0x00090009u, d2 = c[k] + 0x000a000au;
                 const unsigned hq = __vimin3_s16x2(d0, d1, d2);
-                const unsigned Lq = __vimin3_s16x2(e0, d1, d2 + 0x00280028u);
-                const unsigned Uq = __vimin3_s16x2(e0, d1 + 0x00280028u, d2);
-                seed = seed * 4u + (hq & 0x00030003u);
-                seed = seed * 4u + (Lq & 0x00030003u);
-                seed = seed * 4u + (Uq & 0x00030003u);
+                const unsigned Lq = __viaddmin_s16x2(hq, 0x00280028u, d1);
+                const unsigned Uq = __viaddmin_s16x2(hq, 0x00280028u, d2);
+                const unsigned lu = (Lq & 0x00010001u) | (Uq & ~0x00010001u);
+                seed = (seed << 2) | (hq & 0x00030003u);
+                seed ^= (seed << 2) | (lu & 0x00030003u);
                 a[k] = hq & ~0x00030003u; b[k] = Lq & ~0x00030003u; c[k] = Uq & ~0x00030003u;
             }
         }
@@ -667,7 +789,7 @@ __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsi
 }
 
 extern "C" int ga_alu_peak(ga_ctx *ctx, int mode, double *gops) {
-    if (!ctx || !gops || mode < 0 || mode > 5) return GA_E_ARG;
+    if (!ctx || !gops || mode < 0 || mode > 12) return GA_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
     unsigned *d = nullptr;
@@ -675,12 +797,11 @@ extern "C" int ga_alu_peak(ga_ctx *ctx, int mode, double *gops) {
     cudaStream_t st = ctx->stream;
     auto launch = [&](int it) {
         switch (mode) {
-            case 0: alu_kernel<0><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
-            case 1: alu_kernel<1><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
-            case 2: alu_kernel<2><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
-            case 3: alu_kernel<3><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
-            case 4: alu_kernel<4><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
-            default: alu_kernel<5><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+#define GA_ALU_CASE(M) case M: alu_kernel<M><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+            GA_ALU_CASE(0) GA_ALU_CASE(1) GA_ALU_CASE(2) GA_ALU_CASE(3) GA_ALU_CASE(4) GA_ALU_CASE(5)
+            GA_ALU_CASE(6) GA_ALU_CASE(7) GA_ALU_CASE(8) GA_ALU_CASE(9) GA_ALU_CASE(10) GA_ALU_CASE(11)
+            default: alu_kernel<12><<<blocks, threads, 0, st>>>(d, it, 12345u); break;
+#undef GA_ALU_CASE
         }
     };
     launch(64);
@@ -696,7 +817,11 @@ extern "C" int ga_alu_peak(ga_ctx *ctx, int mode, double *gops) {
     }
     CK(cudaGetLastError());
     cudaFree(d);
-    const double per_iter = (mode == 5) ? 8.0 * 20.0 : 8.0 * 2.0;   // instructions per thread per iteration
+    // instructions per thread per iteration
+    double per_iter = 8.0 * 2.0;
+    if (mode == 5) per_iter = 8.0 * 16.0;
+    if (mode == 10) per_iter = 32.0;      // min3 + add per link, 16 links
+    if (mode == 11 || mode == 12) per_iter = 16.0;
     *gops = per_iter * iters * (double)blocks * threads / (best * 1e-3) / 1e9;
     return GA_OK;
 }

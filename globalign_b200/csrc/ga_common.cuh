@@ -2,10 +2,13 @@
 //
 // Data layout in HBM ("Direction-code layout"):
 //   * sequences: one uint8 letter index per residue, CSR offsets (int64);
-//   * direction codes: for every DP cell three 2-bit codes c0,c1,c2 -- the
-//     first-listed argmin of the three candidates the reference's traceback
-//     ranks at that cell when its successor node is on level 0/1/2
-//     (reference globaligner.py:490-514, tie table :595-685);
+//   * direction codes: the reference's traceback ranks, at every cell, the three
+//     level values with an extra gap_open on the levels that differ from the
+//     successor's level L, and takes the first-listed minimum c_L
+//     (reference globaligner.py:490-514, tie table :595-685).  Because
+//     c_1 is either c_0 or 1 and c_2 is either c_0 or 2, a cell needs 4 bits:
+//     plane 0 holds c_0 (2 bits), plane 1 holds bL = [c_1 == 1] (bit 0) and
+//     bU = [c_2 == 2] (bit 1);
 //   * a "tile" is the set of pairs one warp fills together.  The warp's 32
 //     lanes are split into groups of G lanes; each lane owns R consecutive DP
 //     rows; a group sweeps the columns of its pair(s) as an anti-diagonal
@@ -30,6 +33,11 @@ struct SchemeDev {
     const int *gv4t;     // TABLE: A+1 ints, 4*cm[a]["-"] + 2 (level-2 tag), entry A = 2
     const int *gv_raw;   // TABLE: A+1 ints, cm[a]["-"], entry A = 0
     const int *gh_raw;   // TABLE: A ints
+    // Runtime multipliers (1, 4, 0xffffffff).  The fill kernel writes its additions,
+    // tag clears and code packing as a*k+b with these so that ptxas emits IMAD (FMA
+    // pipe) instead of IADD3/LOP3/LEA (ALU pipe): the ALU pipe is the bottleneck of
+    // the cell update (profiles/README.md), the FMA pipe would otherwise idle.
+    unsigned k_one, k_four, k_minus_one;
 };
 
 struct TileDesc {
@@ -46,7 +54,7 @@ struct Lay {
     static constexpr int G = G_;                       // lanes per group (one item per group)
     static constexpr int RPW = PACKED ? 8 : 16;        // rows per 32-bit code word (per plane)
     static constexpr int WPP = (R + RPW - 1) / RPW;    // words per plane per step
-    static constexpr int NW = 3 * WPP;                 // code words per lane per step
+    static constexpr int NW = 2 * WPP;                 // code words per lane per step (2 planes)
     static constexpr int S = (NW % 4 == 0) ? 1 : ((NW % 2 == 0) ? 2 : 4);  // steps per store block
     static constexpr int NQ = S * NW / 4;              // 128-bit stores per lane per block
     static constexpr int IPW = 32 / G;                 // items (lane groups) per warp

@@ -17,12 +17,16 @@
 // three-way minimum the level index (0,1,2) is added in the two low bits, so a
 // single VIMNMX3 returns both the minimum and its first-listed argmin -- ties go
 // to the lowest level, which is the canonical order of the reference's tie
-// table (globaligner.py:599-607).  With D = (d0,d1,d2) the three level values of
-// a cell and o the gap-open cost:
-//     hq = min3(d0, d1|1, d2|2)        -> code c0 (successor on level 0), h
-//     Lq = min3(d0+o, d1|1, (d2|2)+o)  -> code c1 (successor on level 1), L
-//     Uq = min3(d0+o, (d1|1)+o, d2|2)  -> code c2 (successor on level 2), U
-// and the next cells use  d0' = h(diag)+sub, d1' = L(left)+gap_h, d2' = U(up)+gap_v.
+// table (globaligner.py:599-607).  With (d0,d1,d2) the three level values of a
+// cell, o the gap-open cost and hq = min3(d0, d1|1, d2|2):
+//     c0 = hq & 3                      (successor on level 0),     h = hq & ~3
+//     Lq = min(hq + o, d1|1)           value min(d0+o, d1, d2+o),  L = Lq & ~3
+//     Uq = min(hq + o, d2|2)           value min(d0+o, d1+o, d2),  U = Uq & ~3
+// (since d1 <= d1+o, min(d0+o,d1,d2+o) = min(h+o, d1); the tag of hq carried
+// through the fused add-min VIADDMNMX keeps every tie on the reference's side:
+// Lq's tag is c1 in {c0, 1}, Uq's tag is c2 in {c0, 2}).  Stored per cell: c0 and
+// the two bits bL = Lq & 1, bU = Uq & 2.  The next cells use
+//     d0' = h(diag) + sub,  d1' = L(left) + gap_h,  d2' = U(up) + gap_v.
 // The boundary row/column use the reference's finite sentinel
 // (max_cost+1)*max(m,n) so every value equals the reference's.
 #pragma once
@@ -41,8 +45,8 @@ struct VOps<false> {
     static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
         return (unsigned)__vimin3_s32((int)a, (int)b, (int)c);
     }
-    static __device__ __forceinline__ unsigned min2(unsigned a, unsigned b) {
-        return (unsigned)min((int)a, (int)b);
+    static __device__ __forceinline__ unsigned addmin(unsigned a, unsigned b, unsigned c) {
+        return (unsigned)__viaddmin_s32((int)a, (int)b, (int)c);      // min(a + b, c)
     }
     static __device__ __forceinline__ unsigned pk(unsigned lo, unsigned) { return lo; }
 };
@@ -53,7 +57,9 @@ struct VOps<true> {
     static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
         return __vimin3_s16x2(a, b, c);
     }
-    static __device__ __forceinline__ unsigned min2(unsigned a, unsigned b) { return __vmins2(a, b); }
+    static __device__ __forceinline__ unsigned addmin(unsigned a, unsigned b, unsigned c) {
+        return __viaddmin_s16x2(a, b, c);                             // per half: min(a + b, c)
+    }
     static __device__ __forceinline__ unsigned pk(unsigned lo, unsigned hi) { return lo | (hi << 16); }
 };
 
@@ -97,6 +103,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int n_tiles,
     const unsigned ghTc = V::pk(4u * sc.gh + 1u, 4u * sc.gh + 1u);
     const unsigned gvTc = V::pk(4u * sc.gv + 2u, 4u * sc.gv + 2u);
     const unsigned padb = SIMPLE ? (unsigned)PAD_B : 0u;
+    // a*k+b forms that must stay IMADs (FMA pipe); see SchemeDev::k_one
+    const unsigned K1 = sc.k_one, K4 = sc.k_four, KM1 = sc.k_minus_one;
 
     for (;;) {
         int tile = 0;
@@ -259,18 +267,22 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int n_tiles,
                             } else {
                                 d0 = diag + (unsigned)s_sub[aw[r] + bv];
                             }
-                            const unsigned d1 = Lp[r] + ghT;
-                            const unsigned d2 = up + gvT[r];
-                            const unsigned e0 = d0 + o4;
+                            const unsigned d1 = Lp[r] * K1 + ghT;            // IMAD
+                            const unsigned d2 = up * K1 + gvT[r];            // IMAD
                             const unsigned hq = V::min3(d0, d1, d2);
-                            const unsigned Lq = V::min3(e0, d1, d2 + o4);
-                            const unsigned Uq = V::min3(e0, d1 + o4, d2);
+                            const unsigned Lq = V::addmin(hq, o4, d1);
+                            const unsigned Uq = V::addmin(hq, o4, d2);
                             const int w = r / L::RPW;
-                            acc[w] = acc[w] * 4u + (hq & V::TAGM);
-                            acc[L::WPP + w] = acc[L::WPP + w] * 4u + (Lq & V::TAGM);
-                            acc[2 * L::WPP + w] = acc[2 * L::WPP + w] * 4u + (Uq & V::TAGM);
+                            // plane 0: c0.  A code word takes at most RPW inserts, so a half
+                            // never shifts into its neighbour.
+                            const unsigned th = hq & V::TAGM;                 // LOP3
+                            acc[w] = acc[w] * K4 + th;                       // IMAD
+                            // plane 1: bit 0 (of each half) from Lq, bit 1 from Uq
+                            constexpr unsigned B0 = V::TAGM & 0x55555555u;
+                            const unsigned lu = ((Lq & B0) | (Uq & ~B0)) & V::TAGM;   // 2 x LOP3
+                            acc[L::WPP + w] = acc[L::WPP + w] * K4 + lu;     // IMAD
                             diag = hl[r];
-                            hl[r] = hq & ~V::TAGM;
+                            hl[r] = th * KM1 + hq;                           // hq - tag, IMAD
                             Lp[r] = Lq & ~V::TAGM;
                             up = Uq & ~V::TAGM;
                         }

@@ -3,8 +3,9 @@
 // Replaces the reference's dp_array_backward (globaligner.py:395-593),
 // cost_ranks_dispatcher (:595-685, canonical = first listed option) and the four
 // take_* emitters (:688-753).  One thread walks one pair: at cell (i, j) with
-// the successor node on level L it reads the 2-bit code c_L(i, j), emits it as
-// the operation, moves, and sets L to it.  Reaching row 0 / column 0 ends the
+// the successor node on level L it decodes c_L(i, j) -- plane 0 holds c_0; for
+// L = 1 (2) the bit bL (bU) of plane 1 says "take level 1 (2)", otherwise
+// c_L = c_0 -- emits it as the operation, moves, and sets L to it.  Reaching row 0 / column 0 ends the
 // walk with a run of gap operations (:542-581).  Operations are emitted in walk
 // order, 16 per 32-bit word.
 //
@@ -67,12 +68,18 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int pair_lo,
         const int t = (j - 1) + g;
         const int tb = t / L::S, u = t - tb * L::S;
         const int w = r / L::RPW;
-        const int flat = u * L::NW + level * L::WPP + w;
-        const size_t chunk = ((size_t)pass * nTB + tb) * L::NQ + (flat >> 2);
-        const uint32_t cword = cw[(chunk * 32 + lane0 + g) * 4 + (flat & 3)];
         const int rows_in_word = min(L::RPW, R - w * L::RPW);
         const int sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
-        return (int)((cword >> sh) & 3u);
+        const size_t base = (((size_t)pass * nTB + tb) * L::NQ * 32 + lane0 + g) * 4;
+        auto plane = [&](int pl) -> unsigned {
+            const int flat = u * L::NW + pl * L::WPP + w;
+            return (cw[base + (size_t)(flat >> 2) * 128 + (flat & 3)] >> sh) & 3u;
+        };
+        if (level != 0) {
+            const unsigned lu = plane(1);
+            if (lu & (unsigned)level) return level;      // bL is bit 0 (level 1), bU is bit 1 (level 2)
+        }
+        return (int)plane(0);
     };
 
     int i = m, j = n, level = 0, status = 0;

@@ -61,7 +61,8 @@ enum {
 enum {
     GA_F_DEFAULT = 0,
     GA_F_FORCE_GENERIC = 1,   /* never use the packed 16-bit kernel */
-    GA_F_COST_ONLY = 2        /* skip the traceback walk (ops / ops_len untouched) */
+    GA_F_COST_ONLY = 2,       /* skip the traceback walk (ops / ops_len untouched) */
+    GA_F_SERIAL = 4           /* one stream, no fill/walk/copy overlap (isolated kernel timing) */
 };
 
 /* phases reported by ga_get_timing (milliseconds, CUDA events on the ctx stream) */
@@ -79,8 +80,9 @@ const char *ga_last_error(const ga_ctx *ctx);
 /* Launch on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream);
  * NULL/0 = the context's own stream. */
 int ga_ctx_set_stream(ga_ctx *ctx, void *cuda_stream);
-/* Cap on library-owned device scratch in bytes (default 64 GiB); batches whose
- * direction codes exceed it are processed in chunks. */
+/* Cap on library-owned direction-code scratch in bytes (default 64 GiB).  Batches are
+ * processed in chunks whose codes ping-pong between two scratch buffers of at most
+ * half this size each (one buffer of at most this size with GA_F_SERIAL). */
 int ga_ctx_set_scratch_limit(ga_ctx *ctx, int64_t bytes);
 
 /* Replaces: the costing_mat / gap_open_cost arguments of make_dp_array,
@@ -120,7 +122,9 @@ typedef struct {
 } ga_plan_info;
 int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info);
 
-/* CUDA-event milliseconds of the last ga_align_batch / ga_run_batch per phase. */
+/* CUDA-event milliseconds of the last ga_align_batch / ga_run_batch: per-phase sums
+ * over the chunks (phases overlap each other unless GA_F_SERIAL was planned, so they
+ * can add up to more than GA_T_TOTAL) and the bracketed total on the context stream. */
 int ga_get_timing(ga_ctx *ctx, float *ms /* GA_T_COUNT entries */);
 
 /* Debug / parity aid: the full (m+1) x (n+1) x 3 int32 value table of ONE pair,
@@ -131,9 +135,11 @@ int ga_get_timing(ga_ctx *ctx, float *ms /* GA_T_COUNT entries */);
 int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                    int keep_boundary, int32_t *table);
 
-/* Integer-ALU roofline microbenchmark: measured giga-ops/s of dependent-chain-
- * free int32 add / min (mode 0), packed s16x2 add / min3 (mode 1), and the
- * fill kernel's own instruction mix (mode 2). */
+/* Integer-ALU roofline microbenchmark (no memory traffic): giga-instructions/s the
+ * device retires of one instruction kind.  Throughput modes (8 independent chains per
+ * thread): 0 IADD, 1 VIMNMX3.S16x2, 2 VIMNMX3 (s32), 3 LOP3, 4 IMAD, 5 the packed fill
+ * cell's own instruction mix, 6 VIADDMNMX.S16x2, 7 VIMNMX.U16x2, 8 VIADD.16x2,
+ * 9 VIADDMNMX (s32).  Dependent-chain modes: 10 VIMNMX3.S16x2, 11 VIADDMNMX.S16x2, 12 IADD. */
 int ga_alu_peak(ga_ctx *ctx, int mode, double *gops);
 
 #ifdef __cplusplus

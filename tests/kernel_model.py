@@ -16,7 +16,7 @@ TAG = 3
 
 def layout(R, G, rows_per_word):
     wpp = -(-R // rows_per_word)            # words per plane per step
-    nw = 3 * wpp                            # words per step
+    nw = 2 * wpp                            # words per step: plane 0 = c0, plane 1 = (bL, bU)
     from math import gcd
     S = 4 // gcd(nw, 4)                     # steps staged per 128-bit store group
     nq = S * nw // 4                        # uint4 chunks per staged block
@@ -101,13 +101,13 @@ def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=1
                         d0 = diag + s4
                         d1 = st["Lp"][r] + ghT
                         d2 = up + gvT
-                        hq = min(d0, d1, d2)
-                        e0 = d0 + o4
-                        Lq = min(e0, d1, d2 + o4)
-                        Uq = min(e0, d1 + o4, d2)
+                        hq = min(d0, d1, d2)          # tagged: low 2 bits = c0
+                        Lq = min(hq + o4, d1)         # VIADDMNMX; tag is c0 or 1
+                        Uq = min(hq + o4, d2)         # tag is c0 or 2
                         w = r // L["RPW"]
-                        for k, q in enumerate((hq, Lq, Uq)):
-                            words[k * L["WPP"] + w] = words[k * L["WPP"] + w] * 4 + (q & TAG)
+                        lu = (Lq & 1) | (Uq & 2)      # bL = "level-1 successor takes level 1", bU likewise
+                        words[w] = words[w] * 4 + (hq & TAG)
+                        words[L["WPP"] + w] = words[L["WPP"] + w] * 4 + lu
                         diag = st["hl"][r]
                         st["hl"][r] = hq & ~TAG
                         st["Lp"][r] = Lq & ~TAG
@@ -129,8 +129,20 @@ def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=1
     return cost, codes, L
 
 
-def code_at(codes, L, m, i, j, plane):
-    """Direction code of `plane` at DP cell (i, j), 1-based, as the walker reads it."""
+def code_at(codes, L, m, i, j, level):
+    """Direction at DP cell (i, j) (1-based) for a successor on `level`, as the walker
+    decodes it: c0 from plane 0; for level 1 (2) the bit bL (bU) of plane 1 overrides
+    it with 1 (2)."""
+    c0 = _plane_at(codes, L, m, i, j, 0)
+    if level == 0:
+        return c0
+    lu = _plane_at(codes, L, m, i, j, 1)
+    if level == 1:
+        return 1 if lu & 1 else c0
+    return 2 if lu & 2 else c0
+
+
+def _plane_at(codes, L, m, i, j, plane):
     R, G = L["R"], L["G"]
     B = G * R
     p = (i - 1) // B

@@ -34,7 +34,9 @@ def main():
     ops = torch.empty(int(ops_off[-1]) + 16, dtype=torch.uint8, device=dev)
     ctx0 = _native.Context(0)
     res = {"alu_peak_gops": {m: ctx0.alu_peak(k) for k, m in enumerate(
-        ["iadd", "vimnmx3_s16x2", "vimnmx3_s32", "lop3", "imad", "packed_cell_mix"])}}
+        ["iadd", "vimnmx3_s16x2", "vimnmx3_s32", "lop3", "imad", "packed_cell_mix", "viaddmnmx_s16x2",
+         "vimnmx_u16x2", "viadd_16x2", "viaddmnmx_s32", "chain_vimnmx3_s16x2", "chain_viaddmnmx_s16x2",
+         "chain_iadd"])}}
     print(json.dumps(res), flush=True)
     ref_cost = None
     cfgs = sys.argv[3].split(",") if len(sys.argv) > 3 else [
@@ -45,7 +47,7 @@ def main():
         ctx = _native.Context(0)
         ctx.set_scheme(dense)
         try:
-            info = ctx.plan_batch(b.off1, b.off2, ops_off)
+            info = ctx.plan_batch(b.off1, b.off2, ops_off, flags=_native.GA_F_SERIAL)
         except Exception as e:
             print(cfg, "skipped:", e, flush=True)
             continue
