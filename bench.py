@@ -47,11 +47,14 @@ CODE_BYTES_PER_CELL = 0.5   # 2 bits (level-0 argmin) + 1 + 1 (gap-level take bi
 NOMINAL_INT32_TOPS = 148 * 64 * 1.965e9 / 1e12     # 18.6 Tops/s
 
 DESCR = {
+    "cfg1": "single DNA pair 1 kb x 1 kb, match 2 / mismatch -3 / gap open -10 / extend -1 (BASELINE configs[0])",
+    "cfg4": "single long DNA pair 100 kb x 100 kb, band-pipeline fill + checkpointed linear-space traceback "
+            "(BASELINE configs[3])",
     "cfg2": "1M synthetic DNA short-read pairs 150 bp x 150 bp with traceback (BASELINE configs[1])",
     "cfg3": "100k protein pairs 300-1000 aa, BLOSUM62, gap_open_cost=10 (BASELINE configs[2])",
     "cfg5": "10M DNA pairs 250 bp x 250 bp sharded across the GPUs (BASELINE configs[4])",
 }
-DEFAULT_PAIRS = {"cfg2": 1_000_000, "cfg3": 100_000, "cfg5": 10_000_000}
+DEFAULT_PAIRS = {"cfg1": 1, "cfg4": 1, "cfg2": 1_000_000, "cfg3": 100_000, "cfg5": 10_000_000}
 
 
 def parse_args():
@@ -60,7 +63,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(DESCR))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(DESCR))  # cfg1 cfg2 cfg3 cfg4 cfg5
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU (default: the BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -168,6 +171,38 @@ def python_port_mcups(batch, scheme, n: int = 6):
     return cells / (time.perf_counter() - t0) / 1e6
 
 
+def run_reference_long(args, name, scheme, threads):
+    """cfg1: the C port on the pair itself (1 core: one pair does not parallelise in the
+    reference's algorithm).  cfg4: a bounded 8 kb x 8 kb prefix of the pair (the full table the
+    reference's algorithm needs, 12 B x 1e10 cells, does not fit in host memory)."""
+    from oracle import c_oracle
+    batch = synth.workload(name)
+    k = 1000 if name == "cfg1" else 8000
+    dense = scheme.dense_for(sorted(batch.alphabet))
+    remap = np.array([dense.index[ch] for ch in batch.alphabet], dtype=np.uint8)
+    s1, s2 = remap[batch.s1[:k]], remap[batch.s2[:k]]
+    d = oracle_dense(dense)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        c_oracle.align_codes(s1, s2, d)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = k * k / (ms / 1e3) / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": DESCR[name], "sample": f"{k} x {k} prefix of the pair"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{k} x {k} prefix, C restatement (oracle/ga_oracle.c), one thread"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
     if rank != 0:
@@ -176,6 +211,8 @@ def run_reference(args, rank):
     name = args.workload
     scheme = Scheme(**synth.SCHEMES[name])
     threads = os.cpu_count() or 1
+    if name in ("cfg1", "cfg4"):
+        return run_reference_long(args, name, scheme, threads)
     per_pair = {"cfg2": 22500, "cfg3": 450000, "cfg5": 62500}[name]
     n_sample = int(min(DEFAULT_PAIRS[name], max(256, 4e9 / per_pair)))       # ~4e9 cells per step
     batch = synth.workload(name, n_pairs=n_sample)
@@ -204,6 +241,73 @@ def run_reference(args, rank):
         "python_port_mcups_per_core": python_port_mcups(batch, scheme),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- single long pair
+def run_long(args, rank, world, local_rank):
+    """cfg1 / cfg4: one pair per GPU through ga_align_long (every rank aligns the same pair:
+    a single long pair stays on one GPU; N > 1 runs are replicas)."""
+    import torch
+    import torch.distributed as dist
+
+    from globalign_b200 import _native
+    from globalign_b200.batch import Scheme
+
+    torch.cuda.set_device(local_rank)
+    name = args.workload
+    batch = synth.workload(name)
+    scheme = Scheme(**synth.SCHEMES[name])
+    dense = scheme.dense_for(sorted(batch.alphabet))
+    ctx = _native.Context(local_rank)
+    ctx.set_scheme(dense)
+    cells = batch.cells()
+    steps = max(1, min(args.steps, 10))
+    for _ in range(max(1, min(args.warmup, 3))):
+        ctx.align_long(batch.s1, batch.s2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    t_lo = time.perf_counter()
+    dev_ms, fill_ms, trace_ms, info = 0.0, 0.0, 0.0, None
+    for _ in range(steps):
+        cost, ops, status, info = ctx.align_long(batch.s1, batch.s2)
+        dev_ms += info["fill_ms"] + info["trace_ms"]
+        fill_ms += info["fill_ms"]
+        trace_ms += info["trace_ms"]
+    torch.cuda.synchronize()
+    t_hi = time.perf_counter()
+    clocks = sampler.stop(t_lo, t_hi)
+    vals = torch.tensor([dev_ms / steps, (t_hi - t_lo) * 1e3 / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    step_ms, e2e_ms = vals[0].item(), vals[1].item()
+    total_cells = cells * world
+    fill_gcups = cells / (fill_ms / steps / 1e3) / 1e9
+    achieved = fill_gcups * 1e9 * OPS_PER_CELL / 1e12
+    line = {
+        "metric": METRIC, "value": total_cells / (step_ms / 1e3) / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": DESCR[name], "cells_per_gpu": cells, "replicas": world,
+                   "l2": "checkpoints %.0f MB per step" % (info["checkpoint_bytes"] / 1e6),
+                   "tile": [info["tile_rows"], info["tile_cols"]], "retraced_tiles": info["retraced_tiles"]},
+        "clocks": clocks,
+        "e2e": {"value": total_cells / (e2e_ms / 1e3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(batch.s1.nbytes + batch.s2.nbytes + 4 * (len(batch.s1) + len(batch.s2) + 2)),
+                "d2h_bytes_per_step": int(len(ops) // 4 + 32)},
+        "gpu_launches": info["launches"] * steps,
+        "kernels_ms": {"fill": fill_ms / steps, "trace": trace_ms / steps},
+        "roofline": {"bound": "int_alu", "kernel": "long_fill_kernel", "achieved": achieved,
+                     "peak": NOMINAL_INT32_TOPS, "unit": "Tops/s", "frac": achieved / NOMINAL_INT32_TOPS,
+                     "peak_source": "nominal 148 SM x 64 lanes x 1.965 GHz", "ops_per_cell": OPS_PER_CELL,
+                     "fill_gcups": fill_gcups, "traffic": None},
     }
     print(json.dumps(line), flush=True)
 
@@ -412,7 +516,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload in ("cfg1", "cfg4"):
+            run_long(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

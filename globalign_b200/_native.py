@@ -27,7 +27,7 @@ EXPORTS = (
     "ga_version", "ga_device_count", "ga_ctx_create", "ga_ctx_destroy", "ga_last_error",
     "ga_ctx_set_stream", "ga_ctx_set_scratch_limit", "ga_set_scheme", "ga_align_batch",
     "ga_plan_batch", "ga_run_batch", "ga_sync", "ga_get_plan_info", "ga_get_timing",
-    "ga_fill_values", "ga_alu_peak",
+    "ga_fill_values", "ga_alu_peak", "ga_align_long",
 )
 
 
@@ -40,6 +40,12 @@ class PlanInfo(C.Structure):
                 ("lanes_per_group", C.c_int32), ("packed16", C.c_int32),
                 ("launches_per_run", C.c_int32), ("code_bytes", C.c_int64),
                 ("cells", C.c_int64), ("n_chunks", C.c_int64)]
+
+
+class LongInfo(C.Structure):
+    _fields_ = [("fill_ms", C.c_float), ("trace_ms", C.c_float), ("launches", C.c_int32),
+                ("tile_rows", C.c_int32), ("tile_cols", C.c_int32), ("retraced_tiles", C.c_int32),
+                ("checkpoint_bytes", C.c_int64), ("cells", C.c_int64)]
 
 
 _lib = None
@@ -73,6 +79,8 @@ def lib():
     L.ga_get_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.ga_fill_values.argtypes = [vp, vp, i64, vp, i64, C.c_int, vp]
     L.ga_alu_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.ga_align_long.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
+                                C.POINTER(i32), u32, C.POINTER(LongInfo)]
     for name in EXPORTS:
         if name not in ("ga_last_error",):
             getattr(L, name).restype = C.c_int
@@ -208,6 +216,22 @@ class Context:
         g = C.c_double(0.0)
         self._check(self._L.ga_alu_peak(self._h, int(mode), C.byref(g)))
         return g.value
+
+
+    def align_long(self, s1, s2, flags: int = 0):
+        """One long pair, linear-space traceback -> (cost, ops uint8 walk order | None, status, info)."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        m, n = len(s1), len(s2)
+        packed = np.zeros(4 * ((m + n + 15) // 16) + 16, dtype=np.uint8)
+        cost, nops, status = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+        info = LongInfo()
+        self._check(self._L.ga_align_long(self._h, _ptr(s1), m, _ptr(s2), n, C.byref(cost), _ptr(packed),
+                                          C.byref(nops), C.byref(status), flags, C.byref(info)))
+        d = {k: getattr(info, k) for k, _ in LongInfo._fields_}
+        if flags & GA_F_COST_ONLY:
+            return cost.value, None, 0, d
+        return cost.value, unpack_ops(packed, 0, nops.value), status.value, d
 
 
 def ops_offsets(off1, off2) -> np.ndarray:

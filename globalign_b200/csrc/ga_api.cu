@@ -14,6 +14,7 @@
 #include "../../include/globalign_b200.h"
 #include "ga_fill.cuh"
 #include "ga_walk.cuh"
+#include "ga_long.cuh"
 
 using namespace ga;
 
@@ -121,6 +122,7 @@ struct ga_ctx {
     SchemeDev sc{};
     bool uniform_gaps = false;
     DevBuf d_sub4, d_gh4t, d_gv4t, d_gvraw, d_ghraw;
+    std::vector<int> h_gh, h_gv;       // host copies (prefix sums of the long-pair path)
     // plan
     bool have_plan = false;
     const KernelCfg *cfg = nullptr;
@@ -135,6 +137,8 @@ struct ga_ctx {
     DevBuf d_tiles, d_codes[2], d_bnd[2], d_counter;
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
+    // long-pair path
+    DevBuf l_colsum, l_rowsum, l_brow, l_vchk, l_prog, l_misc;
     // timing
     cudaEvent_t ev[8] = {};
     std::vector<ChunkEvents> cev;
@@ -209,7 +213,8 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
                       &ctx->d_tiles, &ctx->d_codes[0], &ctx->d_codes[1], &ctx->d_bnd[0], &ctx->d_bnd[1],
                       &ctx->d_counter, &ctx->d_s1,
                       &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
-                      &ctx->d_opsoff, &ctx->d_len, &ctx->d_status})
+                      &ctx->d_opsoff, &ctx->d_len, &ctx->d_status, &ctx->l_colsum, &ctx->l_rowsum,
+                      &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc})
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &c : ctx->cev)
@@ -308,6 +313,8 @@ extern "C" int ga_set_scheme(ga_ctx *ctx, int A, const int32_t *sub, const int32
     sc.k_four = 4u;
     sc.k_minus_one = 0xffffffffu;
     ctx->uniform_gaps = uniform;
+    ctx->h_gh.assign(gap_h, gap_h + A);
+    ctx->h_gv.assign(gap_v, gap_v + A);
     ctx->have_scheme = true;
     ctx->have_plan = false;
     return GA_OK;
@@ -663,6 +670,125 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->ms[GA_T_H2D], ctx->ev[2], ctx->ev[3]));
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ one long pair
+extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                             int32_t *out_cost, uint8_t *out_ops, int64_t *out_n_ops,
+                             int32_t *out_status, uint32_t flags, ga_long_info *info) {
+    if (!ctx) return GA_E_ARG;
+    if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
+    const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
+    if (!s1 || !s2 || !out_cost || m < 1 || n < 1 || m > (1 << 28) || n > (1 << 28) ||
+        (!cost_only && (!out_ops || !out_n_ops || !out_status)))
+        return fail(ctx, GA_E_ARG, "bad arguments to ga_align_long");
+    const SchemeDev &sc = ctx->sc;
+    if (!sc.simple && sc.A > 64) return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
+    {
+        const long long big = (long long)(sc.max_cost + 1) * std::max(m, n);
+        const long long vmax = big + (std::min<long long>(m + LBAND, n + 32) + 2) * sc.max_cost + 3LL * sc.o;
+        if (4 * vmax + 3 >= 0x7fffffffLL) return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // column-0 / row-0 running sums (reference make_dp_array, globaligner.py:802-819)
+    std::vector<int> colsum((size_t)m + 1), rowsum((size_t)n + 1);
+    colsum[0] = sc.o;
+    for (int64_t i = 1; i <= m; ++i) {
+        if (s1[i - 1] >= sc.A) return fail(ctx, GA_E_ARG, "letter index out of range in seq_1");
+        colsum[(size_t)i] = colsum[(size_t)i - 1] + ctx->h_gv[s1[i - 1]];
+    }
+    rowsum[0] = sc.o;
+    for (int64_t j = 1; j <= n; ++j) {
+        if (s2[j - 1] >= sc.A) return fail(ctx, GA_E_ARG, "letter index out of range in seq_2");
+        rowsum[(size_t)j] = rowsum[(size_t)j - 1] + ctx->h_gh[s2[j - 1]];
+    }
+    const int nbands = (int)((m + LBAND - 1) / LBAND);
+    const int nck = (int)(n / LCC + 2);
+    const size_t brow_b = (size_t)nbands * (size_t)(n + 1) * sizeof(int2);
+    const size_t vchk_b = (size_t)nbands * nck * 32 * LR * sizeof(int2);
+    if ((int64_t)(brow_b + vchk_b) > ctx->scratch_limit)
+        return fail(ctx, GA_E_NOMEM, "checkpoints need %zu bytes, above the scratch limit", brow_b + vchk_b);
+    const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_s1, (size_t)m + 16)) || (rc = ensure(ctx, ctx->d_s2, (size_t)n + 16)) ||
+        (rc = ensure(ctx, ctx->l_colsum, colsum.size() * 4)) || (rc = ensure(ctx, ctx->l_rowsum, rowsum.size() * 4)) ||
+        (rc = ensure(ctx, ctx->l_brow, brow_b)) || (rc = ensure(ctx, ctx->l_vchk, vchk_b)) ||
+        (rc = ensure(ctx, ctx->l_misc, 256)) ||
+        (rc = ensure(ctx, ctx->d_ops, ops_words * 4 + 16)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->d_s1.p, s1, (size_t)m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_s2.p, s2, (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->l_colsum.p, colsum.data(), colsum.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->l_rowsum.p, rowsum.data(), rowsum.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->l_brow.p, 0xFF, brow_b, st));      // -1 = boundary entry not yet written
+    CK(cudaMemsetAsync(ctx->l_misc.p, 0, 256, st));
+    // l_misc: [0] band counter, [1] cost, [2] status, [3] tiles, [4..5] n_ops
+    int *misc = (int *)ctx->l_misc.p;
+    LongArgs a;
+    a.s1 = (const uint8_t *)ctx->d_s1.p;
+    a.s2 = (const uint8_t *)ctx->d_s2.p;
+    a.m = (int)m;
+    a.n = (int)n;
+    a.colsum = (const int *)ctx->l_colsum.p;
+    a.rowsum = (const int *)ctx->l_rowsum.p;
+    a.brow = (int2 *)ctx->l_brow.p;
+    a.vchk = (int2 *)ctx->l_vchk.p;
+    a.band_counter = misc;
+    a.nbands = nbands;
+    a.nck = nck;
+    a.big = (unsigned)((long long)(sc.max_cost + 1) * std::max(m, n));
+    a.out_cost = misc + 1;
+    a.debug_nosync = getenv("GA_DEBUG_LONG_NOSYNC") ? 1 : 0;
+    const size_t table = sc.simple ? 0 : ((((size_t)(sc.A + 1) * sc.A + sc.A) * 4 + 15) & ~(size_t)15);
+    const int grid = std::min((nbands + LWARPS - 1) / LWARPS, ctx->sm_count * 4);
+    CK(cudaEventRecord(ctx->ev[2], st));
+    if (sc.simple) long_fill_kernel<true><<<grid, 32 * LWARPS, 0, st>>>(sc, a);
+    else long_fill_kernel<false><<<grid, 32 * LWARPS, table, st>>>(sc, a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[3], st));
+    int launches = 1;
+    if (!cost_only) {
+        TraceOut to;
+        to.ops = (uint32_t *)ctx->d_ops.p;
+        to.n_ops = (long long *)(misc + 4);
+        to.status = misc + 2;
+        to.tiles_refilled = misc + 3;
+        const size_t tsmem = (size_t)LT_NTB * 32 * sizeof(uint4) + table;
+        if (sc.simple) {
+            CK(cudaFuncSetAttribute(long_trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            long_trace_kernel<true><<<1, 32, tsmem, st>>>(sc, a, to);
+        } else {
+            CK(cudaFuncSetAttribute(long_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            long_trace_kernel<false><<<1, 32, tsmem, st>>>(sc, a, to);
+        }
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    int host_misc[8] = {};
+    CK(cudaMemcpyAsync(host_misc, misc, sizeof host_misc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out_cost = host_misc[1];
+    if (!cost_only) {
+        long long nops = 0;
+        memcpy(&nops, host_misc + 4, 8);
+        *out_n_ops = nops;
+        *out_status = host_misc[2];
+        CK(cudaMemcpy(out_ops, ctx->d_ops.p, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
+    }
+    if (info) {
+        memset(info, 0, sizeof *info);
+        CK(cudaEventElapsedTime(&info->fill_ms, ctx->ev[2], ctx->ev[3]));
+        CK(cudaEventElapsedTime(&info->trace_ms, ctx->ev[3], ctx->ev[4]));
+        info->launches = launches;
+        info->tile_rows = LBAND;
+        info->tile_cols = LCC;
+        info->retraced_tiles = host_misc[3];
+        info->checkpoint_bytes = (int64_t)(brow_b + vchk_b);
+        info->cells = m * n;
+    }
     return GA_OK;
 }
 

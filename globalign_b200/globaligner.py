@@ -26,19 +26,31 @@ from .start import get_max_val, make_matrix, validate_and_transform_args
 __all__ = ["find_global_alignment", "make_dp_array", "dp_array_forward", "dp_array_backward", "main"]
 
 
+#: pairs with at least this many DP cells go to the whole-chip band pipeline with
+#: linear-space traceback (ga_align_long) instead of the one-warp batched kernel
+LONG_PAIR_CELLS = 1 << 22
+
+
 def _align_one(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: int, device: int = 0):
     dense = DenseScheme(costing_mat, gap_open_cost)
     ctx = _native.default_context(device)
     ctx.set_scheme(dense)
     s1, s2 = dense.encode(seq_1), dense.encode(seq_2)
     m, n = len(s1), len(s2)
-    cost, ops, ops_off, ops_len, status = ctx.align_batch(
-        s1, np.array([0, m], dtype=np.int64), s2, np.array([0, n], dtype=np.int64))
+    if m * n >= LONG_PAIR_CELLS or n > 32768:
+        cost1, ops1, status1, _info = ctx.align_long(s1, s2)
+        cost, status = [cost1], [status1]
+    else:
+        cost, ops, ops_off, ops_len, status = ctx.align_batch(
+            s1, np.array([0, m], dtype=np.int64), s2, np.array([0, n], dtype=np.int64))
+        ops1 = None
     if status[0] != 0:
         raise ReferenceUndefinedError(
             "the reference's traceback leaves the DP table for this input "
             "(max(len(seq_1), len(seq_2)) <= gap_open_cost): it raises IndexError or wraps "
             "to negative indices there")
+    if ops1 is not None:
+        return ops1, int(cost[0])
     return _native.unpack_ops(ops, 0, int(ops_len[0])), int(cost[0])
 
 

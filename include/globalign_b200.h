@@ -127,6 +127,28 @@ int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info);
  * can add up to more than GA_T_TOTAL) and the bracketed total on the context stream. */
 int ga_get_timing(ga_ctx *ctx, float *ms /* GA_T_COUNT entries */);
 
+/* One long pair on the whole GPU, linear-space traceback.  Replaces make_dp_array +
+ * dp_array_forward + dp_array_backward (globaligner.py:756-821, :366-392, :395-593) for a
+ * pair whose direction-code matrix should not be stored: the fill (bands of 128 rows
+ * pipelined across all SMs) keeps only band-boundary rows and column checkpoints
+ * (about 0.13 bytes per cell); the traceback re-fills the 128 x <=128 tile under the
+ * path position from its checkpoints and walks it, tile after tile.  The result is the
+ * same canonical alignment as ga_align_batch gives.  Host buffers; out_ops must hold
+ * 4 * ceil((m + n) / 16) + 4 bytes (2-bit ops in walk order, as for ga_align_batch).
+ * The reference refuses len(seq_1) * len(seq_2) >= 2e7 (start.py:213); this entry point
+ * has no such guard. */
+typedef struct {
+    float fill_ms, trace_ms;          /* CUDA events on the context stream */
+    int32_t launches;                 /* kernels launched */
+    int32_t tile_rows, tile_cols;     /* checkpoint grid */
+    int32_t retraced_tiles;           /* tiles the traceback re-filled */
+    int64_t checkpoint_bytes;         /* device memory held by the checkpoints */
+    int64_t cells;
+} ga_long_info;
+int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                  int32_t *out_cost, uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_status,
+                  uint32_t flags, ga_long_info *info /* may be NULL */);
+
 /* Debug / parity aid: the full (m+1) x (n+1) x 3 int32 value table of ONE pair,
  * i.e. what dp_array_forward leaves in dp_array (globaligner.py:366-392).  If
  * keep_boundary != 0, row 0 and column 0 of `table` (host, in/out) are used as

@@ -1,0 +1,119 @@
+"""The long-pair path (ga_align_long: whole-chip band pipeline + checkpointed linear-space
+traceback) against the oracle.  Bit-exact costs and canonical alignments."""
+import random
+
+import numpy as np
+import pytest
+
+from globalign_b200 import _native, batch, start, synth
+from globalign_b200 import globaligner
+from globalign_b200.globaligner import find_global_alignment
+from oracle import c_oracle
+from test_gpu_parity import _oracle_dense, _simple_dense, _table_dense
+from util import DenseView, golden, rescore
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, dense, s1, s2, full_oracle=True):
+    cost, ops, status, info = ctx.align_long(s1, s2)
+    d = _oracle_dense(dense)
+    if full_oracle:
+        o_ops, o_cost, rc = c_oracle.align_codes(s1, s2, d)
+        assert cost == o_cost and status == rc
+        if rc == 0:
+            assert np.array_equal(ops, o_ops)
+    else:
+        rc, vcost = c_oracle.verify_path(s1, s2, d, ops)
+        assert rc == 0 and vcost == cost and status == 0
+    return cost, ops, info
+
+
+def test_long_path_random_sizes_simple_and_table():
+    rng = random.Random(77)
+    ctx = _native.Context(0)
+    for trial in range(60):
+        table = trial % 3 == 2
+        if table:
+            A = rng.choice([4, 20, 24])
+            dense = _table_dense(rng, A, rng.randint(0, 11))
+        else:
+            A = rng.choice([2, 4, 5])
+            dense = _simple_dense(A, rng.randint(1, 6), rng.randint(1, 3), rng.randint(1, 3), rng.randint(0, 12))
+        ctx.set_scheme(dense)
+        m = rng.choice([1, 2, 7, 255, 256, 257, 300, 511, 513, 1000, 1300])
+        n = rng.choice([1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 700, 1100])
+        s1 = np.array([rng.randrange(A) for _ in range(m)], dtype=np.uint8)
+        if rng.random() < 0.6 and m > 8:
+            keep = np.array([rng.random() > 0.08 for _ in range(m)])
+            s2 = s1[keep][:n].copy()
+            flip = np.array([rng.random() < 0.1 for _ in range(len(s2))])
+            s2[flip] = [rng.randrange(A) for _ in range(int(flip.sum()))]
+            if len(s2) == 0:
+                s2 = np.array([0], dtype=np.uint8)
+        else:
+            s2 = np.array([rng.randrange(A) for _ in range(n)], dtype=np.uint8)
+        _check(ctx, dense, s1, s2)
+    ctx.close()
+
+
+def test_long_path_equals_batched_kernel_and_golden_cfg1():
+    row = golden("workload_prefix.json")["cfg1"][0]
+    b = synth.workload("cfg1")
+    scheme = batch.Scheme(**synth.SCHEMES["cfg1"])
+    dense = scheme.dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    cost, ops, info = _check(ctx, dense, b.s1, b.s2)
+    s1, s2 = b.pair(0)
+    assert list(batch.render(ops, s1, s2)) + [cost] == row["out"][:4]
+    bc, bops, boff, blen, bst = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
+    assert bc[0] == cost and np.array_equal(_native.unpack_ops(bops, 0, int(blen[0])), ops)
+    assert info["launches"] == 2 and info["retraced_tiles"] >= 4
+    ctx.close()
+
+
+def test_find_global_alignment_routes_long_pairs(monkeypatch):
+    rec = golden("medium_cases.json")[1]            # 513 x 257 DNA
+    monkeypatch.setattr(globaligner, "LONG_PAIR_CELLS", 1000)
+    r = find_global_alignment(**rec["kw"])
+    assert [r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score] == rec["out"]
+    prot = golden("medium_cases.json")[3]           # protein, BLOSUM62
+    r = find_global_alignment(**prot["kw"])
+    assert [r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score] == prot["out"]
+
+
+def test_long_pair_20kb_canonical_path():
+    b = synth.dna_single(20000, 7001, 7002)
+    dense = batch.Scheme(**synth.SCHEMES["cfg4"]).dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    cost, ops, info = _check(ctx, dense, b.s1, b.s2[:18000].copy(), full_oracle=False)
+    assert rescore(ops, b.s1, b.s2[:18000], DenseView(dense)) == cost
+    only, _, _, _ = ctx.align_long(b.s1, b.s2[:18000].copy(), flags=_native.GA_F_COST_ONLY)
+    assert only == cost
+    ctx.close()
+
+
+def test_config4_100kb_linear_space():
+    """BASELINE configs[3]: one DNA pair 100 kb x 100 kb.  The reference cannot run it
+    (start.py:213 guard; ~1.6 TB of tuples); parity is against the linear-memory C oracle,
+    which re-decides every step of the returned path on forward values (canonical ties)."""
+    b = synth.workload("cfg4")
+    dense = batch.Scheme(**synth.SCHEMES["cfg4"]).dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    cost, ops, status, info = ctx.align_long(b.s1, b.s2)
+    assert status == 0 and info["cells"] == 10**10
+    assert info["checkpoint_bytes"] < 2.2e9            # vs 5 GB of stored direction codes
+    assert rescore(ops, b.s1, b.s2, DenseView(dense)) == cost
+    rc, vcost = c_oracle.verify_path(b.s1, b.s2, _oracle_dense(dense), ops)
+    assert rc == 0 and vcost == cost
+    # through the reference-facing entry point, with the length guard lifted
+    s1, s2 = b.pair(0)
+    with pytest.raises(RuntimeError):
+        find_global_alignment(seq_1=s1, seq_2=s2, **synth.SCHEMES["cfg4"])
+    with start.lifted_length_guard():
+        r = find_global_alignment(seq_1=s1, seq_2=s2, **synth.SCHEMES["cfg4"])
+    assert r.cost == cost and (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) == batch.render(ops, s1, s2)
+    ctx.close()
