@@ -1,0 +1,74 @@
+"""N > 1 host logic on CPU (gloo, world_size 2): contiguous pair shards, no data-path collective,
+max-over-ranks timing reduction and the optional gather of per-pair results."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from globalign_b200 import parallel, synth
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 2, 7, 100, 1_000_003):
+        for world in (1, 2, 3, 8):
+            got = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            sizes = [hi - lo for lo, hi in got]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n_pairs, out_dir):
+    import torch.distributed as dist
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from globalign_b200.batch import Scheme
+        from oracle import c_oracle
+        batch = synth.dna_fixed(n_pairs, 60, 4242)
+        lo, hi = parallel.shard_range(n_pairs, rank, world)
+        mine = batch.slice(lo, hi)
+        dense = Scheme(**synth.SCHEMES["cfg2"]).dense_for(list("ACGT"))
+        d = c_oracle.Dense.__new__(c_oracle.Dense)
+        d.A, d.sub, d.gap_h, d.gap_v, d.o, d.max_cost = dense.A, dense.sub, dense.gap_h, dense.gap_v, dense.gap_open, dense.max_cost
+        # stand-in for the per-rank GPU call: the shard's costs (the CPU checker is test infrastructure)
+        _, _, _, cost, _ = c_oracle.align_batch(mine.s1, mine.off1, mine.s2, mine.off2, d, 1)
+        allc = parallel.gather_int32(cost, n_pairs, rank, world)
+        # timing reduction used by bench.py: max over ranks, sum of cells
+        t = torch.tensor([float(rank + 1), float(mine.cells())], dtype=torch.float64)
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        np.save(os.path.join(out_dir, f"cost_{rank}.npy"), allc)
+        np.save(os.path.join(out_dir, f"red_{rank}.npy"), np.array([mx[0].item(), sm[1].item()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shards_and_gather(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import c_oracle
+    from globalign_b200.batch import Scheme
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    n_pairs, world = 37, 2
+    mp.spawn(_worker, args=(world, port, n_pairs, str(tmp_path)), nprocs=world, join=True)
+    batch = synth.dna_fixed(n_pairs, 60, 4242)
+    dense = Scheme(**synth.SCHEMES["cfg2"]).dense_for(list("ACGT"))
+    d = c_oracle.Dense.__new__(c_oracle.Dense)
+    d.A, d.sub, d.gap_h, d.gap_v, d.o, d.max_cost = dense.A, dense.sub, dense.gap_h, dense.gap_v, dense.gap_open, dense.max_cost
+    _, _, _, full, _ = c_oracle.align_batch(batch.s1, batch.off1, batch.s2, batch.off2, d, 1)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"cost_{r}.npy"), full)
+        red = np.load(tmp_path / f"red_{r}.npy")
+        assert red[0] == world and red[1] == batch.cells()
+
+
+def test_bench_shards_are_disjoint_blocks():
+    """bench.py gives rank r the blocks [r*B, (r+1)*B) of the virtual N-GPU batch."""
+    per_rank = 2 * synth._BLOCK
+    whole = synth.dna_fixed(2 * per_rank, 150, 2000)
+    r1 = synth.dna_fixed(per_rank, 150, 2000, first_block=2)
+    assert np.array_equal(whole.slice(per_rank, 2 * per_rank).s1, r1.s1)
+    assert np.array_equal(whole.slice(per_rank, 2 * per_rank).s2, r1.s2)
