@@ -70,6 +70,16 @@ def parse_args():
 
 
 # ----------------------------------------------------------------------------- helpers
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic_r1.json)."""
+    p = ROOT / "profiles" / "traffic_r1.json"
+    try:
+        e = json.loads(p.read_text()).get(kernel)
+    except (OSError, ValueError):
+        e = None
+    return e
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -485,11 +495,13 @@ def run_ours(args, rank, world, local_rank):
                      "frac_of_nominal_18.6": achieved_tops / NOMINAL_INT32_TOPS,
                      "ops_per_cell": OPS_PER_CELL, "fill_gcups": fill_gcups,
                      "measured_mix_tinstr_s": mix_measured, "measured_vimnmx3_s16x2_tinstr_s": vimnmx3,
-                     "traffic": None},
+                     "traffic": (ncu_traffic(info["fill_kernel"]) or {}).get("dram_bytes"),
+                     "traffic_capture": ncu_traffic(info["fill_kernel"])},
         "roofline_hbm": {"bound": "hbm", "kernel": info["fill_kernel"] + " (direction-code store)",
                          "achieved": cells * CODE_BYTES_PER_CELL / (fms / 1e3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": cells * CODE_BYTES_PER_CELL / (fms / 1e3) / 1e9 / hbm_peak,
-                         "peak_source": hbm_src, "stored_bytes_per_step": info["code_bytes"], "traffic": None},
+                         "peak_source": hbm_src, "stored_bytes_per_step": info["code_bytes"],
+                         "traffic": (ncu_traffic(info["fill_kernel"]) or {}).get("dram_bytes")},
     }
     if world == 1 and not args.no_cpu_baseline:
         g, ns, dt, th = cpu_port_gcups(batch, dense, remap)
