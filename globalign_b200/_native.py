@@ -27,7 +27,7 @@ EXPORTS = (
     "ga_version", "ga_device_count", "ga_ctx_create", "ga_ctx_destroy", "ga_last_error",
     "ga_ctx_set_stream", "ga_ctx_set_scratch_limit", "ga_set_scheme", "ga_align_batch",
     "ga_plan_batch", "ga_run_batch", "ga_sync", "ga_get_plan_info", "ga_get_timing",
-    "ga_fill_values", "ga_alu_peak", "ga_align_long",
+    "ga_fill_values", "ga_alu_peak", "ga_align_long", "ga_align_replay",
 )
 
 
@@ -81,6 +81,8 @@ def lib():
     L.ga_alu_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.ga_align_long.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
                                 C.POINTER(i32), u32, C.POINTER(LongInfo)]
+    L.ga_align_replay.argtypes = [vp, vp, i64, vp, i64, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
+                                  C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTS:
         if name not in ("ga_last_error",):
             getattr(L, name).restype = C.c_int
@@ -232,6 +234,21 @@ class Context:
         if flags & GA_F_COST_ONLY:
             return cost.value, None, 0, d
         return cost.value, unpack_ops(packed, 0, nops.value), status.value, d
+
+
+    def align_replay(self, s1, s2, draws):
+        """One pair with the reference's random tie-breaking replayed from `draws`
+        (uint16 per traceback step) -> (cost, ops walk order, n_eval, status)."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        draws = np.ascontiguousarray(draws, dtype=np.uint16)
+        m, n = len(s1), len(s2)
+        packed = np.zeros(4 * ((m + n + 15) // 16) + 16, dtype=np.uint8)
+        cost, nops, neval, status = C.c_int32(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self._L.ga_align_replay(self._h, _ptr(s1), m, _ptr(s2), n, _ptr(draws), len(draws),
+                                            C.byref(cost), _ptr(packed), C.byref(nops), C.byref(neval),
+                                            C.byref(status)))
+        return cost.value, unpack_ops(packed, 0, nops.value), neval.value, status.value
 
 
 def ops_offsets(off1, off2) -> np.ndarray:

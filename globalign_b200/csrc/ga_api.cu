@@ -851,6 +851,115 @@ extern "C" int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const u
     return GA_OK;
 }
 
+// ------------------------------------------------------------------ seeded replay of random ties
+// The reference breaks traceback ties with random.choice (globaligner.py:595-685): every
+// dispatcher call draws 18 choices (9 for the is_match=True keys, 9 for the False keys), of
+// which at most one is live.  The host emulates CPython's draws and passes, per evaluated
+// cell, eight 2-bit option indices: bits 0-7 for is_match=True, bits 8-15 for False; within a
+// byte: all three tied (options 0,1,2) | levels 0,1 tied (0,1) | 0,2 tied (0,2) | 1,2 tied (1,2).
+// One thread walks the full value table (ga_fill_values' kernel) ranking values as
+// dp_array_backward does (:425-581).  Single pairs only; not a throughput path.
+__global__ void replay_walk_kernel(const SchemeDev sc, const uint8_t *s1, int m, const uint8_t *s2, int n,
+                                   const int *tab, const uint16_t *draws, uint32_t *ops_out,
+                                   long long *n_ops_out, int *n_eval_out, int *status_out, int *cost_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int W = n + 1;
+    const long long o = sc.o;
+    long long nops = 0;
+    uint32_t word = 0;
+    int n_eval = 0, status = 0;
+    auto emit = [&](int op) {
+        word |= (uint32_t)op << (2 * (int)(nops & 15));
+        if ((++nops & 15) == 0) { ops_out[(nops >> 4) - 1] = word; word = 0; }
+    };
+    const int *corner = tab + ((size_t)m * W + n) * 3;
+    *cost_out = min(min(corner[0], corner[1]), corner[2]);
+    int i = m, j = n, level = 0;
+    while (status == 0) {
+        if (i == 0 && j == 0) break;                       // :460 and the loop's natural end
+        // the shortcut tests (:542-581) follow every move except the first one, so a boundary
+        // cell reached by the very first move is still ranked once (18 more draws)
+        if (n_eval >= 2 && (i == 0 || j == 0)) break;
+        const int *c = tab + ((size_t)i * W + j) * 3;
+        long long v0 = c[0], v1 = c[1], v2 = c[2];
+        if (level == 1) { v0 += o; v2 += o; } else if (level == 2) { v0 += o; v1 += o; }
+        const long long lo = min(min(v0, v1), v2);
+        const int t0 = v0 == lo, t1 = v1 == lo, t2 = v2 == lo;
+        // Python's negative index wraps: seq[-1] is the last letter (only at a boundary cell)
+        const int ai = i >= 1 ? i - 1 : m - 1, bj = j >= 1 ? j - 1 : n - 1;
+        const int is_match = s1[ai] == s2[bj];
+        const unsigned d = draws[n_eval] >> (is_match ? 0 : 8);
+        ++n_eval;
+        int k;
+        if (t0 && t1 && t2) k = (int)(d & 3u);                       // options (0, 1, 2)
+        else if (t0 && t1) k = (int)((d >> 2) & 3u);                  // (0, 1)
+        else if (t0 && t2) k = ((d >> 4) & 3u) ? 2 : 0;               // (0, 2)
+        else if (t1 && t2) k = ((d >> 6) & 3u) ? 2 : 1;               // (1, 2)
+        else k = t0 ? 0 : (t1 ? 1 : 2);
+        if ((i == 0 && k != 1) || (j == 0 && k != 2)) { status = 1; break; }   // reference leaves the table
+        emit(k);
+        if (k == 0) { --i; --j; } else if (k == 1) { --j; } else { --i; }
+        level = k;
+    }
+    if (status == 0) {
+        for (; j > 0 && i == 0; --j) emit(1);
+        for (; i > 0 && j == 0; --i) emit(2);
+    }
+    if (nops & 15) ops_out[nops >> 4] = word;
+    *n_ops_out = nops;
+    *n_eval_out = n_eval;
+    *status_out = status;
+}
+
+extern "C" int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                               const uint16_t *draws, int64_t n_draws, int32_t *out_cost, uint8_t *out_ops,
+                               int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
+    if (!ctx) return GA_E_ARG;
+    if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
+    if (!s1 || !s2 || !draws || !out_cost || !out_ops || !out_n_ops || !out_n_eval || !out_status || m < 1 ||
+        n < 1 || n_draws < m + n || (m + 1) * (n + 1) > (int64_t)60'000'000)
+        return fail(ctx, GA_E_ARG, "ga_align_replay: single pairs up to 6e7 table cells, m+n draws");
+    {
+        const long long big = (long long)(ctx->sc.max_cost + 1) * std::max(m, n);
+        if (big + (m + n + 2) * (long long)ctx->sc.max_cost + 3LL * ctx->sc.o >= 0x7fffffffLL)
+            return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t tb = (size_t)(m + 1) * (n + 1) * 3 * 4;
+    const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
+    uint8_t *d1 = nullptr, *d2 = nullptr;
+    int *dt = nullptr, *dmisc = nullptr;
+    uint16_t *dd = nullptr;
+    uint32_t *dops = nullptr;
+    CK(cudaMalloc(&d1, m));
+    CK(cudaMalloc(&d2, n));
+    CK(cudaMalloc(&dt, tb));
+    CK(cudaMalloc(&dd, (size_t)n_draws * 2));
+    CK(cudaMalloc(&dops, ops_words * 4));
+    CK(cudaMalloc(&dmisc, 64));
+    CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dd, draws, (size_t)n_draws * 2, cudaMemcpyHostToDevice, st));
+    values_kernel<<<1, 1024, 0, st>>>(ctx->sc, d1, (int)m, d2, (int)n, 0, dt);
+    CK(cudaGetLastError());
+    replay_walk_kernel<<<1, 32, 0, st>>>(ctx->sc, d1, (int)m, d2, (int)n, dt, dd, dops,
+                                         (long long *)(dmisc + 2), dmisc, dmisc + 1, dmisc + 4);
+    CK(cudaGetLastError());
+    int hm[8] = {};
+    CK(cudaMemcpyAsync(hm, dmisc, sizeof hm, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long nops = 0;
+    memcpy(&nops, hm + 2, 8);
+    *out_n_eval = hm[0];
+    *out_status = hm[1];
+    *out_cost = hm[4];
+    *out_n_ops = nops;
+    CK(cudaMemcpy(out_ops, dops, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d1); cudaFree(d2); cudaFree(dt); cudaFree(dd); cudaFree(dops); cudaFree(dmisc);
+    return GA_OK;
+}
+
 // ------------------------------------------------------------------ integer-ALU roofline probe
 // No memory traffic: how many of the fill kernel's instruction kinds the SMs retire per
 // second.  Throughput modes use 8 independent chains per thread:

@@ -26,6 +26,63 @@ from .start import get_max_val, make_matrix, validate_and_transform_args
 __all__ = ["find_global_alignment", "make_dp_array", "dp_array_forward", "dp_array_backward", "main"]
 
 
+#: "canonical" (default): ties between co-optimal alignments go to the first option listed in
+#: the reference's table (match/mismatch, gap in seq_1, gap in seq_2).  "reference_random":
+#: reproduce the reference's random.choice tie-breaking draw for draw, consuming the global
+#: ``random`` state exactly as it does -- after ``random.seed(s)`` the result equals the
+#: unpatched reference's (single pairs; slower: full value table on the device).
+TIE_BREAKING = "canonical"
+
+_DRAW_SIZES = (3, 2, 2, 2, 3, 2, 2, 2, 3)      # random.choice sizes in dict-literal order (:599-634)
+
+
+def _reference_draws(n_steps: int):
+    """Emulate the 18 random.choice calls cost_ranks_dispatcher makes per step
+    (globaligner.py:599-671) on the global ``random`` state.  CPython: choice(seq) =
+    seq[_randbelow(len(seq))], _randbelow(n) = rejection sampling of getrandbits(n.bit_length())
+    -- 2 bits for both n = 2 and n = 3 -- one Mersenne-Twister word per getrandbits call.
+    -> (uint16 draws per step, cumulative MT words consumed after each step)."""
+    import random
+    grb = random.getrandbits
+    draws = np.zeros(n_steps, dtype=np.uint16)
+    words = np.zeros(n_steps + 1, dtype=np.int64)
+    used = 0
+    for s in range(n_steps):
+        packed = 0
+        for half in range(2):
+            for k, size in enumerate(_DRAW_SIZES):
+                r = grb(2)
+                used += 1
+                while r >= size:
+                    r = grb(2)
+                    used += 1
+                if k < 4:
+                    packed |= r << (8 * half + 2 * k)
+        draws[s] = packed
+        words[s + 1] = used
+    return draws, words
+
+
+def _align_one_replay(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: int, device: int = 0):
+    import random
+    dense = DenseScheme(costing_mat, gap_open_cost)
+    ctx = _native.default_context(device)
+    ctx.set_scheme(dense)
+    s1, s2 = dense.encode(seq_1), dense.encode(seq_2)
+    state = random.getstate()
+    draws, words = _reference_draws(len(s1) + len(s2))
+    cost, ops, n_eval, status = ctx.align_replay(s1, s2, draws)
+    # leave the global generator exactly where the reference would have left it
+    random.setstate(state)
+    if words[n_eval]:
+        random.getrandbits(32 * int(words[n_eval]))
+    if status != 0:
+        raise ReferenceUndefinedError(
+            "the reference's traceback leaves the DP table for this input "
+            "(max(len(seq_1), len(seq_2)) <= gap_open_cost)")
+    return ops, cost
+
+
 #: pairs with at least this many DP cells go to the whole-chip band pipeline with
 #: linear-space traceback (ga_align_long) instead of the one-warp batched kernel
 LONG_PAIR_CELLS = 1 << 22
@@ -81,7 +138,12 @@ def find_global_alignment(
         input_fasta, output, seq_1, seq_2, scoring_mat_name, scoring_mat_path, match_score,
         mismatch_score, mismatch_cost, gap_open_score, gap_open_cost, gap_extension_score,
         gap_extension_cost)
-    ops, cost = _align_one(seq_1, seq_2, costing_mat, gap_open_cost)
+    if TIE_BREAKING == "reference_random":
+        ops, cost = _align_one_replay(seq_1, seq_2, costing_mat, gap_open_cost)
+    elif TIE_BREAKING == "canonical":
+        ops, cost = _align_one(seq_1, seq_2, costing_mat, gap_open_cost)
+    else:
+        raise ValueError("TIE_BREAKING must be 'canonical' or 'reference_random'")
     seq_1_aligned, middle_part, seq_2_aligned = render(ops, seq_1, seq_2)
     score = final_cost_to_score(cost=cost, m=len(seq_1), n=len(seq_2),
                                 max_score=get_max_val(scoring_mat))

@@ -157,6 +157,19 @@ int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, 
 int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                    int keep_boundary, int32_t *table);
 
+/* Seeded replay of the reference's RANDOM tie-breaking for one pair.
+ * cost_ranks_dispatcher (globaligner.py:595-685) draws 18 random.choice values per traceback
+ * step; the caller emulates those draws (CPython: choice = seq[_randbelow(len)], rejection
+ * sampling on getrandbits(2)) and passes per evaluated cell a uint16: bits 0-7 for
+ * is_match = True, bits 8-15 for False; within the byte four 2-bit option indices for the tie
+ * patterns {all three tied -> options (0,1,2); levels 0,1 tied -> (0,1); 0,2 tied -> (0,2);
+ * 1,2 tied -> (1,2)}.  The device fills the full value table and one thread walks it ranking
+ * values exactly as dp_array_backward does (:425-581).  out_n_eval = dispatcher calls made
+ * (= draws consumed).  Not a throughput path: (m+1)*(n+1) <= 6e7. */
+int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                    const uint16_t *draws, int64_t n_draws, int32_t *out_cost, uint8_t *out_ops,
+                    int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status);
+
 /* Integer-ALU roofline microbenchmark (no memory traffic): giga-instructions/s the
  * device retires of one instruction kind.  Throughput modes (8 independent chains per
  * thread): 0 IADD, 1 VIMNMX3.S16x2, 2 VIMNMX3 (s32), 3 LOP3, 4 IMAD, 5 the packed fill

@@ -294,6 +294,7 @@ def main():
         try:
             random.seed(seed)
             r = run_ref(kw)
+            next_random = random.random()      # fingerprint of the generator state the reference leaves
         except Exception:
             random.setstate(state)
             continue
@@ -307,7 +308,7 @@ def main():
         got = py_oracle.render(ops, s1, s2)
         assert got == (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) and cost == r.cost, kw
         assert py_oracle.admissible(ops, s1, s2, r.costing_mat, r.gap_open_cost, table)
-        seeded.append({"kw": portable(kw), "seed": seed, "out": out_of(r)})
+        seeded.append({"kw": portable(kw), "seed": seed, "out": out_of(r), "next_random": next_random})
     canonical(True)
     (HERE / "seeded_cases.json").write_text(json.dumps(seeded, ensure_ascii=True))
 

@@ -339,3 +339,24 @@ def test_config2_full_size_properties():
         c = b.s2[b.off2[k]:b.off2[k + 1]]
         assert rescore(got, a, c, dv) == cost[k]
     ctx.close()
+
+
+# ------------------------------------------------------------------ f1: seeded replay of random ties
+def test_seeded_replay_reproduces_unpatched_reference(monkeypatch):
+    """With TIE_BREAKING = 'reference_random', random.seed(s) + find_global_alignment gives what the
+    UNPATCHED (randomly tie-breaking) reference gave for the same seed, and leaves the global
+    generator in the same state (fingerprint: the next random.random())."""
+    monkeypatch.setattr(globaligner, "TIE_BREAKING", "reference_random")
+    cases = golden("seeded_cases.json")
+    differs_from_canonical = 0
+    for rec in cases:
+        random.seed(rec["seed"])
+        r = find_global_alignment(**fix_paths(rec["kw"]))
+        assert [r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score] == rec["out"], rec["kw"]
+        assert random.random() == rec["next_random"]
+    monkeypatch.setattr(globaligner, "TIE_BREAKING", "canonical")
+    for rec in cases[:60]:
+        r = find_global_alignment(**fix_paths(rec["kw"]))
+        assert r.cost == rec["out"][3]
+        differs_from_canonical += [r.seq_1_aligned, r.seq_2_aligned] != [rec["out"][0], rec["out"][2]]
+    assert differs_from_canonical > 3          # the seeded runs really exercise random ties

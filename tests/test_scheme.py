@@ -141,3 +141,30 @@ def test_synth_prefix_stable_and_shapes():
     assert c1.lens()[0][0] == 1000 and c1.lens()[1][0] == 1000
     sl = b.slice(10, 20)
     assert sl.pair(0) == b.pair(10) and sl.n_pairs == 10
+
+
+def test_reference_draw_emulation_matches_cpython_choice():
+    """globaligner._reference_draws consumes the global Mersenne Twister exactly like the 18
+    random.choice calls of the reference's cost_ranks_dispatcher (sizes 3,2,2,2,3,2,2,2,3 twice)."""
+    import random
+    from globalign_b200 import globaligner
+    sizes = (3, 2, 2, 2, 3, 2, 2, 2, 3)
+    for seed in (0, 1, 12345):
+        random.seed(seed)
+        draws, words = globaligner._reference_draws(40)
+        after_mine = random.random()
+        random.seed(seed)
+        for s in range(40):
+            got = [random.choice(range(size)) for _ in range(2) for size in sizes]
+            for half in range(2):
+                for k in range(4):
+                    assert (int(draws[s]) >> (8 * half + 2 * k)) & 3 == got[9 * half + k]
+        assert random.random() == after_mine
+        # advancing by `words` 32-bit outputs reproduces the state after s steps
+        random.seed(seed)
+        random.getrandbits(32 * int(words[17]))
+        a = random.random()
+        random.seed(seed)
+        for s in range(17):
+            [random.choice(range(size)) for _ in range(2) for size in sizes]
+        assert random.random() == a
