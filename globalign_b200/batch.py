@@ -75,6 +75,16 @@ class BatchAlignment:
     def __iter__(self):
         return (self[k] for k in range(len(self)))
 
+    def write(self, file, descs=None, chars_per_line: int = 70):
+        """Write every alignment, one after the other, in the reference's printout format
+        (AlignmentResults.__str__, conclude.py:19-89).  `descs`: optional list of
+        (desc_1, desc_2) per pair (e.g. FASTA header lines)."""
+        with open(file, mode="w+") as fh:
+            for k in range(len(self)):
+                d1, d2 = descs[k] if descs is not None else (f"seq_1[{k}]", f"seq_2[{k}]")
+                fh.write(self[k].__str__(desc_1=d1, desc_2=d2, chars_per_line=chars_per_line))
+                fh.write("\n")
+
 
 class Scheme:
     """A resolved scoring/costing scheme, independent of any particular pair."""
@@ -160,6 +170,31 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=
     cost, ops, ops_off, ops_len, status = ctx.align_batch(
         np.concatenate(enc1), off1, np.concatenate(enc2), off2)
     return BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme)
+
+
+def read_pairs_from_fasta(fasta_path, fasta_path_2=None):
+    """Batched FASTA ingestion.  One file: consecutive records are paired
+    (1st with 2nd, 3rd with 4th, ...; the reference reads only the first two,
+    start.py:666-688).  Two files: record k of the first with record k of the second.
+    -> (descs [(desc_1, desc_2)], seqs_1, seqs_2), sequences upper-cased as the reference's
+    reader does (start.py:643)."""
+    recs = list(start.read_seq_from_fasta(fasta_path))
+    if fasta_path_2 is None:
+        if len(recs) < 2 or len(recs) % 2:
+            raise RuntimeError("the FASTA file must hold an even, non-zero number of records")
+        left, right = recs[0::2], recs[1::2]
+    else:
+        left, right = recs, list(start.read_seq_from_fasta(fasta_path_2))
+        if len(left) != len(right) or not left:
+            raise RuntimeError("the two FASTA files must hold the same, non-zero number of records")
+    descs = [(a[0], b[0]) for a, b in zip(left, right)]
+    return descs, [a[1] for a in left], [b[1] for b in right]
+
+
+def find_global_alignments_from_fasta(fasta_path, fasta_path_2=None, **kwargs):
+    """-> (descs, BatchAlignment) for every record pair of the file(s)."""
+    descs, s1, s2 = read_pairs_from_fasta(fasta_path, fasta_path_2)
+    return descs, find_global_alignments(s1, s2, **kwargs)
 
 
 def align_encoded(batch, scheme_kwargs: dict, *, device: int = 0, flags: int = 0):

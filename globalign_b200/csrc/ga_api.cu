@@ -8,7 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/globalign_b200.h"
@@ -25,10 +28,10 @@ struct KernelCfg {
     bool simple;
     const void *fill_fn;
     void (*launch_fill)(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
-                        const TileDesc *tiles, int n_tiles, int *counter, const uint8_t *s1,
+                        const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const uint8_t *s1,
                         const long long *off1, const uint8_t *s2, const long long *off2,
                         uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost);
-    void (*launch_walk)(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, int pair_lo,
+    void (*launch_walk)(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, const UniformTiles &ut, int pair_lo,
                         int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
                         const long long *off2, const uint32_t *codes, uint8_t *out_ops,
                         const long long *ops_off, int *out_len, int *out_status);
@@ -36,19 +39,19 @@ struct KernelCfg {
 
 template <bool P, bool S, int R, int G>
 static void launch_fill_t(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
-                          const TileDesc *tiles, int n_tiles, int *counter, const uint8_t *s1,
+                          const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const uint8_t *s1,
                           const long long *off1, const uint8_t *s2, const long long *off2,
                           uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost) {
-    fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, n_tiles, counter, s1, off1, s2, off2,
+    fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, ut, n_tiles, counter, s1, off1, s2, off2,
                                                      codes, bnd, bnd_stride, sb_stride, out_cost);
 }
 template <bool P, int R, int G>
-static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, int pair_lo,
+static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, const UniformTiles &ut, int pair_lo,
                           int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
                           const long long *off2, const uint32_t *codes, uint8_t *out_ops,
                           const long long *ops_off, int *out_len, int *out_status) {
     const int grid = (n_pairs + 127) / 128;
-    walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, pair_lo, n_pairs, s1, off1, s2, off2, codes,
+    walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, ut, pair_lo, n_pairs, s1, off1, s2, off2, codes,
                                                out_ops, ops_off, out_len, out_status);
 }
 template <bool P, bool S, int R, int G>
@@ -114,6 +117,7 @@ struct ga_ctx {
     // pipeline streams: two fill streams (alternating chunks, so the tail of one chunk
     // overlaps the start of the next), two walk streams, copy-in and copy-out
     cudaStream_t aux[6] = {};
+    cudaEvent_t in_piece[8] = {}, in_begin = nullptr;   // host-buffer entry point: upload pieces
     std::string err;
     int64_t scratch_limit = (int64_t)64 << 30;
     int sm_count = 0;
@@ -134,6 +138,9 @@ struct ga_ctx {
     int64_t cells = 0, code_bytes = 0;
     uint32_t plan_flags = 0;
     bool serial = false;
+    bool uniform = false;             // every pair has the same (m, n): arithmetic tile descriptors
+    int uniM = 0, uniN = 0;
+    long long uni_u4 = 0;
     DevBuf d_tiles, d_codes[2], d_bnd[2], d_counter;
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
@@ -145,6 +152,31 @@ struct ga_ctx {
     float ms[GA_T_COUNT] = {};
     bool timing_valid = false, timing_io = false;
 };
+
+// GA_DEBUG_TIMING=1: host-side phase times on stderr (diagnostics)
+struct HostTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer() : on(getenv("GA_DEBUG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ga host] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+// Split [0, n) over a few host threads (planner loops over 10^6 pairs).
+template <typename F>
+static void parallel_for(int64_t n, F body) {
+    const int64_t min_grain = 1 << 16;
+    int T = (int)std::min<int64_t>(std::max(1u, std::min(8u, std::thread::hardware_concurrency())),
+                                   (n + min_grain - 1) / min_grain);
+    if (T <= 1) { body(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back([=] { body(t, n * t / T, n * (t + 1) / T); });
+    for (auto &x : th) x.join();
+}
 
 static int fail(ga_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -201,6 +233,8 @@ extern "C" int ga_ctx_create(int device, ga_ctx **out) {
     for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &e : ctx->in_piece) cudaEventCreate(&e);
+    cudaEventCreate(&ctx->in_begin);
     *out = ctx;
     return GA_OK;
 }
@@ -217,6 +251,8 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
                       &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc})
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->in_piece) if (e) cudaEventDestroy(e);
+    if (ctx->in_begin) cudaEventDestroy(ctx->in_begin);
     for (auto &c : ctx->cev)
         for (cudaEvent_t e : {c.in0, c.in1, c.f0, c.f1, c.w0, c.w1, c.out0, c.out1}) cudaEventDestroy(e);
     for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
@@ -357,24 +393,50 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     if (!s1_off || !s2_off || n_pairs < 1 || n_pairs > 0x7fffff00LL)
         return fail(ctx, GA_E_ARG, "bad batch (1 <= n_pairs < 2^31)");
     CK(cudaSetDevice(ctx->device));
+    HostTimer ht;
     ctx->have_plan = false;
     for (float &v : ctx->ms) v = 0.f;
-    int maxM = 0, maxN = 0;
+    int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30;
     int64_t cells = 0;
-    for (int64_t p = 0; p < n_pairs; ++p) {
-        const int64_t m = s1_off[p + 1] - s1_off[p], n = s2_off[p + 1] - s2_off[p];
-        if (m < 1 || n < 1) return fail(ctx, GA_E_ARG, "pair %lld has an empty sequence", (long long)p);
-        if (m > (1 << 24) || n > (1 << 15))
-            return fail(ctx, GA_E_ARG, "pair %lld too long for the batched kernels (m <= 2^24, n <= 32768); use ga_align_long", (long long)p);
-        if (out_ops_off && !(flags & GA_F_COST_ONLY)) {
-            const int64_t need = (((m + n + 3) / 4) + 3) & ~(int64_t)3;
-            if ((out_ops_off[p] & 3) || out_ops_off[p + 1] - out_ops_off[p] < need)
-                return fail(ctx, GA_E_ARG, "ops slice of pair %lld is too small or misaligned", (long long)p);
+    {
+        struct Part { int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30; int64_t cells = 0, bad = -1; int why = 0; };
+        Part parts[8];
+        const bool check_ops = out_ops_off && !(flags & GA_F_COST_ONLY);
+        parallel_for(n_pairs, [&](int t, int64_t lo, int64_t hi) {
+            Part a;
+            for (int64_t p = lo; p < hi; ++p) {
+                const int64_t m = s1_off[p + 1] - s1_off[p], n = s2_off[p + 1] - s2_off[p];
+                int why = 0;
+                if (m < 1 || n < 1) why = 1;
+                else if (m > (1 << 24) || n > (1 << 15)) why = 2;
+                else if (check_ops) {
+                    const int64_t need = (((m + n + 3) / 4) + 3) & ~(int64_t)3;
+                    if ((out_ops_off[p] & 3) || out_ops_off[p + 1] - out_ops_off[p] < need) why = 3;
+                }
+                if (why) { if (a.bad < 0) { a.bad = p; a.why = why; } continue; }
+                a.maxM = std::max<int>(a.maxM, (int)m);
+                a.maxN = std::max<int>(a.maxN, (int)n);
+                a.minM = std::min<int>(a.minM, (int)m);
+                a.minN = std::min<int>(a.minN, (int)n);
+                a.cells += m * n;
+            }
+            parts[t] = a;
+        });
+        for (const Part &a : parts) {
+            if (a.bad >= 0) {
+                static const char *msg[] = {"", "has an empty sequence",
+                    "is too long for the batched kernels (m <= 2^24, n <= 32768); use ga_align_long",
+                    "has an ops slice that is too small or misaligned"};
+                return fail(ctx, GA_E_ARG, "pair %lld %s", (long long)a.bad, msg[a.why]);
+            }
+            maxM = std::max(maxM, a.maxM);
+            maxN = std::max(maxN, a.maxN);
+            minM = std::min(minM, a.minM);
+            minN = std::min(minN, a.minN);
+            cells += a.cells;
         }
-        maxM = std::max<int>(maxM, (int)m);
-        maxN = std::max<int>(maxN, (int)n);
-        cells += m * n;
     }
+    ht.lap("plan: scan pairs");
     const KernelCfg *cfg = choose_cfg(ctx, maxM, maxN, flags);
     if (!cfg) return fail(ctx, GA_E_ARG, "no usable kernel configuration (GA_FORCE_CFG names an unknown kernel or one whose value range / scheme kind does not fit)");
     const LayInfo &L = cfg->lay;
@@ -388,28 +450,49 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
         return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
     // tiles: consecutive groups of PPT pairs
     const int64_t n_tiles = (n_pairs + L.PPT - 1) / L.PPT;
-    ctx->tiles.resize((size_t)n_tiles);
+    const bool uniform = (minM == maxM && minN == maxN);
     ctx->chunks.clear();
-    std::vector<long long> tile_u4((size_t)n_tiles);
-    long long total_u4 = 0, biggest = 0;
-    for (int64_t t = 0; t < n_tiles; ++t) {
-        TileDesc &td = ctx->tiles[(size_t)t];
-        const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
-        int M = 0, N = 0;
-        for (int64_t p = lo; p < hi; ++p) {
-            M = std::max<int>(M, (int)(s1_off[p + 1] - s1_off[p]));
-            N = std::max<int>(N, (int)(s2_off[p + 1] - s2_off[p]));
-        }
-        const long long npass = (M + L.BAND - 1) / L.BAND;
-        const long long nTB = (N + L.G - 1 + L.S - 1) / L.S;
-        tile_u4[(size_t)t] = npass * nTB * L.NQ * 32;
-        total_u4 += tile_u4[(size_t)t];
-        biggest = std::max(biggest, tile_u4[(size_t)t]);
-        td.first_pair = (int)lo;
-        td.n_pairs = (int)(hi - lo);
-        td.M = M;
-        td.N = N;
+    std::vector<long long> tile_u4;
+    long long total_u4 = 0, biggest = 0, uni_u4 = 0;
+    if (uniform) {
+        // every tile is the same: no descriptor array, the kernels compute them (UniformTiles)
+        const long long npass = (maxM + L.BAND - 1) / L.BAND;
+        const long long nTB = (maxN + L.G - 1 + L.S - 1) / L.S;
+        uni_u4 = npass * nTB * L.NQ * 32;
+        total_u4 = uni_u4 * n_tiles;
+        biggest = uni_u4;
+        ctx->tiles.clear();
+    } else {
+        ctx->tiles.resize((size_t)n_tiles);
+        tile_u4.resize((size_t)n_tiles);
+        long long part_total[8] = {}, part_big[8] = {};
+        TileDesc *tiles = ctx->tiles.data();
+        parallel_for(n_tiles, [&](int tid, int64_t tlo, int64_t thi) {
+            long long tot = 0, big = 0;
+            for (int64_t t = tlo; t < thi; ++t) {
+                TileDesc &td = tiles[t];
+                const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
+                int M = 0, N = 0;
+                for (int64_t p = lo; p < hi; ++p) {
+                    M = std::max<int>(M, (int)(s1_off[p + 1] - s1_off[p]));
+                    N = std::max<int>(N, (int)(s2_off[p + 1] - s2_off[p]));
+                }
+                const long long npass = (M + L.BAND - 1) / L.BAND;
+                const long long nTB = (N + L.G - 1 + L.S - 1) / L.S;
+                tile_u4[(size_t)t] = npass * nTB * L.NQ * 32;
+                tot += tile_u4[(size_t)t];
+                big = std::max(big, tile_u4[(size_t)t]);
+                td.first_pair = (int)lo;
+                td.n_pairs = (int)(hi - lo);
+                td.M = M;
+                td.N = N;
+            }
+            part_total[tid] = tot;
+            part_big[tid] = big;
+        });
+        for (int k = 0; k < 8; ++k) { total_u4 += part_total[k]; biggest = std::max(biggest, part_big[k]); }
     }
+    ht.lap("plan: tiles");
     // Chunks: the direction codes of a chunk live in one of two scratch buffers, so
     // the walk of chunk c overlaps the fill of chunk c+1.  Large batches are cut into
     // ~4 chunks (more if the scratch limit requires); GA_F_SERIAL keeps one stream
@@ -425,23 +508,35 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     }
     Chunk cur{0, 0, 0, 0, 0};
     long long max_chunk_u4 = 0;
-    for (int64_t t = 0; t < n_tiles; ++t) {
-        const long long u4 = tile_u4[(size_t)t];
-        if (cur.code_u4 + u4 > limit_u4 && cur.code_u4 > 0) {
-            cur.tile_hi = (int)t;
-            cur.pair_hi = (int)(t * L.PPT);
-            ctx->chunks.push_back(cur);
-            max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
-            cur = Chunk{(int)t, 0, (int)(t * L.PPT), 0, 0};
+    if (uniform) {
+        const int64_t per_chunk = std::max<int64_t>(1, limit_u4 / uni_u4);       // tiles per chunk
+        for (int64_t t = 0; t < n_tiles; t += per_chunk) {
+            const int64_t thi = std::min(n_tiles, t + per_chunk);
+            Chunk c{(int)t, (int)thi, (int)(t * L.PPT), (int)std::min<int64_t>(n_pairs, thi * L.PPT),
+                    (thi - t) * uni_u4};
+            ctx->chunks.push_back(c);
+            max_chunk_u4 = std::max(max_chunk_u4, c.code_u4);
         }
-        ctx->tiles[(size_t)t].code_off = cur.code_u4;
-        cur.code_u4 += u4;
+    } else {
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const long long u4 = tile_u4[(size_t)t];
+            if (cur.code_u4 + u4 > limit_u4 && cur.code_u4 > 0) {
+                cur.tile_hi = (int)t;
+                cur.pair_hi = (int)(t * L.PPT);
+                ctx->chunks.push_back(cur);
+                max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
+                cur = Chunk{(int)t, 0, (int)(t * L.PPT), 0, 0};
+            }
+            ctx->tiles[(size_t)t].code_off = cur.code_u4;
+            cur.code_u4 += u4;
+        }
+        cur.tile_hi = (int)n_tiles;
+        cur.pair_hi = (int)n_pairs;
+        ctx->chunks.push_back(cur);
+        max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
     }
-    cur.tile_hi = (int)n_tiles;
-    cur.pair_hi = (int)n_pairs;
-    ctx->chunks.push_back(cur);
-    max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
 
+    ht.lap("plan: chunks");
     // launch geometry
     const int warps = 4;
     ctx->sb_stride = ((maxN + L.G - 1 + L.S + 1 + 16) + 15) & ~15;
@@ -458,16 +553,20 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     const long long want_blocks = (n_tiles + warps - 1) / warps;
     ctx->grid = (int)std::min<long long>(want_blocks, (long long)per_sm * ctx->sm_count);
     int rc;
-    if ((rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
+    if (!uniform && (rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
+    ht.lap("plan: occupancy query");
     const int n_bufs = (serial || ctx->chunks.size() == 1) ? 1 : 2;
     for (int b = 0; b < n_bufs; ++b) {
         if ((rc = ensure(ctx, ctx->d_codes[b], (size_t)max_chunk_u4 * 16))) return rc;
         if ((rc = ensure(ctx, ctx->d_bnd[b], (size_t)ctx->grid * warps * L.IPW * ctx->bnd_stride * sizeof(int2)))) return rc;
     }
     if ((rc = ensure(ctx, ctx->d_counter, ctx->chunks.size() * sizeof(int) + 256))) return rc;
-    CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->tiles.data(), (size_t)n_tiles * sizeof(TileDesc),
-                       cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));      // ctx->tiles may be re-planned by the caller
+    if (!uniform) {
+        CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->tiles.data(), (size_t)n_tiles * sizeof(TileDesc),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // ctx->tiles may be re-planned by the caller
+    }
+    ht.lap("plan: scratch + tile upload");
     while (ctx->cev.size() < ctx->chunks.size()) {
         ChunkEvents c;
         for (cudaEvent_t *e : {&c.in0, &c.in1, &c.f0, &c.f1, &c.w0, &c.w1, &c.out0, &c.out1}) CK(cudaEventCreate(e));
@@ -479,6 +578,10 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     ctx->code_bytes = total_u4 * 16;
     ctx->plan_flags = flags;
     ctx->serial = serial;
+    ctx->uniform = uniform;
+    ctx->uniM = maxM;
+    ctx->uniN = maxN;
+    ctx->uni_u4 = uni_u4;
     ctx->have_plan = true;
     return GA_OK;
 }
@@ -498,7 +601,10 @@ extern "C" int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info) {
 }
 
 // Host buffers of the host-buffer entry point (null for ga_run_batch).
+constexpr int IN_PIECES = 8;        // the letters are uploaded in this many pieces, started before planning
+
 struct HostIO {
+    int64_t total1 = 0, total2 = 0;     // letters in s1 / s2 (piece k ends at total * (k+1) / IN_PIECES)
     const uint8_t *s1 = nullptr, *s2 = nullptr;
     const int64_t *off1 = nullptr, *off2 = nullptr, *ops_off = nullptr;
     int32_t *cost = nullptr, *len = nullptr, *status = nullptr;
@@ -529,19 +635,23 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         cudaStream_t sF = serial ? main : ctx->aux[b], sW = serial ? main : ctx->aux[2 + b];
         cudaStream_t sIn = ctx->aux[4], sOut = ctx->aux[5];
         const int n_tiles = ch.tile_hi - ch.tile_lo, np = ch.pair_hi - ch.pair_lo;
-        if (io) {   // this chunk's letters (offset arrays were uploaded up front)
-            const int64_t a0 = io->off1[ch.pair_lo], a1 = io->off1[ch.pair_hi];
-            const int64_t b0 = io->off2[ch.pair_lo], b1 = io->off2[ch.pair_hi];
-            CK(cudaEventRecord(E.in0, sIn));
-            CK(cudaMemcpyAsync((uint8_t *)d_s1 + a0, io->s1 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, sIn));
-            CK(cudaMemcpyAsync((uint8_t *)d_s2 + b0, io->s2 + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sIn));
-            CK(cudaEventRecord(E.in1, sIn));
-            CK(cudaStreamWaitEvent(sF, E.in1, 0));
+        if (io) {   // the letters are already in flight (ga_align_batch): wait for the piece that
+                    // holds this chunk's last letter of either sequence set
+            const int64_t a1 = io->off1[ch.pair_hi], b1 = io->off2[ch.pair_hi];
+            auto piece_of = [](int64_t end, int64_t total) {
+                int k = 0;
+                while (k < IN_PIECES - 1 && total * (k + 1) / IN_PIECES < end) ++k;
+                return k;
+            };
+            const int k = std::max(piece_of(a1, io->total1), piece_of(b1, io->total2));
+            CK(cudaStreamWaitEvent(sF, ctx->in_piece[k], 0));
         }
         if (!serial && c >= 2) CK(cudaStreamWaitEvent(sF, ctx->cev[c - 2].w1, 0));   // code buffer free
         CK(cudaEventRecord(E.f0, sF));
         const int grid = std::min(ctx->grid, (n_tiles + 3) / 4);
-        cfg->launch_fill(grid, ctx->smem, sF, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo,
+        const TileDesc *d_tiles = ctx->uniform ? nullptr : (const TileDesc *)ctx->d_tiles.p + ch.tile_lo;
+        const UniformTiles ut{ctx->uniM, ctx->uniN, ch.pair_lo, ch.pair_hi, ctx->uni_u4};
+        cfg->launch_fill(grid, ctx->smem, sF, ctx->sc, d_tiles, ut,
                          n_tiles, (int *)ctx->d_counter.p + c, d_s1, (const long long *)d_s1_off, d_s2,
                          (const long long *)d_s2_off, (uint4 *)ctx->d_codes[b].p, (int2 *)ctx->d_bnd[b].p,
                          ctx->bnd_stride, ctx->sb_stride, d_cost);
@@ -550,7 +660,7 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         if (sW != sF) CK(cudaStreamWaitEvent(sW, E.f1, 0));
         CK(cudaEventRecord(E.w0, sW));
         if (!cost_only) {
-            cfg->launch_walk(sW, ctx->sc, (const TileDesc *)ctx->d_tiles.p + ch.tile_lo, ch.pair_lo, np,
+            cfg->launch_walk(sW, ctx->sc, d_tiles, ut, ch.pair_lo, np,
                              d_s1, (const long long *)d_s1_off, d_s2, (const long long *)d_s2_off,
                              (const uint32_t *)ctx->d_codes[b].p, d_ops, (const long long *)d_ops_off,
                              d_len, d_status);
@@ -612,20 +722,19 @@ extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
         CK(cudaEventElapsedTime(&t, ctx->cev[c].w0, ctx->cev[c].w1));
         walk += t;
         if (ctx->timing_io) {
-            CK(cudaEventElapsedTime(&t, ctx->cev[c].in0, ctx->cev[c].in1));
-            h2d += t;
             CK(cudaEventElapsedTime(&t, ctx->cev[c].out0, ctx->cev[c].out1));
             d2h += t;
         }
     }
+    if (ctx->timing_io) CK(cudaEventElapsedTime(&h2d, ctx->in_begin, ctx->in_piece[IN_PIECES - 1]));
     CK(cudaEventElapsedTime(&total, ctx->ev[0], ctx->ev[1]));
     // per-phase sums; with the pipeline on, phases overlap each other, so they add up
     // to more than `total` (the bracketing events on the caller-visible stream)
-    ms[GA_T_H2D] = h2d + ctx->ms[GA_T_H2D];
+    ms[GA_T_H2D] = h2d;
     ms[GA_T_FILL] = fill;
     ms[GA_T_WALK] = walk;
     ms[GA_T_D2H] = d2h;
-    ms[GA_T_TOTAL] = total + ctx->ms[GA_T_H2D];
+    ms[GA_T_TOTAL] = total;
     return GA_OK;
 }
 
@@ -639,12 +748,16 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     if (!s1 || !s2 || !s1_off || !s2_off || !out_cost ||
         (!cost_only && (!out_ops || !out_ops_off || !out_ops_len || !out_status)))
         return fail(ctx, GA_E_ARG, "null host buffer");
-    int rc = ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
-    if (rc) return rc;
-    cudaStream_t st = ctx->stream;
-    const size_t b1 = (size_t)s1_off[n_pairs], b2 = (size_t)s2_off[n_pairs];
+    if (n_pairs < 1 || n_pairs > 0x7fffff00LL) return fail(ctx, GA_E_ARG, "bad batch (1 <= n_pairs < 2^31)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream, sIn = ctx->aux[4];
+    const int64_t t1 = s1_off[n_pairs], t2 = s2_off[n_pairs];
+    if (t1 < n_pairs || t2 < n_pairs || s1_off[0] != 0 || s2_off[0] != 0)
+        return fail(ctx, GA_E_ARG, "offset arrays must start at 0 and be increasing");
+    const size_t b1 = (size_t)t1, b2 = (size_t)t2;
     const size_t offb = (size_t)(n_pairs + 1) * 8;
     const size_t opsb = cost_only ? 0 : (size_t)out_ops_off[n_pairs];
+    int rc;
     if ((rc = ensure(ctx, ctx->d_s1, b1 + 16)) || (rc = ensure(ctx, ctx->d_s2, b2 + 16)) ||
         (rc = ensure(ctx, ctx->d_off1, offb)) || (rc = ensure(ctx, ctx->d_off2, offb)) ||
         (rc = ensure(ctx, ctx->d_cost, (size_t)n_pairs * 4)))
@@ -654,13 +767,38 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
          (rc = ensure(ctx, ctx->d_len, (size_t)n_pairs * 4)) ||
          (rc = ensure(ctx, ctx->d_status, (size_t)n_pairs * 4))))
         return rc;
-    // offset arrays first (every chunk needs them); letters follow chunk by chunk
+    HostTimer ht0;
+    // Start the uploads right away on the copy-in stream -- offset arrays, then the letters in
+    // IN_PIECES pieces with an event each -- so that host-side planning overlaps with them and
+    // the first fill can start as soon as its own piece has landed.
     CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, st));
-    if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaStreamWaitEvent(sIn, ctx->ev[2], 0));
+    CK(cudaEventRecord(ctx->in_begin, sIn));
+    CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, sIn));
+    CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, sIn));
+    if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
+    auto upload_piece = [&](int k) -> int {
+        const int64_t a0 = t1 * k / IN_PIECES, a1 = t1 * (k + 1) / IN_PIECES;
+        const int64_t c0 = t2 * k / IN_PIECES, c1 = t2 * (k + 1) / IN_PIECES;
+        if (a1 > a0) CK(cudaMemcpyAsync((uint8_t *)ctx->d_s1.p + a0, s1 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, sIn));
+        if (c1 > c0) CK(cudaMemcpyAsync((uint8_t *)ctx->d_s2.p + c0, s2 + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, sIn));
+        CK(cudaEventRecord(ctx->in_piece[k], sIn));
+        return GA_OK;
+    };
+    // only the first pieces go out before planning: the copy engine works in issue order and the
+    // (small) tile-descriptor upload of a non-uniform plan must not queue behind the whole batch
+    constexpr int EARLY = 2;
+    for (int k = 0; k < EARLY; ++k)
+        if ((rc = upload_piece(k))) return rc;
+    ht0.lap("align: enqueue uploads");
+    HostTimer ht;
+    rc = ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
+    if (rc) { cudaStreamSynchronize(sIn); return rc; }
+    for (int k = EARLY; k < IN_PIECES; ++k)
+        if ((rc = upload_piece(k))) return rc;
+    ht.lap("align: plan total");
     HostIO io;
+    io.total1 = t1; io.total2 = t2;
     io.s1 = s1; io.s2 = s2; io.off1 = s1_off; io.off2 = s2_off; io.ops_off = out_ops_off;
     io.cost = out_cost; io.len = out_ops_len; io.status = out_status; io.ops = out_ops;
     rc = run_pipeline(ctx, (const uint8_t *)ctx->d_s1.p, (const int64_t *)ctx->d_off1.p,
@@ -668,8 +806,9 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
                       (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p, (const int64_t *)ctx->d_opsoff.p,
                       (int32_t *)ctx->d_len.p, (int32_t *)ctx->d_status.p, &io);
     if (rc) return rc;
+    ht.lap("align: enqueue pipeline");
     CK(cudaStreamSynchronize(st));
-    CK(cudaEventElapsedTime(&ctx->ms[GA_T_H2D], ctx->ev[2], ctx->ev[3]));
+    ht.lap("align: wait for the device");
     return GA_OK;
 }
 

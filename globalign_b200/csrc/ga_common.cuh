@@ -47,6 +47,25 @@ struct TileDesc {
     int M, N;            // longest seq_1 / seq_2 in the tile
 };
 
+// When every pair of a chunk has the same (m, n) the tile descriptors are arithmetic and are
+// not uploaded: tiles == nullptr and this struct (a kernel parameter) describes them all.
+struct UniformTiles {
+    int M, N;             // the common lengths
+    int pair_lo, pair_hi; // pairs of the chunk
+    long long u4;         // direction-code words (uint4) per tile
+};
+
+__device__ __forceinline__ TileDesc tile_desc(const TileDesc *tiles, const UniformTiles &ut, int tile, int ppt) {
+    if (tiles) return tiles[tile];
+    TileDesc td;
+    td.code_off = (long long)tile * ut.u4;
+    td.first_pair = ut.pair_lo + tile * ppt;
+    td.n_pairs = min(ppt, ut.pair_hi - td.first_pair);
+    td.M = ut.M;
+    td.N = ut.N;
+    return td;
+}
+
 // Compile-time layout of one kernel configuration.
 template <bool PACKED, int R_, int G_>
 struct Lay {

@@ -65,7 +65,8 @@ struct VOps<true> {
 
 template <bool PACKED, bool SIMPLE, int R, int G>
 __global__ void __launch_bounds__(128)
-fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int n_tiles, int *tile_counter,
+fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const UniformTiles ut, int n_tiles,
+            int *tile_counter,
             const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
             const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
             uint4 *__restrict__ codes, int2 *bnd, int bnd_stride, int sb_stride,
@@ -111,7 +112,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int n_tiles,
         if (lane == 0) tile = atomicAdd(tile_counter, 1);
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= n_tiles) break;
-        const TileDesc td = tiles[tile];
+        const TileDesc td = tile_desc(tiles, ut, tile, L::PPT);
 
         // ---- the pair(s) of my item
         const int ia = my_item * L::PPI, ibx = ia + (PACKED ? 1 : 0);

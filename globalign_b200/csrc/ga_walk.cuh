@@ -29,7 +29,8 @@ __device__ __forceinline__ int first_min3(long long v0, long long v1, long long 
 
 template <bool PACKED, int R, int G>
 __global__ void __launch_bounds__(128)
-walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int pair_lo, int n_pairs,
+walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const UniformTiles ut, int pair_lo,
+            int n_pairs,
             const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
             const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
             const uint32_t *__restrict__ codes, uint8_t *__restrict__ out_ops,
@@ -43,7 +44,7 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, int pair_lo,
     const int within = k - tile * L::PPT;
     const int item = within / L::PPI;
     const int half = within - item * L::PPI;
-    const TileDesc td = tiles[tile];
+    const TileDesc td = tile_desc(tiles, ut, tile, L::PPT);
     const long long a1 = off1[p], a2 = off2[p];
     const int m = (int)(off1[p + 1] - a1), n = (int)(off2[p + 1] - a2);
     const int nsteps = td.N + G - 1;

@@ -207,12 +207,23 @@ def dp_array_backward(dp_array, seq_1: str, seq_2: str, costing_mat: dict, gap_o
     return top, mid, bot, cost
 
 
+def _version() -> str:
+    """The reference asks importlib.metadata for 'globalign' eagerly and crashes when the
+    package is not pip-installed (globaligner.py:35); here a missing install is not fatal."""
+    try:
+        from importlib.metadata import version
+        return version("globalign_b200")
+    except Exception:
+        return "0+b200"
+
+
 def main(argv=None):
     """Command line with the reference's flags (globaligner.py:23-129)."""
     import argparse
 
     p = argparse.ArgumentParser(
         description="Perform optimal global alignment of two nucleotide or amino acid sequences.")
+    p.add_argument("--version", action="version", version=_version(), help="Prints the version and exits.")
     p.add_argument("-i", "--input_fasta", required=False)
     p.add_argument("-o", "--output", required=False)
     p.add_argument("--seq_1", required=False)

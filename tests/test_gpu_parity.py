@@ -360,3 +360,36 @@ def test_seeded_replay_reproduces_unpatched_reference(monkeypatch):
         assert r.cost == rec["out"][3]
         differs_from_canonical += [r.seq_1_aligned, r.seq_2_aligned] != [rec["out"][0], rec["out"][2]]
     assert differs_from_canonical > 3          # the seeded runs really exercise random ties
+
+
+# ------------------------------------------------------------------ f3 / f4: FASTA batches, CLI, batch output
+def test_cli_prints_the_reference_printout(capsys):
+    rec = golden("kat.json")["tutorial"][0]            # globaligner --seq_1 ACGT --seq_2 AGT (tutorial.qmd:9-47)
+    globaligner.main(["--seq_1", "ACGT", "--seq_2", "AGT"])
+    assert capsys.readouterr().out == rec["str"] + "\n"
+    rec = golden("kat.json")["tutorial"][1]
+    globaligner.main(["--seq_1", "CCTGAA", "--seq_2", "GCCGA", "--match_score", "1", "--mismatch_score", "-1",
+                      "--gap_open_score", "-2", "--gap_extension_score", "-1"])
+    assert capsys.readouterr().out == rec["str"] + "\n"
+    with pytest.raises(TypeError):                       # the reference's str-vs-int comparison (start.py:138)
+        globaligner.main(["--seq_1", "ACGT", "--seq_2", "AGT", "--mismatch_cost", "5"])
+    with pytest.raises(SystemExit):
+        globaligner.main(["--version"])
+
+
+def test_fasta_batch_and_batch_writer(tmp_path):
+    recs = [r for r in golden("random_cases.json") if set(r["kw"]) == {"seq_1", "seq_2"}
+            and r["kw"]["seq_1"].isascii() and r["kw"]["seq_2"].isascii()][:12]
+    fa = tmp_path / "in.fa"
+    fa.write_text("".join(f">a{k}\n{r['kw']['seq_1']}\n>b{k}\n{r['kw']['seq_2']}\n" for k, r in enumerate(recs)))
+    descs, res = batch.find_global_alignments_from_fasta(fa)
+    assert len(res) == len(recs)
+    for k, rec in enumerate(recs):
+        a = res[k]
+        assert [a.seq_1_aligned, a.middle_part, a.seq_2_aligned, a.cost, a.score] == rec["out"]
+    out = tmp_path / "all.txt"
+    res.write(out, descs)
+    text = out.read_text()
+    one = find_global_alignment(input_fasta=str(fa))      # the reference-style call reads the first two records
+    assert text.startswith(one.__str__(desc_1=">a0", desc_2=">b0"))
+    assert text.count("\nscore: ") == len(recs)

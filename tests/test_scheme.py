@@ -168,3 +168,17 @@ def test_reference_draw_emulation_matches_cpython_choice():
         for s in range(17):
             [random.choice(range(size)) for _ in range(2) for size in sizes]
         assert random.random() == a
+
+
+def test_batched_fasta_ingestion(tmp_path):
+    p = tmp_path / "pairs.fa"
+    p.write_text(">r1\nacgt\n>r2 x\nAGT\n>r3\nGG\nTT\n>r4\nGGT\n")
+    descs, s1, s2 = batch.read_pairs_from_fasta(p)
+    assert descs == [(">r1", ">r2 x"), (">r3", ">r4")] and s1 == ["ACGT", "GGTT"] and s2 == ["AGT", "GGT"]
+    q = tmp_path / "other.fa"
+    q.write_text(">q1\nAC\n>q2\nTTA\n>q3\nG\n>q4\nC\n")
+    descs, s1, s2 = batch.read_pairs_from_fasta(p, q)
+    assert len(s1) == 4 and s2 == ["AC", "TTA", "G", "C"] and descs[2] == (">r3", ">q3")
+    (tmp_path / "odd.fa").write_text(">a\nAC\n>b\nAC\n>c\nAC\n")
+    with pytest.raises(RuntimeError):
+        batch.read_pairs_from_fasta(tmp_path / "odd.fa")
