@@ -45,7 +45,8 @@ class PlanInfo(C.Structure):
 class LongInfo(C.Structure):
     _fields_ = [("fill_ms", C.c_float), ("trace_ms", C.c_float), ("launches", C.c_int32),
                 ("tile_rows", C.c_int32), ("tile_cols", C.c_int32), ("retraced_tiles", C.c_int32),
-                ("checkpoint_bytes", C.c_int64), ("cells", C.c_int64)]
+                ("checkpoint_bytes", C.c_int64), ("cells", C.c_int64), ("trace_mode", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 _lib = None

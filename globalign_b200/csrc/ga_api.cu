@@ -145,7 +145,7 @@ struct ga_ctx {
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
     // long-pair path
-    DevBuf l_colsum, l_rowsum, l_brow, l_vchk, l_prog, l_misc;
+    DevBuf l_colsum, l_rowsum, l_brow, l_vchk, l_prog, l_misc, l_xrow, l_meta, l_seg;
     // timing
     cudaEvent_t ev[8] = {};
     std::vector<ChunkEvents> cev;
@@ -248,7 +248,8 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
                       &ctx->d_counter, &ctx->d_s1,
                       &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
                       &ctx->d_opsoff, &ctx->d_len, &ctx->d_status, &ctx->l_colsum, &ctx->l_rowsum,
-                      &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc})
+                      &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc, &ctx->l_xrow, &ctx->l_meta,
+                      &ctx->l_seg})
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->in_piece) if (e) cudaEventDestroy(e);
@@ -888,6 +889,7 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[3], st));
     int launches = 1;
+    const bool parallel = !cost_only && m >= 2 && n >= 2 && !(flags & GA_F_SERIAL);
     if (!cost_only) {
         TraceOut to;
         to.ops = (uint32_t *)ctx->d_ops.p;
@@ -895,18 +897,57 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         to.status = misc + 2;
         to.tiles_refilled = misc + 3;
         const size_t tsmem = (size_t)LT_NTB * 32 * sizeof(uint4) + table;
+        const int *skip = nullptr;
+        if (parallel) {
+            // parallel traceback: X-propagation over a diagonal corridor, chain, per-band detail, pack
+            ParTrace pt;
+            pt.W = 512 + (int)((m + n) / 128);
+            pt.XW = 2 * pt.W + (int)(((int64_t)LBAND * n + m - 1) / m) + LCC + 8;
+            pt.seg_cap = 2 * (m + n) + 4096 + (int64_t)nbands * 4;
+            const size_t xrow_b = (size_t)nbands * pt.XW * 3 * 4;
+            const size_t meta_b = (size_t)nbands * (16 + 8 + 4 + 8) + 64;
+            if ((rc = ensure(ctx, ctx->l_xrow, xrow_b)) || (rc = ensure(ctx, ctx->l_meta, meta_b)) ||
+                (rc = ensure(ctx, ctx->l_seg, (size_t)pt.seg_cap + 64)))
+                return rc;
+            uint8_t *meta = (uint8_t *)ctx->l_meta.p;
+            pt.xrow = (int *)ctx->l_xrow.p;
+            pt.seg_off = (long long *)meta;
+            pt.seg_pos = (long long *)(meta + (size_t)nbands * 8);
+            pt.entry = (int *)(meta + (size_t)nbands * 16);
+            pt.seg_len = (int *)(meta + (size_t)nbands * 32);
+            pt.seg_ops = (uint8_t *)ctx->l_seg.p;
+            pt.xlast = misc + 7;
+            pt.failed = misc + 6;
+            pt.tiles = misc + 3;
+            if (sc.simple) {
+                CK(cudaFuncSetAttribute(long_detail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                long_xprop_kernel<true><<<(nbands + LWARPS - 1) / LWARPS, 32 * LWARPS, 0, st>>>(sc, a, pt);
+                long_chain_kernel<<<1, 32, 0, st>>>(a, pt);
+                long_detail_kernel<true><<<nbands, 32, tsmem, st>>>(sc, a, pt);
+            } else {
+                CK(cudaFuncSetAttribute(long_detail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                long_xprop_kernel<false><<<(nbands + LWARPS - 1) / LWARPS, 32 * LWARPS, table, st>>>(sc, a, pt);
+                long_chain_kernel<<<1, 32, 0, st>>>(a, pt);
+                long_detail_kernel<false><<<nbands, 32, tsmem, st>>>(sc, a, pt);
+            }
+            long_prefix_kernel<<<1, 32, 0, st>>>(a, pt, to.n_ops, to.status);
+            long_pack_kernel<<<(int)((ops_words + 255) / 256), 256, 0, st>>>(a, pt, to.n_ops, to.ops);
+            CK(cudaGetLastError());
+            launches += 5;
+            skip = pt.failed;           // the sequential form below runs only if the chain failed
+        }
         if (sc.simple) {
             CK(cudaFuncSetAttribute(long_trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-            long_trace_kernel<true><<<1, 32, tsmem, st>>>(sc, a, to);
+            long_trace_kernel<true><<<1, 32, tsmem, st>>>(sc, a, to, skip);
         } else {
             CK(cudaFuncSetAttribute(long_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-            long_trace_kernel<false><<<1, 32, tsmem, st>>>(sc, a, to);
+            long_trace_kernel<false><<<1, 32, tsmem, st>>>(sc, a, to, skip);
         }
         CK(cudaGetLastError());
         ++launches;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
-    int host_misc[8] = {};
+    int host_misc[16] = {};
     CK(cudaMemcpyAsync(host_misc, misc, sizeof host_misc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *out_cost = host_misc[1];
@@ -925,6 +966,7 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         info->tile_rows = LBAND;
         info->tile_cols = LCC;
         info->retraced_tiles = host_misc[3];
+        info->trace_mode = cost_only ? -1 : (!parallel ? 0 : (host_misc[6] ? 2 : 1));
         info->checkpoint_bytes = (int64_t)(brow_b + vchk_b);
         info->cells = m * n;
     }

@@ -223,24 +223,132 @@ struct TraceOut {
     int *tiles_refilled;
 };
 
+// ---- shared pieces of the traceback kernels -------------------------------------------------
+
+struct TraceConsts {
+    unsigned o4, mm4, ghTc, big;
+};
+
+// Left-boundary state of the lanes' rows at column jc (a multiple of LCC): column-0 formulas
+// for jc == 0, the fill's checkpoint otherwise.  Returns h(ib_lane, jc), the diagonal input of
+// the lane's first row at column jc+1.
 template <bool SIMPLE>
-__global__ void __launch_bounds__(32)
-long_trace_kernel(const SchemeDev sc, const LongArgs a, const TraceOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [tile codes: LT_NTB x 32 lanes x uint4][TABLE: sub | gh]
-    uint4 *s_codes = reinterpret_cast<uint4 *>(smem_raw);
-    int *s_sub = reinterpret_cast<int *>(smem_raw + (size_t)LT_NTB * 32 * sizeof(uint4));
-    int *s_gh = s_sub;
+__device__ __forceinline__ unsigned long_restore(const SchemeDev &sc, const LongArgs &a, int band, int jc, int g,
+                                                 LongLane<SIMPLE> &ln, unsigned big) {
+    const int ib = band * LBAND + g * LR;
+    long_load_rows<SIMPLE>(sc, a, ib, ln);
+    if (jc == 0) {
+#pragma unroll
+        for (int r = 0; r < LR; ++r) {
+            const unsigned c = (unsigned)a.colsum[min(ib + r + 1, a.m)];
+            ln.hl[r] = min(big, c) << 2;
+            ln.Lp[r] = min(big, c + sc.o) << 2;
+        }
+        return ib == 0 ? 0u : (min(big, (unsigned)a.colsum[min(ib, a.m)]) << 2);
+    }
+    const int2 *src = a.vchk + (((size_t)band * a.nck + jc / LCC) * 32 + g) * LR;
+#pragma unroll
+    for (int r = 0; r < LR; ++r) {
+        const int2 v = __ldcg(src + r);
+        ln.hl[r] = (unsigned)v.x;
+        ln.Lp[r] = (unsigned)v.y;
+    }
+    unsigned above = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);   // bottom-row h of the lane above
+    if (g == 0) {
+        if (band > 0) above = (unsigned)__ldcg(a.brow + (size_t)(band - 1) * (a.n + 1) + jc).x;
+        else above = min(big, (unsigned)a.rowsum[jc]) << 2;
+    }
+    return above;
+}
+
+// Re-fill columns jc+1 .. jc+width of `band` with direction codes into shared memory
+// (two steps per uint4: plane 0 / plane 1 of the even step, then of the odd step).
+template <bool SIMPLE>
+__device__ __forceinline__ void long_refill_codes(const SchemeDev &sc, const LongArgs &a, const int *s_sub,
+                                                  const int *s_gh, uint4 *s_codes, int band, int jc, int width,
+                                                  int g, const TraceConsts &k) {
+    LongLane<SIMPLE> ln;
+    unsigned rh_prev = long_restore<SIMPLE>(sc, a, band, jc, g, ln, k.big);
+    const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (a.n + 1);
+    unsigned hb = 0, ub = 0, bv = 0, st0 = 0, st1 = 0, bblk = 0;
+    int2 tblk = make_int2(0, 0);
+    const int nsteps = width + 31;
+    for (int t = 0; t < nsteps; ++t) {
+        if ((t & 31) == 0) {       // letters of seq_2 and the boundary row above, 32 columns at a time
+            const int cj = min(jc + t + 1 + g, a.n);
+            bblk = (unsigned)a.s2[cj - 1];
+            if (band > 0) {
+                tblk = __ldcg(up_brow + cj);
+            } else {
+                const unsigned rj = (unsigned)a.rowsum[cj];
+                tblk = make_int2((int)(min(k.big, rj) << 2), (int)(min(k.big, rj + sc.o) << 2));
+            }
+        }
+        const int jl = t - g + 1;                // column within the tile, 1-based
+        unsigned rh = __shfl_up_sync(FULL, hb, 1);
+        unsigned ru = __shfl_up_sync(FULL, ub, 1);
+        unsigned bin = __shfl_up_sync(FULL, bv, 1);
+        const unsigned b0 = __shfl_sync(FULL, bblk, t & 31);
+        const unsigned th = (unsigned)__shfl_sync(FULL, tblk.x, t & 31);
+        const unsigned tu = (unsigned)__shfl_sync(FULL, tblk.y, t & 31);
+        if (g == 0) { bin = b0; rh = th; ru = tu; }
+        bv = bin;
+        unsigned w0 = 0, w1 = 0;
+        if (jl >= 1 && jl <= width) {
+            unsigned diag = rh_prev;
+            rh_prev = rh;
+            const unsigned ghT = SIMPLE ? k.ghTc : (unsigned)s_gh[bv];
+            long_cells<SIMPLE, true>(sc, s_sub, ln, diag, ru, bv, ghT, k.o4, k.mm4, hb, ub, w0, w1);
+        }
+        if (t & 1) {
+            s_codes[(t >> 1) * 32 + g] = make_uint4(st0, st1, w0, w1);
+        } else {
+            st0 = w0;
+            st1 = w1;
+        }
+    }
+    if (nsteps & 1) s_codes[(nsteps >> 1) * 32 + g] = make_uint4(st0, st1, 0u, 0u);
+    __syncwarp();
+}
+
+// direction at cell (ii, jj) of the tile in shared memory, for a successor on `level`
+__device__ __forceinline__ int long_tile_dir(const uint4 *s_codes, int band, int jc, int ii, int jj, int level) {
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(s_codes);
+    const int rem = (ii - 1) - band * LBAND;
+    const int lg = rem / LR, r = rem - lg * LR;
+    const int t = (jj - jc - 1) + lg;
+    const uint32_t *base = cw + ((size_t)(t >> 1) * 32 + lg) * 4 + (t & 1) * 2;
+    const int sh = 2 * (LR - 1 - r);
+    if (level != 0 && (((base[1] >> sh) & 3u) & (unsigned)level)) return level;
+    return (int)((base[0] >> sh) & 3u);
+}
+
+template <bool SIMPLE>
+__device__ __forceinline__ void long_load_tables(const SchemeDev &sc, int *s_sub, int *&s_gh) {
+    s_gh = s_sub;
     if (!SIMPLE) {
         const int n_sub = (sc.A + 1) * sc.A;
         s_gh = s_sub + n_sub;
-        for (int k = threadIdx.x; k < n_sub; k += 32) s_sub[k] = sc.sub4[k];
-        for (int k = threadIdx.x; k < sc.A; k += 32) s_gh[k] = sc.gh4t[k];
-        __syncwarp();
+        for (int k = threadIdx.x; k < n_sub; k += blockDim.x) s_sub[k] = sc.sub4[k];
+        for (int k = threadIdx.x; k < sc.A; k += blockDim.x) s_gh[k] = sc.gh4t[k];
+        __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------- K5, sequential form
+// One warp re-fills and walks tile after tile.  Exact for every input; used for tiny pairs,
+// with GA_F_SERIAL, and as the fallback of the parallel form below.
+template <bool SIMPLE>
+__global__ void __launch_bounds__(32)
+long_trace_kernel(const SchemeDev sc, const LongArgs a, const TraceOut out, const int *skip_unless_failed) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *s_codes = reinterpret_cast<uint4 *>(smem_raw);
+    int *s_sub = reinterpret_cast<int *>(smem_raw + (size_t)LT_NTB * 32 * sizeof(uint4));
+    int *s_gh;
+    if (skip_unless_failed && *skip_unless_failed == 0) return;      // the parallel form succeeded
+    long_load_tables<SIMPLE>(sc, s_sub, s_gh);
     const int g = threadIdx.x;
-    const unsigned o4 = 4u * sc.o, mm4 = 4u * sc.mm, ghTc = 4u * sc.gh + 1u;
-    const unsigned big = a.big;
+    const TraceConsts k{4u * sc.o, 4u * sc.mm, 4u * sc.gh + 1u, a.big};
 
     int i = a.m, j = a.n, level = 0, status = 0, tiles = 0;
     long long nops = 0;
@@ -250,100 +358,14 @@ long_trace_kernel(const SchemeDev sc, const LongArgs a, const TraceOut out) {
         word |= (uint32_t)op << (2 * (int)(nops & 15));
         if ((++nops & 15) == 0) { out.ops[(nops >> 4) - 1] = word; word = 0; }
     };
-
     while (i > 0 && j > 0 && status == 0) {
         const int band = (i - 1) / LBAND;
-        const int cblk = (j - 1) / LCC;
-        const int jc = cblk * LCC;                  // columns jc+1 .. j are re-filled
-        const int width = j - jc;
-        // ---- re-fill the tile with direction codes
-        const int ib = band * LBAND + g * LR;
-        LongLane<SIMPLE> ln;
-        long_load_rows<SIMPLE>(sc, a, ib, ln);
-        unsigned rh_prev;
-        if (cblk == 0) {
-#pragma unroll
-            for (int r = 0; r < LR; ++r) {
-                const unsigned c = (unsigned)a.colsum[min(ib + r + 1, a.m)];
-                ln.hl[r] = min(big, c) << 2;
-                ln.Lp[r] = min(big, c + sc.o) << 2;
-            }
-            rh_prev = ib == 0 ? 0u : (min(big, (unsigned)a.colsum[min(ib, a.m)]) << 2);
-        } else {
-            const int2 *src = a.vchk + (((size_t)band * a.nck + cblk) * 32 + g) * LR;
-#pragma unroll
-            for (int r = 0; r < LR; ++r) {
-                const int2 v = __ldcg(src + r);
-                ln.hl[r] = (unsigned)v.x;
-                ln.Lp[r] = (unsigned)v.y;
-            }
-            // h(ib, jc): bottom-row h of the lane above at the checkpoint column
-            unsigned above = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
-            if (g == 0) {
-                if (band > 0) above = (unsigned)__ldcg(a.brow + (size_t)(band - 1) * (a.n + 1) + jc).x;
-                else above = min(big, (unsigned)a.rowsum[jc]) << 2;
-            }
-            rh_prev = above;
-        }
-        const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (a.n + 1);
-        unsigned hb = 0, ub = 0, bv = 0;
-        const int nsteps = width + 31;
-        unsigned st0 = 0, st1 = 0;
-        unsigned bblk = 0;
-        int2 tblk = make_int2(0, 0);
-        for (int t = 0; t < nsteps; ++t) {
-            if ((t & 31) == 0) {
-                // letters of seq_2 and the boundary row above the band, 32 columns at a time
-                const int cj = min(jc + t + 1 + g, a.n);
-                bblk = (unsigned)a.s2[cj - 1];
-                if (band > 0) {
-                    tblk = __ldcg(up_brow + cj);
-                } else {
-                    const unsigned rj = (unsigned)a.rowsum[cj];
-                    tblk = make_int2((int)(min(big, rj) << 2), (int)(min(big, rj + sc.o) << 2));
-                }
-            }
-            const int jl = t - g + 1;                // column within the tile, 1-based
-            unsigned rh = __shfl_up_sync(FULL, hb, 1);
-            unsigned ru = __shfl_up_sync(FULL, ub, 1);
-            unsigned bin = __shfl_up_sync(FULL, bv, 1);
-            const unsigned b0 = __shfl_sync(FULL, bblk, t & 31);
-            const unsigned th = (unsigned)__shfl_sync(FULL, tblk.x, t & 31);
-            const unsigned tu = (unsigned)__shfl_sync(FULL, tblk.y, t & 31);
-            if (g == 0) { bin = b0; rh = th; ru = tu; }
-            bv = bin;
-            unsigned w0 = 0, w1 = 0;
-            if (jl >= 1 && jl <= width) {
-                unsigned diag = rh_prev;
-                rh_prev = rh;
-                const unsigned ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
-                long_cells<SIMPLE, true>(sc, s_sub, ln, diag, ru, bv, ghT, o4, mm4, hb, ub, w0, w1);
-            }
-            if (t & 1) {
-                s_codes[(t >> 1) * 32 + g] = make_uint4(st0, st1, w0, w1);
-            } else {
-                st0 = w0;
-                st1 = w1;
-            }
-        }
-        if (nsteps & 1) s_codes[(nsteps >> 1) * 32 + g] = make_uint4(st0, st1, 0u, 0u);
-        __syncwarp();
+        const int jc = ((j - 1) / LCC) * LCC;       // columns jc+1 .. j are re-filled
+        long_refill_codes<SIMPLE>(sc, a, s_sub, s_gh, s_codes, band, jc, j - jc, g, k);
         ++tiles;
-        // ---- walk inside the tile (lane 0)
         if (g == 0) {
-            const uint32_t *cw = reinterpret_cast<const uint32_t *>(s_codes);
-            auto plane = [&](int ii, int jj, int pl) -> unsigned {
-                const int rem = (ii - 1) - band * LBAND;
-                const int lg = rem / LR, r = rem - lg * LR;
-                const int t = (jj - jc - 1) + lg;
-                const int flat = (t & 1) * 2 + pl;
-                const uint32_t w = cw[((size_t)(t >> 1) * 32 + lg) * 4 + flat];
-                return (w >> (2 * (LR - 1 - r))) & 3u;
-            };
             while (i > 0 && j > jc && (i - 1) / LBAND == band) {
-                int op;
-                if (level != 0 && (plane(i, j, 1) & (unsigned)level)) op = level;
-                else op = (int)plane(i, j, 0);
+                const int op = long_tile_dir(s_codes, band, jc, i, j, level);
                 emit(op);
                 if (op == 0) { --i; --j; } else if (op == 1) { --j; } else { --i; }
                 level = op;
@@ -351,15 +373,15 @@ long_trace_kernel(const SchemeDev sc, const LongArgs a, const TraceOut out) {
                     first = false;
                     if ((i == 0) != (j == 0)) {
                         // boundary cell ranked once by the reference (m == 1 or n == 1)
-                        long long v0 = big, v1 = big, v2 = big;
+                        long long v0 = k.big, v1 = k.big, v2 = k.big;
                         int want;
                         if (i == 0) { v1 = a.rowsum[j]; want = 1; } else { v2 = a.colsum[i]; want = 2; }
                         if (level == 1) { v0 += sc.o; v2 += sc.o; } else if (level == 2) { v0 += sc.o; v1 += sc.o; }
-                        int k = 0;
+                        int pick = 0;
                         long long best = v0;
-                        if (v1 < best) { best = v1; k = 1; }
-                        if (v2 < best) { k = 2; }
-                        if (k != want) status = 1;
+                        if (v1 < best) { best = v1; pick = 1; }
+                        if (v2 < best) { pick = 2; }
+                        if (pick != want) status = 1;
                     }
                 }
             }
@@ -381,6 +403,296 @@ long_trace_kernel(const SchemeDev sc, const LongArgs a, const TraceOut out) {
         *out.status = status;
         *out.tiles_refilled = tiles;
     }
+}
+
+// ---------------------------------------------------------------------------- K5, parallel form
+// The sequential form spends its time on a chain of ~m/LBAND + n/LCC dependent tile refills.
+// The parallel form removes the dependency between bands:
+//   (a) long_xprop_kernel, all bands at once: re-fill each band over a corridor of columns
+//       around the diagonal and propagate, with every cell and level L, the record
+//       X_L(i,j) = where the canonical walk from state (i, j, L) leaves the band:
+//       TOP(j', L') = crossing into the band above at column j' with successor level L',
+//       LEFT(i')    = reaching column 0 at row i', OUT = running out of the corridor.
+//       X follows the same decisions as the codes: X_0 = X of the c0-predecessor,
+//       X_1 = bL ? X_1(left) : X_0, X_2 = bU ? X_2(up) : X_0.  Kept: X of the band's last row.
+//   (b) long_chain_kernel, one thread: follow the records from (m, n, 0) band by band -> the
+//       entry state of every band (one lookup per band).
+//   (c) long_detail_kernel, all bands at once: each band re-fills and walks only its own
+//       segment of the path (the sequential form's loop, confined to one band).
+//   (d) long_pack_kernel: concatenate the segments into the 2-bit op stream.
+// If a crossing falls outside the corridor (very dissimilar sequences) the chain sets `failed`
+// and the sequential form runs instead: the result is exact either way.
+constexpr int X_OUT = (int)0x80000000;
+__host__ __device__ inline int x_top(int j, int L) { return j * 4 + L; }
+__host__ __device__ inline int x_left(int i) { return -i - 1; }
+
+struct ParTrace {
+    int W;                      // corridor half-width (columns)
+    int XW;                     // row stride of xrow (entries)
+    int *xrow;                  // nbands x XW x 3
+    int *xlast;                 // X_0(m, n)
+    int *entry;                 // nbands x 4: i, j, L, kind (0 walk, 1 vertical run only, 2 not on the path)
+    long long *seg_off;         // nbands: start of the band's ops in seg_ops
+    int *seg_len;               // nbands: ops the band produced
+    long long *seg_pos;         // nbands: position of the band's ops in the final stream
+    uint8_t *seg_ops;           // one byte per op
+    long long seg_cap;
+    int *failed;
+    int *tiles;
+};
+
+__host__ __device__ inline void long_corridor(int band, int m, int n, int W, int &lo, int &hi) {
+    const long long r0 = (long long)band * LBAND, r1 = (long long)min((band + 1) * LBAND, m);
+    long long c0 = r0 * n / m - W, c1 = (r1 * n + m - 1) / m + W;
+    if (c0 < 0) c0 = 0;
+    if (c1 > n) c1 = n;
+    lo = (int)(c0 / LCC) * LCC;
+    hi = (int)c1;
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__(32 * LWARPS)
+long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *s_sub = reinterpret_cast<int *>(smem_raw);
+    int *s_gh;
+    long_load_tables<SIMPLE>(sc, s_sub, s_gh);
+    const int g = threadIdx.x & 31;
+    const int band = blockIdx.x * LWARPS + (threadIdx.x >> 5);
+    if (band >= a.nbands) return;
+    const TraceConsts k{4u * sc.o, 4u * sc.mm, 4u * sc.gh + 1u, a.big};
+    int lo, hi;
+    long_corridor(band, a.m, a.n, pt.W, lo, hi);
+    const int width = hi - lo;
+    const int ib = band * LBAND + g * LR;
+    LongLane<SIMPLE> ln;
+    unsigned rh_prev = long_restore<SIMPLE>(sc, a, band, lo, g, ln, k.big);
+    // X state: x0[r] = X_0 of my row r at the previous column (diagonal input of row r+1),
+    // x1[r] = X_1 of my row r at the previous column (left input).  At the corridor's left edge
+    // every walk that continues leftwards is LEFT (lo == 0) or OUT.
+    int x0[LR], x1[LR];
+#pragma unroll
+    for (int r = 0; r < LR; ++r) x0[r] = x1[r] = (lo == 0) ? x_left(ib + r + 1) : X_OUT;
+    int xh_prev = (g == 0) ? x_top(lo, 0) : ((lo == 0) ? x_left(ib) : X_OUT);
+    const bool last_band = band == a.nbands - 1;
+    const int gm = ((a.m - 1) % LBAND) / LR, rm = (a.m - 1) % LR;
+    int *my_xrow = pt.xrow + (size_t)band * pt.XW * 3;
+    const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (a.n + 1);
+    unsigned hb = 0, ub = 0, bv = 0, bblk = 0;
+    int xb0 = 0, xb2 = 0;
+    int2 tblk = make_int2(0, 0);
+    const int nsteps = width + 31;
+    for (int t = 0; t < nsteps; ++t) {
+        if ((t & 31) == 0) {
+            const int cj = min(lo + t + 1 + g, a.n);
+            bblk = (unsigned)a.s2[cj - 1];
+            if (band > 0) {
+                tblk = __ldcg(up_brow + cj);
+            } else {
+                const unsigned rj = (unsigned)a.rowsum[cj];
+                tblk = make_int2((int)(min(k.big, rj) << 2), (int)(min(k.big, rj + sc.o) << 2));
+            }
+        }
+        const int jl = t - g + 1;
+        unsigned rh = __shfl_up_sync(FULL, hb, 1);
+        unsigned ru = __shfl_up_sync(FULL, ub, 1);
+        unsigned bin = __shfl_up_sync(FULL, bv, 1);
+        int rx0 = __shfl_up_sync(FULL, xb0, 1);
+        int rx2 = __shfl_up_sync(FULL, xb2, 1);
+        const unsigned b0 = __shfl_sync(FULL, bblk, t & 31);
+        const unsigned th = (unsigned)__shfl_sync(FULL, tblk.x, t & 31);
+        const unsigned tu = (unsigned)__shfl_sync(FULL, tblk.y, t & 31);
+        if (g == 0) {
+            bin = b0; rh = th; ru = tu;
+            rx0 = x_top(lo + jl, 0);       // leaving through the top of the band at this column
+            rx2 = x_top(lo + jl, 2);
+        }
+        bv = bin;
+        if (jl >= 1 && jl <= width) {
+            unsigned diag = rh_prev, up = ru;
+            rh_prev = rh;
+            int xdiag = xh_prev, xup = rx2;
+            xh_prev = rx0;
+            const unsigned ghT = SIMPLE ? k.ghTc : (unsigned)s_gh[bv];
+#pragma unroll
+            for (int r = 0; r < LR; ++r) {
+                unsigned d0;
+                if (SIMPLE) d0 = diag + (ln.aw[r] != bv ? k.mm4 : 0u);
+                else d0 = diag + (unsigned)s_sub[ln.aw[r] + bv];
+                const unsigned d1 = ln.Lp[r] + ghT;
+                const unsigned d2 = up + ln.gvT[r];
+                const unsigned hq = (unsigned)__vimin3_s32((int)d0, (int)d1, (int)d2);
+                const unsigned Lq = (unsigned)__viaddmin_s32((int)hq, (int)k.o4, (int)d1);
+                const unsigned Uq = (unsigned)__viaddmin_s32((int)hq, (int)k.o4, (int)d2);
+                const unsigned c0 = hq & 3u;
+                const int X0 = c0 == 0u ? xdiag : (c0 == 1u ? x1[r] : xup);
+                const int X1 = (Lq & 1u) ? x1[r] : X0;
+                const int X2 = (Uq & 2u) ? xup : X0;
+                xdiag = x0[r];
+                x0[r] = X0;
+                x1[r] = X1;
+                xup = X2;
+                diag = ln.hl[r];
+                ln.hl[r] = hq & ~3u;
+                ln.Lp[r] = Lq & ~3u;
+                up = Uq & ~3u;
+            }
+            hb = ln.hl[LR - 1];
+            ub = up;
+            xb0 = x0[LR - 1];
+            xb2 = xup;
+            if (g == 31) {                  // the band's last row: keep all three records
+                int *dst = my_xrow + (size_t)jl * 3;
+                dst[0] = x0[LR - 1];
+                dst[1] = x1[LR - 1];
+                dst[2] = xup;
+            }
+            if (last_band && g == gm && lo + jl == a.n) {
+#pragma unroll
+                for (int r = 0; r < LR; ++r)
+                    if (r == rm) *pt.xlast = x0[r];
+            }
+        }
+    }
+}
+
+__global__ void long_chain_kernel(const LongArgs a, const ParTrace pt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nb = a.nbands;
+    for (int b = 0; b < nb; ++b) pt.entry[b * 4 + 3] = 2;
+    int b = nb - 1, X = *pt.xlast;
+    int ei = a.m, ej = a.n, eL = 0;
+    long long off = 0;
+    bool ok = true;
+    for (;;) {
+        const int ib = b * LBAND;
+        pt.entry[b * 4 + 0] = ei;
+        pt.entry[b * 4 + 1] = ej;
+        pt.entry[b * 4 + 2] = eL;
+        pt.entry[b * 4 + 3] = 0;
+        if (X == X_OUT) { ok = false; break; }
+        int jx = X < 0 ? 0 : (X >> 2);                 // column at which the walk leaves the band
+        long long cap = (long long)(ei - ib) + (ej - jx) + 2;
+        if (b == 0 && X >= 0) cap += jx;               // trailing run along row 0
+        pt.seg_off[b] = off;
+        off += cap;
+        if (X < 0) {                                   // reached column 0 inside band b: the rest is vertical
+            for (int c = b - 1; c >= 0; --c) {
+                pt.entry[c * 4 + 0] = (c + 1) * LBAND;
+                pt.entry[c * 4 + 1] = 0;
+                pt.entry[c * 4 + 2] = 2;
+                pt.entry[c * 4 + 3] = 1;
+                pt.seg_off[c] = off;
+                off += LBAND;
+            }
+            break;
+        }
+        if (b == 0) break;
+        --b;
+        ei = (b + 1) * LBAND;
+        ej = jx;
+        eL = X & 3;
+        if (ej == 0) {                                 // crossed exactly into column 0
+            for (int c = b; c >= 0; --c) {
+                pt.entry[c * 4 + 0] = (c + 1) * LBAND;
+                pt.entry[c * 4 + 1] = 0;
+                pt.entry[c * 4 + 2] = 2;
+                pt.entry[c * 4 + 3] = 1;
+                pt.seg_off[c] = off;
+                off += LBAND;
+            }
+            break;
+        }
+        int lo, hi;
+        long_corridor(b, a.m, a.n, pt.W, lo, hi);
+        if (!(ej > lo && ej <= hi)) { ok = false; break; }
+        X = pt.xrow[((size_t)b * pt.XW + (ej - lo)) * 3 + eL];
+    }
+    if (off > pt.seg_cap) ok = false;
+    *pt.failed = ok ? 0 : 1;
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__(32)
+long_detail_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *s_codes = reinterpret_cast<uint4 *>(smem_raw);
+    int *s_sub = reinterpret_cast<int *>(smem_raw + (size_t)LT_NTB * 32 * sizeof(uint4));
+    int *s_gh;
+    if (*pt.failed) return;
+    const int band = blockIdx.x;
+    const int kind = pt.entry[band * 4 + 3];
+    const int g = threadIdx.x;
+    if (kind == 2) { if (g == 0) pt.seg_len[band] = 0; return; }
+    uint8_t *seg = pt.seg_ops + pt.seg_off[band];
+    const int ib = band * LBAND;
+    int i = pt.entry[band * 4 + 0], j = pt.entry[band * 4 + 1], level = pt.entry[band * 4 + 2];
+    if (kind == 1) {                                   // column 0: gaps in seq_2 only
+        for (int q = g; q < i - ib; q += 32) seg[q] = 2;
+        if (g == 0) pt.seg_len[band] = i - ib;
+        return;
+    }
+    long_load_tables<SIMPLE>(sc, s_sub, s_gh);
+    const TraceConsts k{4u * sc.o, 4u * sc.mm, 4u * sc.gh + 1u, a.big};
+    int cnt = 0, tiles = 0;
+    while (i > ib && j > 0) {
+        const int jc = ((j - 1) / LCC) * LCC;
+        long_refill_codes<SIMPLE>(sc, a, s_sub, s_gh, s_codes, band, jc, j - jc, g, k);
+        ++tiles;
+        if (g == 0) {
+            while (i > ib && j > jc) {
+                const int op = long_tile_dir(s_codes, band, jc, i, j, level);
+                seg[cnt++] = (uint8_t)op;
+                if (op == 0) { --i; --j; } else if (op == 1) { --j; } else { --i; }
+                level = op;
+            }
+        }
+        i = __shfl_sync(FULL, i, 0);
+        j = __shfl_sync(FULL, j, 0);
+        level = __shfl_sync(FULL, level, 0);
+        __syncwarp();
+    }
+    if (g == 0) {
+        for (; j == 0 && i > ib; --i) seg[cnt++] = 2;          // reached column 0 inside the band
+        if (band == 0) for (; j > 0; --j) seg[cnt++] = 1;      // reached row 0: gaps in seq_1
+        pt.seg_len[band] = cnt;
+        atomicAdd(pt.tiles, tiles);
+    }
+}
+
+// positions of the segments in the final stream (walk order: last band first) and the total
+__global__ void long_prefix_kernel(const LongArgs a, const ParTrace pt, long long *n_ops, int *status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || *pt.failed) return;
+    long long pos = 0;
+    for (int b = a.nbands - 1; b >= 0; --b) {
+        pt.seg_pos[b] = pos;
+        pos += pt.seg_len[b];
+    }
+    *n_ops = pos;
+    *status = 0;
+}
+
+__global__ void long_pack_kernel(const LongArgs a, const ParTrace pt, const long long *n_ops, uint32_t *ops) {
+    if (*pt.failed) return;
+    const long long total = *n_ops;
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 16 >= total) return;
+    // band holding op w*16: seg_pos decreases with the band index
+    int lo = 0, hi = a.nbands - 1;
+    while (lo < hi) {                                   // smallest band index b with seg_pos[b] <= w*16
+        const int mid = (lo + hi) >> 1;
+        if (pt.seg_pos[mid] <= w * 16) hi = mid; else lo = mid + 1;
+    }
+    int b = lo;
+    while (b > 0 && pt.seg_len[b] == 0) --b;            // skip empty segments sharing the position
+    long long within = w * 16 - pt.seg_pos[b];
+    uint32_t word = 0;
+    for (int q = 0; q < 16 && w * 16 + q < total; ++q) {
+        while (within >= pt.seg_len[b]) { within -= pt.seg_len[b]; --b; }
+        word |= (uint32_t)pt.seg_ops[pt.seg_off[b] + within] << (2 * q);
+        ++within;
+    }
+    ops[w] = word;
 }
 
 }  // namespace ga

@@ -131,8 +131,9 @@ int ga_get_timing(ga_ctx *ctx, float *ms /* GA_T_COUNT entries */);
  * dp_array_forward + dp_array_backward (globaligner.py:756-821, :366-392, :395-593) for a
  * pair whose direction-code matrix should not be stored: the fill (bands of 128 rows
  * pipelined across all SMs) keeps only band-boundary rows and column checkpoints
- * (about 0.13 bytes per cell); the traceback re-fills the 128 x <=128 tile under the
- * path position from its checkpoints and walks it, tile after tile.  The result is the
+ * (about 0.13 bytes per cell); the traceback re-fills 128 x <=128 tiles under the path
+ * from those checkpoints and walks them -- all bands in parallel once a cheap pass has
+ * located the path's crossing of every band boundary (GA_F_SERIAL: tile after tile).  The result is the
  * same canonical alignment as ga_align_batch gives.  Host buffers; out_ops must hold
  * 4 * ceil((m + n) / 16) + 4 bytes (2-bit ops in walk order, as for ga_align_batch).
  * The reference refuses len(seq_1) * len(seq_2) >= 2e7 (start.py:213); this entry point
@@ -144,6 +145,8 @@ typedef struct {
     int32_t retraced_tiles;           /* tiles the traceback re-filled */
     int64_t checkpoint_bytes;         /* device memory held by the checkpoints */
     int64_t cells;
+    int32_t trace_mode;               /* 1 parallel across bands, 0 sequential, 2 parallel fell back, -1 none */
+    int32_t reserved;
 } ga_long_info;
 int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                   int32_t *out_cost, uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_status,

@@ -17,6 +17,13 @@ pytestmark = pytest.mark.gpu
 
 def _check(ctx, dense, s1, s2, full_oracle=True):
     cost, ops, status, info = ctx.align_long(s1, s2)
+    # the sequential traceback (GA_F_SERIAL) and the band-parallel one must agree exactly
+    cost_s, ops_s, status_s, info_s = ctx.align_long(s1, s2, flags=_native.GA_F_SERIAL)
+    assert (cost, status) == (cost_s, status_s) and info_s["trace_mode"] == 0
+    if status == 0:
+        assert np.array_equal(ops, ops_s)
+    if len(s1) >= 2 and len(s2) >= 2:
+        assert info["trace_mode"] in (1, 2)
     d = _oracle_dense(dense)
     if full_oracle:
         o_ops, o_cost, rc = c_oracle.align_codes(s1, s2, d)
@@ -69,7 +76,7 @@ def test_long_path_equals_batched_kernel_and_golden_cfg1():
     assert list(batch.render(ops, s1, s2)) + [cost] == row["out"][:4]
     bc, bops, boff, blen, bst = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
     assert bc[0] == cost and np.array_equal(_native.unpack_ops(bops, 0, int(blen[0])), ops)
-    assert info["launches"] == 2 and info["retraced_tiles"] >= 4
+    assert info["trace_mode"] == 1 and info["retraced_tiles"] >= 4
     ctx.close()
 
 
@@ -104,7 +111,7 @@ def test_config4_100kb_linear_space():
     ctx = _native.Context(0)
     ctx.set_scheme(dense)
     cost, ops, status, info = ctx.align_long(b.s1, b.s2)
-    assert status == 0 and info["cells"] == 10**10
+    assert status == 0 and info["cells"] == 10**10 and info["trace_mode"] == 1
     assert info["checkpoint_bytes"] < 2.2e9            # vs 5 GB of stored direction codes
     assert rescore(ops, b.s1, b.s2, DenseView(dense)) == cost
     rc, vcost = c_oracle.verify_path(b.s1, b.s2, _oracle_dense(dense), ops)
@@ -116,4 +123,26 @@ def test_config4_100kb_linear_space():
     with start.lifted_length_guard():
         r = find_global_alignment(seq_1=s1, seq_2=s2, **synth.SCHEMES["cfg4"])
     assert r.cost == cost and (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) == batch.render(ops, s1, s2)
+    ctx.close()
+
+
+def test_parallel_trace_falls_back_outside_the_corridor():
+    """Unrelated sequences of very different composition push the path far off the diagonal;
+    whichever form runs, the result is the canonical alignment."""
+    rng = np.random.default_rng(5)
+    ctx = _native.Context(0)
+    dense = _simple_dense(4, 3, 1, 1, 2)
+    ctx.set_scheme(dense)
+    modes = set()
+    for trial in range(6):
+        m, n = int(rng.integers(3000, 6000)), int(rng.integers(3000, 6000))
+        s1 = rng.integers(0, 4, m).astype(np.uint8)
+        s2 = rng.integers(0, 4, n).astype(np.uint8)
+        if trial % 2 == 0:          # a long insertion at one end: the path hugs an edge
+            s2 = np.concatenate([rng.integers(0, 4, 2500).astype(np.uint8), s1[: n - 2500]])
+        cost, ops, status, info = ctx.align_long(s1, s2)
+        modes.add(info["trace_mode"])
+        rc, vcost = c_oracle.verify_path(s1, s2, _oracle_dense(dense), ops)
+        assert rc == 0 and vcost == cost and status == 0
+    assert modes <= {1, 2}
     ctx.close()
