@@ -30,7 +30,7 @@ struct KernelCfg {
     void (*launch_fill)(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
                         const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const uint8_t *s1,
                         const long long *off1, const uint8_t *s2, const long long *off2,
-                        uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost);
+                        uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost, int persistent);
     void (*launch_walk)(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, const UniformTiles &ut, int pair_lo,
                         int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
                         const long long *off2, const uint32_t *codes, uint8_t *out_ops,
@@ -41,9 +41,10 @@ template <bool P, bool S, int R, int G>
 static void launch_fill_t(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
                           const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const uint8_t *s1,
                           const long long *off1, const uint8_t *s2, const long long *off2,
-                          uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost) {
+                          uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost,
+                          int persistent) {
     fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, ut, n_tiles, counter, s1, off1, s2, off2,
-                                                     codes, bnd, bnd_stride, sb_stride, out_cost);
+                                                     codes, bnd, bnd_stride, sb_stride, out_cost, persistent);
 }
 template <bool P, int R, int G>
 static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, const UniformTiles &ut, int pair_lo,
@@ -139,6 +140,8 @@ struct ga_ctx {
     uint32_t plan_flags = 0;
     bool serial = false;
     bool uniform = false;             // every pair has the same (m, n): arithmetic tile descriptors
+    bool plan_for_io = false;         // planning on behalf of the host-buffer entry point
+    bool persistent = true;           // fill grid: machine-filling + tile counter, or one tile per warp
     int uniM = 0, uniN = 0;
     long long uni_u4 = 0;
     DevBuf d_tiles, d_codes[2], d_bnd[2], d_counter;
@@ -230,7 +233,12 @@ extern "C" int ga_ctx_create(int device, ga_ctx **out) {
         return GA_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    for (auto &a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+    {   // walk / copy streams outrank the fill streams: their blocks take freed SM slots first
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        for (int k = 0; k < 6; ++k)
+            cudaStreamCreateWithPriority(&ctx->aux[k], cudaStreamNonBlocking, k < 2 ? lo_pri : hi_pri);
+    }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->in_piece) cudaEventCreate(&e);
@@ -505,7 +513,11 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     long long limit_u4 = hard_u4;
     if (!serial) {
         const long long min_u4 = ((long long)1 << 30) / 16;            // do not cut below 1 GiB of codes
-        limit_u4 = std::min(hard_u4, std::max(min_u4, (total_u4 + 3) / 4));
+        // measured on 1M x (150 x 150): device-resident runs are fastest with 2-4 chunks (fewer
+        // fill tails), the host-buffer path with ~8 (finer overlap of copies and kernels)
+        int want_chunks = ctx->plan_for_io ? 8 : 4;
+        if (const char *e = getenv("GA_CHUNKS")) want_chunks = std::max(1, atoi(e));
+        limit_u4 = std::min(hard_u4, std::max(min_u4, (total_u4 + want_chunks - 1) / want_chunks));
     }
     Chunk cur{0, 0, 0, 0, 0};
     long long max_chunk_u4 = 0;
@@ -580,6 +592,10 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     ctx->plan_flags = flags;
     ctx->serial = serial;
     ctx->uniform = uniform;
+    // one-tile-per-warp grids measured slower than the persistent grid (10.7 vs 10.1 ms per 1M
+    // pairs); kept behind an environment switch for experiments.  Multi-pass tiles always need
+    // the persistent form (per-warp boundary scratch).
+    ctx->persistent = maxM > L.BAND || getenv("GA_NONPERSISTENT_FILL") == nullptr;
     ctx->uniM = maxM;
     ctx->uniN = maxN;
     ctx->uni_u4 = uni_u4;
@@ -649,13 +665,14 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         }
         if (!serial && c >= 2) CK(cudaStreamWaitEvent(sF, ctx->cev[c - 2].w1, 0));   // code buffer free
         CK(cudaEventRecord(E.f0, sF));
-        const int grid = std::min(ctx->grid, (n_tiles + 3) / 4);
+        const bool persistent = ctx->persistent || serial;
+        const int grid = persistent ? std::min(ctx->grid, (n_tiles + 3) / 4) : (n_tiles + 3) / 4;
         const TileDesc *d_tiles = ctx->uniform ? nullptr : (const TileDesc *)ctx->d_tiles.p + ch.tile_lo;
         const UniformTiles ut{ctx->uniM, ctx->uniN, ch.pair_lo, ch.pair_hi, ctx->uni_u4};
         cfg->launch_fill(grid, ctx->smem, sF, ctx->sc, d_tiles, ut,
                          n_tiles, (int *)ctx->d_counter.p + c, d_s1, (const long long *)d_s1_off, d_s2,
                          (const long long *)d_s2_off, (uint4 *)ctx->d_codes[b].p, (int2 *)ctx->d_bnd[b].p,
-                         ctx->bnd_stride, ctx->sb_stride, d_cost);
+                         ctx->bnd_stride, ctx->sb_stride, d_cost, persistent ? 1 : 0);
         CK(cudaGetLastError());
         CK(cudaEventRecord(E.f1, sF));
         if (sW != sF) CK(cudaStreamWaitEvent(sW, E.f1, 0));
@@ -793,7 +810,9 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
         if ((rc = upload_piece(k))) return rc;
     ht0.lap("align: enqueue uploads");
     HostTimer ht;
+    ctx->plan_for_io = true;
     rc = ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
+    ctx->plan_for_io = false;
     if (rc) { cudaStreamSynchronize(sIn); return rc; }
     for (int k = EARLY; k < IN_PIECES; ++k)
         if ((rc = upload_piece(k))) return rc;

@@ -70,7 +70,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
             const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
             const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
             uint4 *__restrict__ codes, int2 *bnd, int bnd_stride, int sb_stride,
-            int *__restrict__ out_cost) {
+            int *__restrict__ out_cost, int persistent) {
     using L = Lay<PACKED, R, G>;
     using V = VOps<PACKED>;
     using BT = typename std::conditional<PACKED, uint32_t, uint8_t>::type;
@@ -107,10 +107,18 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     // a*k+b forms that must stay IMADs (FMA pipe); see SchemeDev::k_one
     const unsigned K1 = sc.k_one, K4 = sc.k_four, KM1 = sc.k_minus_one;
 
-    for (;;) {
-        int tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1);
-        tile = __shfl_sync(FULL, tile, 0);
+    // persistent: a machine-filling grid whose warps claim tiles from an atomic counter (needed
+    // for multi-pass tiles: the boundary-row scratch is per resident warp).  Otherwise one tile
+    // per warp and the block retires, which lets the block scheduler slip the (high-priority)
+    // walk blocks of the previous chunk in between.
+    for (int round = 0;; ++round) {
+        int tile = gwarp;
+        if (persistent) {
+            if (lane == 0) tile = atomicAdd(tile_counter, 1);
+            tile = __shfl_sync(FULL, tile, 0);
+        } else if (round > 0) {
+            break;
+        }
         if (tile >= n_tiles) break;
         const TileDesc td = tile_desc(tiles, ut, tile, L::PPT);
 
