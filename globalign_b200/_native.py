@@ -20,6 +20,8 @@ GA_F_DEFAULT = 0
 GA_F_FORCE_GENERIC = 1
 GA_F_COST_ONLY = 2
 GA_F_SERIAL = 4
+GA_F_SEQ_4BIT = 8
+GA_F_SEQ_2BIT = 16
 T_H2D, T_FILL, T_WALK, T_D2H, T_TOTAL, T_COUNT = 0, 1, 2, 3, 4, 5
 
 #: every symbol include/globalign_b200.h declares (checked by the CPU tests)
@@ -250,6 +252,26 @@ class Context:
                                             C.byref(cost), _ptr(packed), C.byref(nops), C.byref(neval),
                                             C.byref(status)))
         return cost.value, unpack_ops(packed, 0, nops.value), neval.value, status.value
+
+
+def pack_letters(codes: np.ndarray, bits: int) -> np.ndarray:
+    """uint8 letter indices -> little-endian `bits`-bit stream (bits = 2 or 4), the layout
+    GA_F_SEQ_2BIT / GA_F_SEQ_4BIT expect (letter k in bits [k*bits, (k+1)*bits))."""
+    if bits == 8:
+        return np.ascontiguousarray(codes, dtype=np.uint8)
+    per = 8 // bits
+    n = len(codes)
+    padded = np.zeros(-(-n // per) * per, dtype=np.uint8)
+    padded[:n] = codes
+    lanes = padded.reshape(-1, per)
+    out = np.zeros(len(lanes), dtype=np.uint8)
+    for k in range(per):
+        out |= (lanes[:, k] << (bits * k)).astype(np.uint8)
+    return out
+
+
+def seq_flag(bits: int) -> int:
+    return {8: 0, 4: GA_F_SEQ_4BIT, 2: GA_F_SEQ_2BIT}[bits]
 
 
 def ops_offsets(off1, off2) -> np.ndarray:

@@ -357,6 +357,7 @@ extern "C" int ga_set_scheme(ga_ctx *ctx, int A, const int32_t *sub, const int32
     sc.k_one = 1u;
     sc.k_four = 4u;
     sc.k_minus_one = 0xffffffffu;
+    sc.seq_bits = 8;
     ctx->uniform_gaps = uniform;
     ctx->h_gh.assign(gap_h, gap_h + A);
     ctx->h_gv.assign(gap_v, gap_v + A);
@@ -405,6 +406,12 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     HostTimer ht;
     ctx->have_plan = false;
     for (float &v : ctx->ms) v = 0.f;
+    {
+        const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
+        if ((flags & GA_F_SEQ_2BIT) && (flags & GA_F_SEQ_4BIT)) return fail(ctx, GA_E_ARG, "choose one sequence packing");
+        if (ctx->sc.A > (1 << bits)) return fail(ctx, GA_E_ARG, "alphabet of %d letters does not fit %d-bit packed sequences", ctx->sc.A, bits);
+        ctx->sc.seq_bits = bits;
+    }
     int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30;
     int64_t cells = 0;
     {
@@ -772,7 +779,8 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     const int64_t t1 = s1_off[n_pairs], t2 = s2_off[n_pairs];
     if (t1 < n_pairs || t2 < n_pairs || s1_off[0] != 0 || s2_off[0] != 0)
         return fail(ctx, GA_E_ARG, "offset arrays must start at 0 and be increasing");
-    const size_t b1 = (size_t)t1, b2 = (size_t)t2;
+    const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
+    const size_t b1 = (size_t)((t1 * bits + 7) / 8), b2 = (size_t)((t2 * bits + 7) / 8);
     const size_t offb = (size_t)(n_pairs + 1) * 8;
     const size_t opsb = cost_only ? 0 : (size_t)out_ops_off[n_pairs];
     int rc;
@@ -796,8 +804,9 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, sIn));
     if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
     auto upload_piece = [&](int k) -> int {
-        const int64_t a0 = t1 * k / IN_PIECES, a1 = t1 * (k + 1) / IN_PIECES;
-        const int64_t c0 = t2 * k / IN_PIECES, c1 = t2 * (k + 1) / IN_PIECES;
+        // piece k = letters [t*k/8, t*(k+1)/8) -> the bytes that hold them (edges may be sent twice)
+        const int64_t a0 = (t1 * k / IN_PIECES) * bits / 8, a1 = ((t1 * (k + 1) / IN_PIECES) * bits + 7) / 8;
+        const int64_t c0 = (t2 * k / IN_PIECES) * bits / 8, c1 = ((t2 * (k + 1) / IN_PIECES) * bits + 7) / 8;
         if (a1 > a0) CK(cudaMemcpyAsync((uint8_t *)ctx->d_s1.p + a0, s1 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, sIn));
         if (c1 > c0) CK(cudaMemcpyAsync((uint8_t *)ctx->d_s2.p + c0, s2 + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, sIn));
         CK(cudaEventRecord(ctx->in_piece[k], sIn));
@@ -842,6 +851,7 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     if (!s1 || !s2 || !out_cost || m < 1 || n < 1 || m > (1 << 28) || n > (1 << 28) ||
         (!cost_only && (!out_ops || !out_n_ops || !out_status)))
         return fail(ctx, GA_E_ARG, "bad arguments to ga_align_long");
+    ctx->sc.seq_bits = 8;               // this entry point takes one letter per byte
     const SchemeDev &sc = ctx->sc;
     if (!sc.simple && sc.A > 64) return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
     {

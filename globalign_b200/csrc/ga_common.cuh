@@ -38,6 +38,7 @@ struct SchemeDev {
     // pipe) instead of IADD3/LOP3/LEA (ALU pipe): the ALU pipe is the bottleneck of
     // the cell update (profiles/README.md), the FMA pipe would otherwise idle.
     unsigned k_one, k_four, k_minus_one;
+    int seq_bits;        // letters per input byte: 8 (one letter per byte), 4 or 2 (bit-packed stream)
 };
 
 struct TileDesc {
@@ -46,6 +47,14 @@ struct TileDesc {
     int n_pairs;         // pairs in the tile (<= items per warp * pairs per item)
     int M, N;            // longest seq_1 / seq_2 in the tile
 };
+
+// Letter k of a sequence buffer.  seq_bits = 8: one letter per byte.  4 / 2: the letters form a
+// little-endian bit stream (letter k in bits [k*bits, (k+1)*bits) of the byte array), the usual
+// packed nucleotide layouts; offsets stay in letters.
+__device__ __forceinline__ unsigned ld_letter(const uint8_t *__restrict__ s, long long k, int bits) {
+    const long long bit = k * bits;
+    return ((unsigned)s[bit >> 3] >> (unsigned)(bit & 7)) & ((1u << bits) - 1u);
+}
 
 // When every pair of a chunk has the same (m, n) the tile descriptors are arithmetic and are
 // not uploaded: tiles == nullptr and this struct (a kernel parameter) describes them all.

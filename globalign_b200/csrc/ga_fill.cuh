@@ -11,7 +11,8 @@
 // t computes column j = t - g + 1 of those rows (anti-diagonal wavefront).  The
 // bottom row of a lane (h = min of the three levels, and U = the level-2
 // candidate for the row below) travels to lane g+1 by warp shuffle; nothing but
-// the letters of seq_2 goes through shared memory.
+// the letters of seq_2 goes through shared memory (unpacked there from the 8-, 4- or 2-bit
+// input stream, see ld_letter).
 //
 // Arithmetic (all integer, exact):  values are kept multiplied by 4; before a
 // three-way minimum the level index (0,1,2) is added in the two low bits, so a
@@ -153,9 +154,9 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
             const int na = (int)(off2[qa + 1] - oa), nb = (int)(off2[qb + 1] - ob);
             BT *row = sb + (size_t)q * sb_stride;
             for (int c = lane; c < sb_len; c += 32) {
-                const unsigned va = c < na ? (unsigned)s2[oa + c] : padb;
+                const unsigned va = c < na ? ld_letter(s2, oa + c, sc.seq_bits) : padb;
                 if (PACKED) {
-                    const unsigned vb = c < nb ? (unsigned)s2[ob + c] : padb;
+                    const unsigned vb = c < nb ? ld_letter(s2, ob + c, sc.seq_bits) : padb;
                     row[c] = (BT)(va | (vb << 16));
                 } else {
                     row[c] = (BT)va;
@@ -179,9 +180,9 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int row = ib + r;
-                    const unsigned la = row < mA ? (unsigned)s1[a1 + row] : (unsigned)PAD_A;
+                    const unsigned la = row < mA ? ld_letter(s1, a1 + row, sc.seq_bits) : (unsigned)PAD_A;
                     if (PACKED) {
-                        const unsigned lb = row < mB ? (unsigned)s1[b1 + row] : (unsigned)PAD_A;
+                        const unsigned lb = row < mB ? ld_letter(s1, b1 + row, sc.seq_bits) : (unsigned)PAD_A;
                         aw[r] = la | (lb << 16);
                     } else {
                         aw[r] = la;
@@ -195,7 +196,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int row = ib + r;
-                    const int a = row < mA ? (int)s1[a1 + row] : sc.A;
+                    const int a = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
                     aw[r] = (unsigned)(a * sc.A);
                     gvT[r] = (unsigned)sc.gv4t[a];
                     gvr[r] = sc.gv_raw[a];

@@ -393,3 +393,24 @@ def test_fasta_batch_and_batch_writer(tmp_path):
     one = find_global_alignment(input_fasta=str(fa))      # the reference-style call reads the first two records
     assert text.startswith(one.__str__(desc_1=">a0", desc_2=">b0"))
     assert text.count("\nscore: ") == len(recs)
+
+
+# ------------------------------------------------------------------ bit-packed sequence input
+@pytest.mark.parametrize("bits,A", [(2, 4), (4, 4), (4, 13), (2, 3)])
+def test_packed_sequence_streams_give_identical_results(bits, A):
+    """GA_F_SEQ_2BIT / GA_F_SEQ_4BIT: the same batch as little-endian 2-bit / 4-bit letter
+    streams (what packed nucleotide files hold) must give byte-identical outputs."""
+    rng = random.Random(bits * 100 + A)
+    ctx = _native.Context(0)
+    for dense in (_simple_dense(A, 4, 2, 1, 6), _table_dense(rng, A, 3)):
+        ctx.set_scheme(dense)
+        s1, off1, s2, off2 = _random_batch(rng, 333, A, 170, 190)
+        plain = ctx.align_batch(s1, off1, s2, off2)
+        packed = ctx.align_batch(_native.pack_letters(s1, bits), off1, _native.pack_letters(s2, bits), off2,
+                                 flags=_native.seq_flag(bits))
+        for x, y in zip(plain, packed):
+            assert np.array_equal(x, y)
+    with pytest.raises(RuntimeError):                 # 5 letters do not fit 2 bits
+        ctx.set_scheme(_simple_dense(5, 4, 2, 1, 6))
+        ctx.plan_batch(off1, off2, flags=_native.GA_F_SEQ_2BIT)
+    ctx.close()
