@@ -414,3 +414,48 @@ def test_packed_sequence_streams_give_identical_results(bits, A):
         ctx.set_scheme(_simple_dense(5, 4, 2, 1, 6))
         ctx.plan_batch(off1, off2, flags=_native.GA_F_SEQ_2BIT)
     ctx.close()
+
+
+# ------------------------------------------------------------------ more edges
+def test_long_seq2_in_batched_kernels_and_auto_routing():
+    """seq_2 up to 32768 letters is staged in shared memory by the batched kernels; beyond that
+    (or beyond 4M cells) find_global_alignment routes to the long-pair path."""
+    rng = random.Random(9)
+    ctx = _native.Context(0)
+    for dense, A in ((_simple_dense(4, 5, 2, 2, 10), 4), (_table_dense(rng, 20, 7), 20)):
+        ctx.set_scheme(dense)
+        s1 = np.array([rng.randrange(A) for _ in range(300 + 90)], dtype=np.uint8)
+        s2 = np.array([rng.randrange(A) for _ in range(20000 + 5000)], dtype=np.uint8)
+        off1 = np.array([0, 300, 390], dtype=np.int64)
+        off2 = np.array([0, 20000, 25000], dtype=np.int64)
+        out = ctx.align_batch(s1, off1, s2, off2)
+        _compare_with_oracle(s1, off1, s2, off2, dense, out)
+    with pytest.raises(RuntimeError):
+        ctx.plan_batch(np.array([0, 10], dtype=np.int64), np.array([0, 40000], dtype=np.int64))
+    ctx.close()
+    a = "ACGT" * 3
+    b = "".join(rng.choice("ACGT") for _ in range(33000))
+    with start.lifted_length_guard():
+        r = find_global_alignment(seq_1=a, seq_2=b)
+    ops, cost, rc = c_oracle.align(a, b, r.costing_mat, r.gap_open_cost)
+    assert rc == 0 and r.cost == cost and (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) == batch.render(ops, a, b)
+
+
+def test_one_letter_and_large_alphabets():
+    r = find_global_alignment(seq_1="AAAAAAA", seq_2="AAAA")
+    ops, cost, rc = c_oracle.align("AAAAAAA", "AAAA", r.costing_mat, r.gap_open_cost)
+    assert r.cost == cost and r.seq_1_aligned == "AAAAAAA" and r.seq_2_aligned.count("-") == 3
+    letters = "".join(chr(0x100 + k) for k in range(120))          # 120 distinct non-ASCII letters
+    rng = random.Random(3)
+    s1 = "".join(rng.choice(letters) for _ in range(200))
+    s2 = "".join(rng.choice(letters) if rng.random() < 0.3 else c for c in s1[5:180])
+    r = find_global_alignment(seq_1=s1, seq_2=s2, mismatch_cost=3, gap_open_cost=2, gap_extension_cost=1)
+    ops, cost, rc = c_oracle.align(s1.upper(), s2.upper(), r.costing_mat, r.gap_open_cost)
+    assert rc == 0 and r.cost == cost
+    assert (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) == batch.render(ops, s1.upper(), s2.upper())
+    ctx = _native.Context(0)
+    big = _table_dense(rng, 70, 2)                                   # table scheme with > 64 letters
+    ctx.set_scheme(big)
+    with pytest.raises(RuntimeError):
+        ctx.plan_batch(np.array([0, 10], dtype=np.int64), np.array([0, 10], dtype=np.int64))
+    ctx.close()
