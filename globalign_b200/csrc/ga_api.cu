@@ -909,7 +909,6 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     a.nck = nck;
     a.big = (unsigned)((long long)(sc.max_cost + 1) * std::max(m, n));
     a.out_cost = misc + 1;
-    a.debug_nosync = getenv("GA_DEBUG_LONG_NOSYNC") ? 1 : 0;
     const size_t table = sc.simple ? 0 : ((((size_t)(sc.A + 1) * sc.A + sc.A) * 4 + 15) & ~(size_t)15);
     const int grid = std::min((nbands + LWARPS - 1) / LWARPS, ctx->sm_count * 4);
     CK(cudaEventRecord(ctx->ev[2], st));

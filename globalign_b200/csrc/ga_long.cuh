@@ -48,7 +48,6 @@ struct LongArgs {
     int nbands, nck;
     unsigned big;                   // reference sentinel (max_cost+1)*max(m,n)
     int *out_cost;
-    int debug_nosync;               // timing experiments only: do not wait for the band above
 };
 
 template <bool SIMPLE>
@@ -115,6 +114,56 @@ __device__ __forceinline__ void long_cells(const SchemeDev &sc, const int *s_sub
 // ---------------------------------------------------------------------------- K2
 constexpr int LWARPS = 4;           // independent band-sweeping warps per block (one per scheduler)
 
+// One block of LSYNC steps of a band sweep, fully unrolled (compile-time shuffle lanes and store
+// offsets).  The fill keeps no direction codes, so it needs no argmin tags: values stay
+// multiples of 4 (the traceback kernels' domain) and the per-cell tag clears disappear --
+// min over tagged values, cleared, equals min over the untagged ones.  CHECK = false is the
+// steady state (every lane inside the matrix for the whole block).
+template <bool SIMPLE, bool CHECK>
+__device__ __forceinline__ void long_fill_block(LongLane<SIMPLE> &ln, const int *s_sub, const int *s_gh,
+                                                unsigned &rh_prev, unsigned &hb, unsigned &ub, unsigned &bv,
+                                                unsigned bblk, int2 tblk, int g, int j0, int N, int2 *brow_j0,
+                                                int2 *my_vchk, unsigned gh4c, unsigned o4, unsigned mm4) {
+#pragma unroll
+    for (int u = 0; u < LSYNC; ++u) {
+        const int j = j0 + u;
+        unsigned rh = __shfl_up_sync(FULL, hb, 1);
+        unsigned ru = __shfl_up_sync(FULL, ub, 1);
+        unsigned bin = __shfl_up_sync(FULL, bv, 1);
+        const unsigned b0 = __shfl_sync(FULL, bblk, u);
+        const unsigned th = (unsigned)__shfl_sync(FULL, tblk.x, u);
+        const unsigned tu = (unsigned)__shfl_sync(FULL, tblk.y, u);
+        if (g == 0) { bin = b0; rh = th; ru = tu; }
+        bv = bin;
+        if (!CHECK || (j >= 1 && j <= N)) {
+            unsigned diag = rh_prev, up = ru;
+            rh_prev = rh;
+            const unsigned gh4 = SIMPLE ? gh4c : (unsigned)(s_gh[bv] - 1);
+#pragma unroll
+            for (int r = 0; r < LR; ++r) {
+                unsigned d0;
+                if (SIMPLE) d0 = diag + (ln.aw[r] != bv ? mm4 : 0u);
+                else d0 = diag + (unsigned)s_sub[ln.aw[r] + bv];
+                const unsigned d1 = ln.Lp[r] + gh4;
+                const unsigned d2 = up + ln.gvT[r];
+                const unsigned h = (unsigned)__vimin3_s32((int)d0, (int)d1, (int)d2);
+                diag = ln.hl[r];
+                ln.hl[r] = h;
+                ln.Lp[r] = (unsigned)__viaddmin_s32((int)h, (int)o4, (int)d1);
+                up = (unsigned)__viaddmin_s32((int)h, (int)o4, (int)d2);
+            }
+            hb = ln.hl[LR - 1];
+            ub = up;
+            if (g == 31) __stcg(brow_j0 + u, make_int2((int)hb, (int)ub));   // one 64-bit store
+            if ((j & (LCC - 1)) == 0) {
+                int2 *dst = my_vchk + (size_t)(j / LCC) * (32 * LR);
+#pragma unroll
+                for (int r = 0; r < LR; ++r) __stcg(dst + r, make_int2((int)ln.hl[r], (int)ln.Lp[r]));
+            }
+        }
+    }
+}
+
 template <bool SIMPLE>
 __global__ void __launch_bounds__(32 * LWARPS)
 long_fill_kernel(const SchemeDev sc, const LongArgs a) {
@@ -130,7 +179,7 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
     }
     const int g = threadIdx.x & 31;     // the warps of a block never synchronise with each other again
     const unsigned o4 = 4u * sc.o, mm4 = 4u * sc.mm;
-    const unsigned ghTc = 4u * sc.gh + 1u;
+    const unsigned gh4c = 4u * sc.gh;
     const unsigned big = a.big;
     // hot fields in registers (kernel parameters live in constant memory; an LDC inside
     // the step loop sits on the critical path of a lone warp)
@@ -138,7 +187,6 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
     const uint8_t *const S2 = a.s2;
     const int *const ROWSUM = a.rowsum;
     const unsigned O = (unsigned)sc.o;
-    const int nosync = a.debug_nosync;
     for (;;) {
         int band = 0;
         if (g == 0) band = atomicAdd(a.band_counter, 1);
@@ -152,63 +200,48 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             const unsigned c = (unsigned)a.colsum[min(ib + r + 1, a.m)];
             ln.hl[r] = min(big, c) << 2;
             ln.Lp[r] = min(big, c + sc.o) << 2;
+            ln.gvT[r] -= 2u;                         // untagged vertical gap cost (4 * gap_v)
         }
         unsigned rh_prev = 0;
         if (ib != 0) rh_prev = min(big, (unsigned)a.colsum[min(ib, a.m)]) << 2;
-        const int pm = (M - 1) / LBAND, gm = ((M - 1) % LBAND) / LR, rm = (M - 1) % LR;
         int2 *my_brow = a.brow + (size_t)band * (N + 1);
         const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (N + 1);
         int2 *my_vchk = a.vchk + ((size_t)band * a.nck) * (32 * LR) + (size_t)g * LR;
 
         unsigned hb = 0, ub = 0, bv = 0;
-        unsigned bblk = 0;
-        int2 tblk = make_int2(0, 0);
         const int nsteps = N + 31;
-        for (int t = 0; t < nsteps; ++t) {
-            if ((t & (LSYNC - 1)) == 0) {
-                // next 32 columns: letters of seq_2 and the boundary row above this band
-                const int c0 = t + 1;                       // first column of the block (1-based)
-                const int cj = c0 + (g & (LSYNC - 1));      // lanes >= LSYNC duplicate a valid column
-                bblk = cj <= N ? (unsigned)S2[cj - 1] : (SIMPLE ? (unsigned)PAD_B : 0u);
-                if (band > 0 && c0 <= N) {
-                    if (cj <= N) {
-                        do { tblk = ld_volatile_int2(up_brow + cj); } while (tblk.x < 0 && !nosync);   // -1 = not yet written
-                    }
-                    __syncwarp();
-                } else if (band == 0) {
-                    const unsigned rj = (unsigned)ROWSUM[min(cj, N)];
-                    tblk = make_int2((int)(min(big, rj) << 2), (int)(min(big, rj + O) << 2));
+        for (int t0 = 0; t0 < nsteps; t0 += LSYNC) {
+            // next LSYNC columns: letters of seq_2 and the boundary row above this band
+            const int c0 = t0 + 1;                          // first column of the block (1-based)
+            const int cj = c0 + (g & (LSYNC - 1));          // lanes >= LSYNC duplicate a valid column
+            const unsigned bblk = cj <= N ? (unsigned)S2[cj - 1] : (SIMPLE ? (unsigned)PAD_B : 0u);
+            int2 tblk = make_int2(0, 0);
+            if (band > 0) {
+                if (cj <= N) {
+                    do { tblk = ld_volatile_int2(up_brow + cj); } while (tblk.x < 0);   // -1 = not yet written
                 }
+                __syncwarp();
+            } else {
+                const unsigned rj = (unsigned)ROWSUM[min(cj, N)];
+                tblk = make_int2((int)(min(big, rj) << 2), (int)(min(big, rj + O) << 2));
             }
-            const int j = t - g + 1;
-            unsigned rh = __shfl_up_sync(FULL, hb, 1);
-            unsigned ru = __shfl_up_sync(FULL, ub, 1);
-            unsigned bin = __shfl_up_sync(FULL, bv, 1);
-            const unsigned b0 = __shfl_sync(FULL, bblk, t & (LSYNC - 1));
-            const unsigned th = (unsigned)__shfl_sync(FULL, tblk.x, t & (LSYNC - 1));
-            const unsigned tu = (unsigned)__shfl_sync(FULL, tblk.y, t & (LSYNC - 1));
-            if (g == 0) { bin = b0; rh = th; ru = tu; }
-            bv = bin;
-            if (j >= 1 && j <= N) {
-                unsigned diag = rh_prev;
-                rh_prev = rh;
-                const unsigned ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
-                unsigned w0, w1;
-                long_cells<SIMPLE, false>(sc, s_sub, ln, diag, ru, bv, ghT, o4, mm4, hb, ub, w0, w1);
-                if (g == 31) __stcg(my_brow + j, make_int2((int)hb, (int)ub));   // one 64-bit store
-                if ((j & (LCC - 1)) == 0) {
-                    int2 *dst = my_vchk + (size_t)(j / LCC) * (32 * LR);
+            const int j0 = t0 - g + 1;                      // my column at the first step of the block
+            int2 *brow_j0 = my_brow + j0;
+            if (t0 >= 31 && t0 + LSYNC <= N)
+                long_fill_block<SIMPLE, false>(ln, s_sub, s_gh, rh_prev, hb, ub, bv, bblk, tblk, g, j0, N,
+                                               brow_j0, my_vchk, gh4c, o4, mm4);
+            else
+                long_fill_block<SIMPLE, true>(ln, s_sub, s_gh, rh_prev, hb, ub, bv, bblk, tblk, g, j0, N,
+                                              brow_j0, my_vchk, gh4c, o4, mm4);
+        }
+        // the last active step of every lane was column N: hl[] now holds h(row, N)
+        if (band == (M - 1) / LBAND && g == ((M - 1) % LBAND) / LR) {
+            const int rm = (M - 1) % LR;
+            unsigned v = 0;
 #pragma unroll
-                    for (int r = 0; r < LR; ++r) __stcg(dst + r, make_int2((int)ln.hl[r], (int)ln.Lp[r]));
-                }
-                if (j == N && band == pm && g == gm) {
-                    unsigned v = 0;
-#pragma unroll
-                    for (int r = 0; r < LR; ++r)
-                        if (r == rm) v = ln.hl[r];
-                    *a.out_cost = (int)(v >> 2);
-                }
-            }
+            for (int r = 0; r < LR; ++r)
+                if (r == rm) v = ln.hl[r];
+            *a.out_cost = (int)(v >> 2);
         }
     }
 }
