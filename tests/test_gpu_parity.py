@@ -459,3 +459,26 @@ def test_one_letter_and_large_alphabets():
     with pytest.raises(RuntimeError):
         ctx.plan_batch(np.array([0, 10], dtype=np.int64), np.array([0, 10], dtype=np.int64))
     ctx.close()
+
+
+def test_pipeline_variants_on_mixed_length_batches():
+    """Non-uniform batches cut into many chunks (uploaded tile descriptors, chunk-relative code
+    offsets, ping-pong scratch), the serial plan, and cost-only must all agree with the oracle."""
+    rng = random.Random(21)
+    ctx = _native.Context(0)
+    for dense, A in ((_simple_dense(4, 5, 2, 2, 10), 4), (_table_dense(rng, 20, 8), 20)):
+        ctx.set_scheme(dense)
+        data = _random_batch(rng, 1500, A, 260, 240)
+        ctx.set_scratch_limit(64 << 30)
+        whole = ctx.align_batch(*data)
+        assert ctx.plan_info()["n_chunks"] == 1
+        _compare_with_oracle(*data, dense, whole, sample=range(0, 1500, 7))
+        ctx.set_scratch_limit(6 << 20)
+        chunked = ctx.align_batch(*data)
+        assert ctx.plan_info()["n_chunks"] >= 5
+        serial = ctx.align_batch(*data, flags=_native.GA_F_SERIAL)
+        only = ctx.align_batch(*data, flags=_native.GA_F_COST_ONLY)
+        for x, y, z in zip(whole, chunked, serial):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+        assert np.array_equal(only[0], whole[0])
+    ctx.close()
