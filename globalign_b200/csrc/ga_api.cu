@@ -472,9 +472,7 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     long long total_u4 = 0, biggest = 0, uni_u4 = 0;
     if (uniform) {
         // every tile is the same: no descriptor array, the kernels compute them (UniformTiles)
-        const long long npass = (maxM + L.BAND - 1) / L.BAND;
-        const long long nTB = (maxN + L.G - 1 + L.S - 1) / L.S;
-        uni_u4 = npass * nTB * L.NQ * 32;
+        uni_u4 = tile_code_u4(maxM, maxN, L.G, L.BAND, L.NW);
         total_u4 = uni_u4 * n_tiles;
         biggest = uni_u4;
         ctx->tiles.clear();
@@ -493,9 +491,7 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
                     M = std::max<int>(M, (int)(s1_off[p + 1] - s1_off[p]));
                     N = std::max<int>(N, (int)(s2_off[p + 1] - s2_off[p]));
                 }
-                const long long npass = (M + L.BAND - 1) / L.BAND;
-                const long long nTB = (N + L.G - 1 + L.S - 1) / L.S;
-                tile_u4[(size_t)t] = npass * nTB * L.NQ * 32;
+                tile_u4[(size_t)t] = tile_code_u4(M, N, L.G, L.BAND, L.NW);
                 tot += tile_u4[(size_t)t];
                 big = std::max(big, tile_u4[(size_t)t]);
                 td.first_pair = (int)lo;

@@ -142,7 +142,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         const unsigned bigB = (unsigned)(sc.max_cost + 1) * (unsigned)max(mB, nB);
 
         const int nsteps = td.N + G - 1;
-        const int nTB = (nsteps + L::S - 1) / L::S;
+        const int nTB = (nsteps + L::S - 1) / L::S;        // store blocks of 2 steps
         const int sb_len = nTB * L::S + 1;
 
         // ---- stage the seq_2 letters of every item of the tile in shared memory
@@ -227,7 +227,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
             int rowj = sc.o;                       // TABLE: running row-0 value (pass 0, lane g == 0)
             int2 nxt = make_int2(0, 0);
             if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
-            uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::NQ * 32) + lane;
+            uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::WPP * 32) + lane;
 
             for (int tb = 0; tb < nTB; ++tb) {
                 unsigned stg[L::S * L::NW];
@@ -314,10 +314,11 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                         }
                     }
                 }
+                // one 128-bit store per row-word: both planes of the two staged steps; lane-adjacent
 #pragma unroll
-                for (int q = 0; q < L::NQ; ++q)
-                    cbase[(size_t)(tb * L::NQ + q) * 32] =
-                        make_uint4(stg[4 * q], stg[4 * q + 1], stg[4 * q + 2], stg[4 * q + 3]);
+                for (int w = 0; w < L::WPP; ++w)
+                    cbase[(size_t)(tb * L::WPP + w) * 32] =
+                        make_uint4(stg[w], stg[L::NW + w], stg[L::WPP + w], stg[L::NW + L::WPP + w]);
             }
             __syncwarp();
         }

@@ -48,7 +48,7 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const long long a1 = off1[p], a2 = off2[p];
     const int m = (int)(off1[p + 1] - a1), n = (int)(off2[p + 1] - a2);
     const int nsteps = td.N + G - 1;
-    const int nTB = (nsteps + L::S - 1) / L::S;
+    const int nB2 = (nsteps + 1) / 2;
     const uint32_t *cw = codes + 4 * td.code_off;
     const int lane0 = item * G;
     const int hshift = (PACKED && half) ? 16 : 0;
@@ -67,15 +67,12 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         const int g = rem / R;
         const int r = rem - g * R;
         const int t = (j - 1) + g;
-        const int tb = t / L::S, u = t - tb * L::S;
         const int w = r / L::RPW;
         const int rows_in_word = min(L::RPW, R - w * L::RPW);
         const int sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
-        const size_t base = (((size_t)pass * nTB + tb) * L::NQ * 32 + lane0 + g) * 4;
-        auto plane = [&](int pl) -> unsigned {
-            const int flat = u * L::NW + pl * L::WPP + w;
-            return (cw[base + (size_t)(flat >> 2) * 128 + (flat & 3)] >> sh) & 3u;
-        };
+        // 128-bit word (pass, 2-step block, row-word, lane) = {p0 s0, p0 s1, p1 s0, p1 s1}
+        const size_t q = ((((size_t)pass * nB2 + (t >> 1)) * L::WPP + w) * 32 + lane0 + g) * 4 + (t & 1);
+        auto plane = [&](int pl) -> unsigned { return (cw[q + 2 * pl] >> sh) & 3u; };
         if (level != 0) {
             const unsigned lu = plane(1);
             if (lu & (unsigned)level) return level;      // bL is bit 0 (level 1), bU is bit 1 (level 2)

@@ -17,10 +17,11 @@ TAG = 3
 def layout(R, G, rows_per_word):
     wpp = -(-R // rows_per_word)            # words per plane per step
     nw = 2 * wpp                            # words per step: plane 0 = c0, plane 1 = (bL, bU)
-    from math import gcd
-    S = 4 // gcd(nw, 4)                     # steps staged per 128-bit store group
-    nq = S * nw // 4                        # uint4 chunks per staged block
-    return dict(R=R, G=G, RPW=rows_per_word, WPP=wpp, NW=nw, S=S, NQ=nq)
+    # The fill stages 2 steps and stores, per row-word w, one uint4 =
+    # (plane 0, step 0), (plane 0, step 1), (plane 1, step 0), (plane 1, step 1) of that word;
+    # uint4s are laid out [pass][2-step block][row-word][lane]: a warp store is 512 contiguous
+    # bytes and the walker finds both planes of two consecutive steps in 16 bytes.
+    return dict(R=R, G=G, RPW=rows_per_word, WPP=wpp, NW=nw, S=2, NQ=wpp)
 
 
 def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=16):
@@ -34,7 +35,7 @@ def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=1
     nTB = -(-nsteps // L["S"])
     big4 = 4 * (max_cost + 1) * max(m, n)
     o4 = 4 * o
-    codes = {}                               # (pass, tb, q, lane) -> [w0, w1, w2, w3]
+    codes = {}                               # (pass, 2-step block, row-word, lane) -> [p0u0, p0u1, p1u0, p1u1]
     bnd = [None] * (n + 2)                   # boundary row between passes: (h, U) per column j
     # prefix sums of vertical gap costs: col_i = o + sum_{t<=i} gap_v[s1[t-1]]
     col = [0] * (m + B + 2)
@@ -123,8 +124,9 @@ def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=1
                         cost = st["hl"][(m - 1) % R] >> 2
                 rowj = rowj_next
             for g in range(G):
-                for q in range(L["NQ"]):
-                    codes[(p, tb, q, g)] = stage[g][4 * q:4 * q + 4]
+                for w in range(L["WPP"]):
+                    codes[(p, tb, w, g)] = [stage[g][w], stage[g][L["NW"] + w],
+                                            stage[g][L["WPP"] + w], stage[g][L["NW"] + L["WPP"] + w]]
         bnd = new_bnd
     return cost, codes, L
 
@@ -149,11 +151,8 @@ def _plane_at(codes, L, m, i, j, plane):
     g = ((i - 1) % B) // R
     r = (i - 1) % R
     t = (j - 1) + g
-    tb, u = divmod(t, L["S"])
     w = r // L["RPW"]
-    flat = u * L["NW"] + plane * L["WPP"] + w
-    q, comp = divmod(flat, 4)
-    word = codes[(p, tb, q, g)][comp]
+    word = codes[(p, t >> 1, w, g)][plane * 2 + (t & 1)]
     rows_in_word = min(L["RPW"], R - w * L["RPW"])
     shift = 2 * (rows_in_word - 1 - (r % L["RPW"]))
     return (word >> shift) & 3
