@@ -430,38 +430,52 @@ def run_ours(args, rank, world, local_rank):
     d2h = outs[0].nbytes + outs[1].nbytes + outs[3].nbytes + outs[4].nbytes
     e2e_steps = max(2, min(args.steps, 5))
 
-    def time_e2e(bits):
+    lens1, lens2 = np.diff(batch.off1), np.diff(batch.off2)
+    fixed = bool((lens1 == lens1[0]).all() and (lens2 == lens2[0]).all())
+    um, un = int(lens1[0]), int(lens2[0])
+
+    def time_e2e(bits, uniform):
+        """uniform: the fixed-length entry point (ga_align_batch_uniform, no offset arrays);
+        otherwise ga_align_batch with its three offset arrays."""
         hb = []
         for a in (_native.pack_letters(s1h, bits), batch.off1, _native.pack_letters(s2h, bits), batch.off2):
             tt, v = pinned(a)
             keep.append(tt)
             hb.append(v)
         fl = _native.seq_flag(bits)
+        if uniform:
+            uo = (outs[0], outs[1], outs[3], outs[4])
+            call = lambda: ctx.align_batch_uniform(hb[0], um, hb[2], un, n, flags=fl, out=uo)
+            h2d_bytes = hb[0].nbytes + hb[2].nbytes
+        else:
+            call = lambda: ctx.align_batch(hb[0], hb[1], hb[2], hb[3], flags=fl, out=tuple(outs))
+            h2d_bytes = hb[0].nbytes + hb[2].nbytes + 2 * batch.off1.nbytes + ops_off_h.nbytes
         for _ in range(2):
-            ctx.align_batch(hb[0], hb[1], hb[2], hb[3], flags=fl, out=tuple(outs))
+            call()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.align_batch(hb[0], hb[1], hb[2], hb[3], flags=fl, out=tuple(outs))
+            call()
         torch.cuda.synchronize()
         dt_s = (time.perf_counter() - t0) / e2e_steps
         assert np.array_equal(outs[0], dev_cost), "device-resident and host-buffer paths disagree"
-        return dt_s, hb[0].nbytes + hb[2].nbytes + 2 * batch.off1.nbytes + ops_off_h.nbytes, ctx.timing()
+        return dt_s, h2d_bytes, ctx.timing()
 
     seq_bits = 2 if len(dense.letters) <= 4 else 8
-    e2e_s, h2d, e2e_phase = time_e2e(seq_bits)
-    e2e_plain = time_e2e(8) if seq_bits != 8 else (e2e_s, h2d, e2e_phase)
+    e2e_s, h2d, e2e_phase = time_e2e(seq_bits, fixed)
+    e2e_offsets = time_e2e(seq_bits, False) if fixed else (e2e_s, h2d, e2e_phase)
+    e2e_plain = time_e2e(8, False) if seq_bits != 8 else e2e_offsets
 
     # ---- reduce over ranks: max time, sum of cells
-    vals = torch.tensor([dev_ms / args.steps, e2e_s * 1e3, float(cells), e2e_plain[0] * 1e3], dtype=torch.float64, device=dev)
+    vals = torch.tensor([dev_ms / args.steps, e2e_s * 1e3, float(cells), e2e_plain[0] * 1e3, e2e_offsets[0] * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         mx = vals.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        step_ms, e2e_ms, total_cells, e2e_plain_ms = mx[0].item(), mx[1].item(), sm[2].item(), mx[3].item()
+        step_ms, e2e_ms, total_cells, e2e_plain_ms, e2e_off_ms = mx[0].item(), mx[1].item(), sm[2].item(), mx[3].item(), mx[4].item()
     else:
-        step_ms, e2e_ms, total_cells, e2e_plain_ms = vals[0].item(), vals[1].item(), float(cells), vals[3].item()
+        step_ms, e2e_ms, total_cells, e2e_plain_ms, e2e_off_ms = vals[0].item(), vals[1].item(), float(cells), vals[3].item(), vals[4].item()
     if rank != 0:
         return
 
@@ -491,7 +505,11 @@ def run_ours(args, rank, world, local_rank):
                                "kernels_ms / roofline are from a serial (non-overlapped) plan"},
         "clocks": clocks, "wall_ms_timed_region": wall_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "input": "%d-bit letters, pinned host memory" % seq_bits,
+                "ms_per_step": e2e_ms,
+                "input": "%d-bit letters, pinned host memory, %s" % (
+                    seq_bits, "fixed-length call (ga_align_batch_uniform)" if fixed else "offset arrays (ga_align_batch)"),
+                "offset_array_input": {"value": total_cells / (e2e_off_ms / 1e3) / 1e9, "ms_per_step": e2e_off_ms,
+                                       "h2d_bytes_per_step": int(e2e_offsets[1])},
                 "phases_ms": {k: round(v, 3) for k, v in e2e_phase.items()},
                 "byte_per_letter_input": {"value": total_cells / (e2e_plain_ms / 1e3) / 1e9, "ms_per_step": e2e_plain_ms,
                                           "h2d_bytes_per_step": int(e2e_plain[1])}},

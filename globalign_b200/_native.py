@@ -29,7 +29,8 @@ EXPORTS = (
     "ga_version", "ga_device_count", "ga_ctx_create", "ga_ctx_destroy", "ga_last_error",
     "ga_ctx_set_stream", "ga_ctx_set_scratch_limit", "ga_set_scheme", "ga_align_batch",
     "ga_plan_batch", "ga_run_batch", "ga_sync", "ga_get_plan_info", "ga_get_timing",
-    "ga_fill_values", "ga_alu_peak", "ga_align_long", "ga_align_replay",
+    "ga_fill_values", "ga_alu_peak", "ga_align_long", "ga_align_replay", "ga_align_batch_uniform",
+    "ga_fill_values_f64", "ga_align_f64",
 )
 
 
@@ -75,6 +76,7 @@ def lib():
     L.ga_ctx_set_scratch_limit.argtypes = [vp, i64]
     L.ga_set_scheme.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32]
     L.ga_align_batch.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, u32]
+    L.ga_align_batch_uniform.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, u32]
     L.ga_plan_batch.argtypes = [vp, vp, vp, i64, vp, u32]
     L.ga_run_batch.argtypes = [vp] + [vp] * 9
     L.ga_sync.argtypes = [vp]
@@ -84,6 +86,10 @@ def lib():
     L.ga_alu_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.ga_align_long.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
                                 C.POINTER(i32), u32, C.POINTER(LongInfo)]
+    f64 = C.c_double
+    L.ga_fill_values_f64.argtypes = [vp, i32, vp, vp, vp, f64, f64, vp, i64, vp, i64, C.c_int, vp]
+    L.ga_align_f64.argtypes = [vp, i32, vp, vp, vp, f64, f64, vp, i64, vp, i64, vp, i64, C.POINTER(f64), vp,
+                               C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     L.ga_align_replay.argtypes = [vp, vp, i64, vp, i64, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
                                   C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTS:
@@ -180,6 +186,25 @@ class Context:
                                            _ptr(status), flags))
         return cost, ops, ops_off, ops_len, status
 
+    def align_batch_uniform(self, s1, m: int, s2, n: int, n_pairs: int, flags: int = 0, out=None):
+        """Fixed-length batch (every pair m x n), no offset arrays.
+        -> (cost, ops, ops_stride, ops_len, status); pair p's ops start at byte p * ops_stride."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        stride = (((m + n + 3) // 4) + 3) // 4 * 4
+        if flags & GA_F_COST_ONLY:
+            cost = np.empty(n_pairs, dtype=np.int32) if out is None else out[0]
+            self._check(self._L.ga_align_batch_uniform(self._h, _ptr(s1), m, _ptr(s2), n, n_pairs, _ptr(cost),
+                                                       None, None, None, flags))
+            return cost, None, stride, None, None
+        if out is None:
+            out = (np.empty(n_pairs, dtype=np.int32), np.empty(stride * n_pairs, dtype=np.uint8),
+                   np.empty(n_pairs, dtype=np.int32), np.empty(n_pairs, dtype=np.int32))
+        cost, ops, ops_len, status = out
+        self._check(self._L.ga_align_batch_uniform(self._h, _ptr(s1), m, _ptr(s2), n, n_pairs, _ptr(cost),
+                                                   _ptr(ops), _ptr(ops_len), _ptr(status), flags))
+        return cost, ops, stride, ops_len, status
+
     # -- device-buffer entry points (pointers are ints, e.g. torch.Tensor.data_ptr())
     def plan_batch(self, off1, off2, ops_off=None, flags: int = 0):
         off1 = np.ascontiguousarray(off1, dtype=np.int64)
@@ -216,6 +241,32 @@ class Context:
         self._check(self._L.ga_fill_values(self._h, _ptr(s1), len(s1), _ptr(s2), len(s2),
                                            1 if keep_boundary else 0, _ptr(table)))
         return table
+
+    def fill_values_f64(self, dense, s1, s2, table, keep_boundary: bool):
+        """dense: lowering.DenseSchemeF64.  table: float64 (m+1, n+1, 3), filled in place."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        assert table.dtype == np.float64 and table.flags.c_contiguous
+        self._check(self._L.ga_fill_values_f64(self._h, dense.A, _ptr(dense.sub), _ptr(dense.gap_h),
+                                               _ptr(dense.gap_v), dense.gap_open, dense.max_cost, _ptr(s1),
+                                               len(s1), _ptr(s2), len(s2), 1 if keep_boundary else 0, _ptr(table)))
+        return table
+
+    def align_f64(self, dense, s1, s2, draws=None):
+        """One pair with float-valued penalties -> (cost float, ops walk order, n_eval, status)."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        m, n = len(s1), len(s2)
+        if draws is not None:
+            draws = np.ascontiguousarray(draws, dtype=np.uint16)
+        packed = np.zeros(4 * ((m + n + 15) // 16) + 16, dtype=np.uint8)
+        cost, nops, neval, status = C.c_double(0.0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self._L.ga_align_f64(self._h, dense.A, _ptr(dense.sub), _ptr(dense.gap_h), _ptr(dense.gap_v),
+                                         dense.gap_open, dense.max_cost, _ptr(s1), m, _ptr(s2), n,
+                                         None if draws is None else _ptr(draws), 0 if draws is None else len(draws),
+                                         C.byref(cost), _ptr(packed), C.byref(nops), C.byref(neval),
+                                         C.byref(status)))
+        return cost.value, unpack_ops(packed, 0, nops.value), neval.value, status.value
 
     def alu_peak(self, mode: int) -> float:
         g = C.c_double(0.0)

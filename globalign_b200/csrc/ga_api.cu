@@ -144,6 +144,7 @@ struct ga_ctx {
     bool persistent = true;           // fill grid: machine-filling + tile counter, or one tile per warp
     int uniM = 0, uniN = 0;
     long long uni_u4 = 0;
+    long long uni_ops_stride = 0;      // bytes per pair of packed ops when offsets are implicit
     DevBuf d_tiles, d_codes[2], d_bnd[2], d_counter;
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
@@ -396,6 +397,9 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
     return find_cfg(maxM <= 64 ? "fill_i32t_r8_g8" : maxM <= 128 ? "fill_i32t_r8_g16" : "fill_i32t_r8_g32");
 }
 
+static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
+                       uint32_t flags, int maxM, int maxN, int minM, int minN, int64_t cells, HostTimer &ht);
+
 extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off,
                              int64_t n_pairs, const int64_t *out_ops_off, uint32_t flags) {
     if (!ctx) return GA_E_ARG;
@@ -405,13 +409,6 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     CK(cudaSetDevice(ctx->device));
     HostTimer ht;
     ctx->have_plan = false;
-    for (float &v : ctx->ms) v = 0.f;
-    {
-        const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
-        if ((flags & GA_F_SEQ_2BIT) && (flags & GA_F_SEQ_4BIT)) return fail(ctx, GA_E_ARG, "choose one sequence packing");
-        if (ctx->sc.A > (1 << bits)) return fail(ctx, GA_E_ARG, "alphabet of %d letters does not fit %d-bit packed sequences", ctx->sc.A, bits);
-        ctx->sc.seq_bits = bits;
-    }
     int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30;
     int64_t cells = 0;
     {
@@ -451,6 +448,29 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
             minN = std::min(minN, a.minN);
             cells += a.cells;
         }
+    }
+    return plan_common(ctx, s1_off, s2_off, n_pairs, flags, maxM, maxN, minM, minN, cells, ht);
+}
+
+// Planning for a fixed-length batch without offset arrays (every pair m x n).
+static int plan_uniform(ga_ctx *ctx, int64_t m, int64_t n, int64_t n_pairs, uint32_t flags) {
+    if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
+    if (n_pairs < 1 || n_pairs > 0x7fffff00LL || m < 1 || n < 1 || m > (1 << 24) || n > (1 << 15))
+        return fail(ctx, GA_E_ARG, "bad uniform batch (1 <= n_pairs < 2^31, 1 <= m <= 2^24, 1 <= n <= 32768)");
+    CK(cudaSetDevice(ctx->device));
+    HostTimer ht;
+    ctx->have_plan = false;
+    return plan_common(ctx, nullptr, nullptr, n_pairs, flags, (int)m, (int)n, (int)m, (int)n, m * n * n_pairs, ht);
+}
+
+static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
+                       uint32_t flags, int maxM, int maxN, int minM, int minN, int64_t cells, HostTimer &ht) {
+    for (float &v : ctx->ms) v = 0.f;
+    {
+        const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
+        if ((flags & GA_F_SEQ_2BIT) && (flags & GA_F_SEQ_4BIT)) return fail(ctx, GA_E_ARG, "choose one sequence packing");
+        if (ctx->sc.A > (1 << bits)) return fail(ctx, GA_E_ARG, "alphabet of %d letters does not fit %d-bit packed sequences", ctx->sc.A, bits);
+        ctx->sc.seq_bits = bits;
     }
     ht.lap("plan: scan pairs");
     const KernelCfg *cfg = choose_cfg(ctx, maxM, maxN, flags);
@@ -602,6 +622,7 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     ctx->uniM = maxM;
     ctx->uniN = maxN;
     ctx->uni_u4 = uni_u4;
+    ctx->uni_ops_stride = ((((long long)maxM + maxN + 3) / 4) + 3) & ~3LL;
     ctx->have_plan = true;
     return GA_OK;
 }
@@ -657,7 +678,8 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         const int n_tiles = ch.tile_hi - ch.tile_lo, np = ch.pair_hi - ch.pair_lo;
         if (io) {   // the letters are already in flight (ga_align_batch): wait for the piece that
                     // holds this chunk's last letter of either sequence set
-            const int64_t a1 = io->off1[ch.pair_hi], b1 = io->off2[ch.pair_hi];
+            const int64_t a1 = io->off1 ? io->off1[ch.pair_hi] : (int64_t)ch.pair_hi * ctx->uniM;
+            const int64_t b1 = io->off2 ? io->off2[ch.pair_hi] : (int64_t)ch.pair_hi * ctx->uniN;
             auto piece_of = [](int64_t end, int64_t total) {
                 int k = 0;
                 while (k < IN_PIECES - 1 && total * (k + 1) / IN_PIECES < end) ++k;
@@ -671,7 +693,7 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         const bool persistent = ctx->persistent || serial;
         const int grid = persistent ? std::min(ctx->grid, (n_tiles + 3) / 4) : (n_tiles + 3) / 4;
         const TileDesc *d_tiles = ctx->uniform ? nullptr : (const TileDesc *)ctx->d_tiles.p + ch.tile_lo;
-        const UniformTiles ut{ctx->uniM, ctx->uniN, ch.pair_lo, ch.pair_hi, ctx->uni_u4};
+        const UniformTiles ut{ctx->uniM, ctx->uniN, ch.pair_lo, ch.pair_hi, ctx->uni_u4, ctx->uni_ops_stride};
         cfg->launch_fill(grid, ctx->smem, sF, ctx->sc, d_tiles, ut,
                          n_tiles, (int *)ctx->d_counter.p + c, d_s1, (const long long *)d_s1_off, d_s2,
                          (const long long *)d_s2_off, (uint4 *)ctx->d_codes[b].p, (int2 *)ctx->d_bnd[b].p,
@@ -693,7 +715,8 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
             CK(cudaEventRecord(E.out0, sOut));
             CK(cudaMemcpyAsync(io->cost + ch.pair_lo, d_cost + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
             if (!cost_only) {
-                const int64_t o0 = io->ops_off[ch.pair_lo], o1 = io->ops_off[ch.pair_hi];
+                const int64_t o0 = io->ops_off ? io->ops_off[ch.pair_lo] : (int64_t)ch.pair_lo * ctx->uni_ops_stride;
+                const int64_t o1 = io->ops_off ? io->ops_off[ch.pair_hi] : (int64_t)ch.pair_hi * ctx->uni_ops_stride;
                 CK(cudaMemcpyAsync(io->ops + o0, d_ops + o0, (size_t)(o1 - o0), cudaMemcpyDeviceToHost, sOut));
                 CK(cudaMemcpyAsync(io->len + ch.pair_lo, d_len + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
                 CK(cudaMemcpyAsync(io->status + ch.pair_lo, d_status + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
@@ -759,33 +782,33 @@ extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
     return GA_OK;
 }
 
-// ------------------------------------------------------------------ host-buffer entry point
-extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off,
-                              const uint8_t *s2, const int64_t *s2_off, int64_t n_pairs,
-                              int32_t *out_cost, uint8_t *out_ops, const int64_t *out_ops_off,
-                              int32_t *out_ops_len, int32_t *out_status, uint32_t flags) {
-    if (!ctx) return GA_E_ARG;
+// ------------------------------------------------------------------ host-buffer entry points
+// Shared by ga_align_batch (offset arrays) and ga_align_batch_uniform (every pair um x un, offset
+// arrays implicit: s1_off == s2_off == out_ops_off == nullptr).
+static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off, const uint8_t *s2,
+                            const int64_t *s2_off, int64_t um, int64_t un, int64_t n_pairs, int32_t *out_cost,
+                            uint8_t *out_ops, const int64_t *out_ops_off, int32_t *out_ops_len,
+                            int32_t *out_status, uint32_t flags) {
     const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
-    if (!s1 || !s2 || !s1_off || !s2_off || !out_cost ||
-        (!cost_only && (!out_ops || !out_ops_off || !out_ops_len || !out_status)))
-        return fail(ctx, GA_E_ARG, "null host buffer");
+    const bool implicit = s1_off == nullptr;
     if (n_pairs < 1 || n_pairs > 0x7fffff00LL) return fail(ctx, GA_E_ARG, "bad batch (1 <= n_pairs < 2^31)");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream, sIn = ctx->aux[4];
-    const int64_t t1 = s1_off[n_pairs], t2 = s2_off[n_pairs];
-    if (t1 < n_pairs || t2 < n_pairs || s1_off[0] != 0 || s2_off[0] != 0)
+    const int64_t t1 = implicit ? um * n_pairs : s1_off[n_pairs], t2 = implicit ? un * n_pairs : s2_off[n_pairs];
+    if (t1 < n_pairs || t2 < n_pairs || (!implicit && (s1_off[0] != 0 || s2_off[0] != 0)))
         return fail(ctx, GA_E_ARG, "offset arrays must start at 0 and be increasing");
     const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
     const size_t b1 = (size_t)((t1 * bits + 7) / 8), b2 = (size_t)((t2 * bits + 7) / 8);
     const size_t offb = (size_t)(n_pairs + 1) * 8;
-    const size_t opsb = cost_only ? 0 : (size_t)out_ops_off[n_pairs];
+    const int64_t ops_stride = ((((um + un) + 3) / 4) + 3) & ~(int64_t)3;
+    const size_t opsb = cost_only ? 0 : (size_t)(implicit ? ops_stride * n_pairs : out_ops_off[n_pairs]);
     int rc;
     if ((rc = ensure(ctx, ctx->d_s1, b1 + 16)) || (rc = ensure(ctx, ctx->d_s2, b2 + 16)) ||
-        (rc = ensure(ctx, ctx->d_off1, offb)) || (rc = ensure(ctx, ctx->d_off2, offb)) ||
         (rc = ensure(ctx, ctx->d_cost, (size_t)n_pairs * 4)))
         return rc;
+    if (!implicit && ((rc = ensure(ctx, ctx->d_off1, offb)) || (rc = ensure(ctx, ctx->d_off2, offb)))) return rc;
     if (!cost_only &&
-        ((rc = ensure(ctx, ctx->d_ops, opsb + 16)) || (rc = ensure(ctx, ctx->d_opsoff, offb)) ||
+        ((rc = ensure(ctx, ctx->d_ops, opsb + 16)) || (!implicit && (rc = ensure(ctx, ctx->d_opsoff, offb))) ||
          (rc = ensure(ctx, ctx->d_len, (size_t)n_pairs * 4)) ||
          (rc = ensure(ctx, ctx->d_status, (size_t)n_pairs * 4))))
         return rc;
@@ -796,9 +819,11 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     CK(cudaEventRecord(ctx->ev[2], st));
     CK(cudaStreamWaitEvent(sIn, ctx->ev[2], 0));
     CK(cudaEventRecord(ctx->in_begin, sIn));
-    CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, sIn));
-    CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, sIn));
-    if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
+    if (!implicit) {
+        CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, sIn));
+        CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, sIn));
+        if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
+    }
     auto upload_piece = [&](int k) -> int {
         // piece k = letters [t*k/8, t*(k+1)/8) -> the bytes that hold them (edges may be sent twice)
         const int64_t a0 = (t1 * k / IN_PIECES) * bits / 8, a1 = ((t1 * (k + 1) / IN_PIECES) * bits + 7) / 8;
@@ -816,7 +841,8 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     ht0.lap("align: enqueue uploads");
     HostTimer ht;
     ctx->plan_for_io = true;
-    rc = ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
+    rc = implicit ? plan_uniform(ctx, um, un, n_pairs, flags)
+                  : ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
     ctx->plan_for_io = false;
     if (rc) { cudaStreamSynchronize(sIn); return rc; }
     for (int k = EARLY; k < IN_PIECES; ++k)
@@ -826,15 +852,40 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     io.total1 = t1; io.total2 = t2;
     io.s1 = s1; io.s2 = s2; io.off1 = s1_off; io.off2 = s2_off; io.ops_off = out_ops_off;
     io.cost = out_cost; io.len = out_ops_len; io.status = out_status; io.ops = out_ops;
-    rc = run_pipeline(ctx, (const uint8_t *)ctx->d_s1.p, (const int64_t *)ctx->d_off1.p,
-                      (const uint8_t *)ctx->d_s2.p, (const int64_t *)ctx->d_off2.p,
-                      (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p, (const int64_t *)ctx->d_opsoff.p,
+    rc = run_pipeline(ctx, (const uint8_t *)ctx->d_s1.p, implicit ? nullptr : (const int64_t *)ctx->d_off1.p,
+                      (const uint8_t *)ctx->d_s2.p, implicit ? nullptr : (const int64_t *)ctx->d_off2.p,
+                      (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p,
+                      implicit ? nullptr : (const int64_t *)ctx->d_opsoff.p,
                       (int32_t *)ctx->d_len.p, (int32_t *)ctx->d_status.p, &io);
     if (rc) return rc;
     ht.lap("align: enqueue pipeline");
     CK(cudaStreamSynchronize(st));
     ht.lap("align: wait for the device");
     return GA_OK;
+}
+
+extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off,
+                              const uint8_t *s2, const int64_t *s2_off, int64_t n_pairs,
+                              int32_t *out_cost, uint8_t *out_ops, const int64_t *out_ops_off,
+                              int32_t *out_ops_len, int32_t *out_status, uint32_t flags) {
+    if (!ctx) return GA_E_ARG;
+    const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
+    if (!s1 || !s2 || !s1_off || !s2_off || !out_cost ||
+        (!cost_only && (!out_ops || !out_ops_off || !out_ops_len || !out_status)))
+        return fail(ctx, GA_E_ARG, "null host buffer");
+    return align_batch_impl(ctx, s1, s1_off, s2, s2_off, 0, 0, n_pairs, out_cost, out_ops, out_ops_off,
+                            out_ops_len, out_status, flags);
+}
+
+extern "C" int ga_align_batch_uniform(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                                      int64_t n_pairs, int32_t *out_cost, uint8_t *out_ops,
+                                      int32_t *out_ops_len, int32_t *out_status, uint32_t flags) {
+    if (!ctx) return GA_E_ARG;
+    const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
+    if (!s1 || !s2 || !out_cost || m < 1 || n < 1 || (!cost_only && (!out_ops || !out_ops_len || !out_status)))
+        return fail(ctx, GA_E_ARG, "null host buffer or empty sequences");
+    return align_batch_impl(ctx, s1, nullptr, s2, nullptr, m, n, n_pairs, out_cost, out_ops, nullptr,
+                            out_ops_len, out_status, flags);
 }
 
 // ------------------------------------------------------------------ one long pair
@@ -997,33 +1048,65 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     return GA_OK;
 }
 
-// ------------------------------------------------------------------ debug: full value table
+// ------------------------------------------------------------------ full value table
 // What dp_array_forward leaves in dp_array (reference globaligner.py:366-392), for ONE
-// small pair; anti-diagonals in parallel, one block.  Not a performance path.
-__global__ void values_kernel(const SchemeDev sc, const uint8_t *s1, int m, const uint8_t *s2, int n,
-                              int keep_boundary, int *tab) {
+// small pair; anti-diagonals in parallel, one block.  Not a throughput path.  Templated on the
+// value type: int32 for the reference's own (int()-coerced) entry point, f64 for float-valued
+// penalties, which the reference accepts when its inner functions are called directly (type
+// hints globaligner.py:371,761).  The f64 instance adds and compares in the reference's own
+// order -- min of the three predecessors (with gap_open added where levels differ), then the
+// step cost (:359-363) -- so its doubles are bit-identical to CPython's.
+struct IntCosts {
+    SchemeDev sc;
+    typedef int value_t;
+    typedef long long acc_t;
+    static constexpr bool exact_adds = false;
+    __device__ int sub(int a, int b) const { return sc.sub4[a * sc.A + b] / 4; }
+    __device__ int gh(int b) const { return sc.gh_raw[b]; }
+    __device__ int gv(int a) const { return sc.gv_raw[a]; }
+    __device__ int open() const { return sc.o; }
+    __device__ int big(int m, int n) const { return (sc.max_cost + 1) * max(m, n); }
+};
+struct F64Costs {
+    int A;
+    const double *s, *h, *v;
+    double o, max_cost;
+    typedef double value_t;
+    typedef double acc_t;
+    static constexpr bool exact_adds = true;   // floating point: a common addend can change ranks
+    __device__ double sub(int a, int b) const { return s[a * A + b]; }
+    __device__ double gh(int b) const { return h[b]; }
+    __device__ double gv(int a) const { return v[a]; }
+    __device__ double open() const { return o; }
+    __device__ double big(int m, int n) const { return (max_cost + 1.0) * (double)max(m, n); }
+};
+
+template <typename C>
+__global__ void values_kernel(const C c, const uint8_t *s1, int m, const uint8_t *s2, int n,
+                              int keep_boundary, typename C::value_t *tab) {
+    typedef typename C::value_t T;
     const int W = n + 1;
-    auto at = [&](int i, int j, int k) -> int & { return tab[((size_t)i * W + j) * 3 + k]; };
+    auto at = [&](int i, int j, int k) -> T & { return tab[((size_t)i * W + j) * 3 + k]; };
     if (!keep_boundary) {
         if (threadIdx.x == 0) {
-            const int big = (sc.max_cost + 1) * max(m, n);
+            const T big = c.big(m, n);
             at(0, 0, 0) = at(0, 0, 1) = at(0, 0, 2) = 0;
-            int run = sc.o;
-            for (int j = 1; j <= n; ++j) { run += sc.gh_raw[s2[j - 1]]; at(0, j, 0) = big; at(0, j, 1) = run; at(0, j, 2) = big; }
-            run = sc.o;
-            for (int i = 1; i <= m; ++i) { run += sc.gv_raw[s1[i - 1]]; at(i, 0, 0) = big; at(i, 0, 1) = big; at(i, 0, 2) = run; }
+            T run = c.open();
+            for (int j = 1; j <= n; ++j) { run += c.gh(s2[j - 1]); at(0, j, 0) = big; at(0, j, 1) = run; at(0, j, 2) = big; }
+            run = c.open();
+            for (int i = 1; i <= m; ++i) { run += c.gv(s1[i - 1]); at(i, 0, 0) = big; at(i, 0, 1) = big; at(i, 0, 2) = run; }
         }
         __syncthreads();
     }
+    const T o = c.open();
     for (int d = 2; d <= m + n; ++d) {
         const int ilo = max(1, d - n), ihi = min(m, d - 1);
         for (int i = ilo + threadIdx.x; i <= ihi; i += blockDim.x) {
             const int j = d - i;
             const int a = s1[i - 1], b = s2[j - 1];
-            const int o = sc.o;
-            at(i, j, 0) = min(min(at(i - 1, j - 1, 0), at(i - 1, j - 1, 1)), at(i - 1, j - 1, 2)) + sc.sub4[a * sc.A + b] / 4;
-            at(i, j, 1) = min(min(at(i, j - 1, 0) + o, at(i, j - 1, 1)), at(i, j - 1, 2) + o) + sc.gh_raw[b];
-            at(i, j, 2) = min(min(at(i - 1, j, 0) + o, at(i - 1, j, 1) + o), at(i - 1, j, 2)) + sc.gv_raw[a];
+            at(i, j, 0) = min(min(at(i - 1, j - 1, 0), at(i - 1, j - 1, 1)), at(i - 1, j - 1, 2)) + c.sub(a, b);
+            at(i, j, 1) = min(min(at(i, j - 1, 0) + o, at(i, j - 1, 1)), at(i, j - 1, 2) + o) + c.gh(b);
+            at(i, j, 2) = min(min(at(i - 1, j, 0) + o, at(i - 1, j, 1) + o), at(i - 1, j, 2)) + c.gv(a);
         }
         __syncthreads();
     }
@@ -1046,7 +1129,7 @@ extern "C" int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const u
     CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dt, table, tb, cudaMemcpyHostToDevice, st));
-    values_kernel<<<1, 256, 0, st>>>(ctx->sc, d1, (int)m, d2, (int)n, keep_boundary, dt);
+    values_kernel<IntCosts><<<1, 256, 0, st>>>(IntCosts{ctx->sc}, d1, (int)m, d2, (int)n, keep_boundary, dt);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(table, dt, tb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1064,12 +1147,24 @@ extern "C" int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const u
 // byte: all three tied (options 0,1,2) | levels 0,1 tied (0,1) | 0,2 tied (0,2) | 1,2 tied (1,2).
 // One thread walks the full value table (ga_fill_values' kernel) ranking values as
 // dp_array_backward does (:425-581).  Single pairs only; not a throughput path.
-__global__ void replay_walk_kernel(const SchemeDev sc, const uint8_t *s1, int m, const uint8_t *s2, int n,
-                                   const int *tab, const uint16_t *draws, uint32_t *ops_out,
-                                   long long *n_ops_out, int *n_eval_out, int *status_out, int *cost_out) {
+// `draws` == nullptr: canonical order (first-listed option of every tie).
+//
+// What is ranked (:490-514): the cell's three values plus, per level, the cost of the step to the
+// successor -- on level 0 cm[a][b] for all three, on levels 1 and 2 cm["-"][b] (the reference
+// uses the "-" ROW on both gap levels) with gap_open_cost added FIRST on the levels that differ
+// from the successor's -- and nothing at the first evaluation (:425-435).  A common addend
+// cannot change integer ranks, so the integer instance adds gap_open only; the f64 instance
+// adds exactly what the reference adds, in its order: value + (gap_open + step).
+template <typename C>
+__global__ void replay_walk_kernel(const C cs, const uint8_t *s1, int m, const uint8_t *s2, int n,
+                                   const typename C::value_t *tab, const uint16_t *draws, uint32_t *ops_out,
+                                   long long *n_ops_out, int *n_eval_out, int *status_out,
+                                   typename C::value_t *cost_out) {
+    typedef typename C::value_t T;
+    typedef typename C::acc_t ACC;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int W = n + 1;
-    const long long o = sc.o;
+    const ACC o = cs.open();
     long long nops = 0;
     uint32_t word = 0;
     int n_eval = 0, status = 0;
@@ -1077,7 +1172,7 @@ __global__ void replay_walk_kernel(const SchemeDev sc, const uint8_t *s1, int m,
         word |= (uint32_t)op << (2 * (int)(nops & 15));
         if ((++nops & 15) == 0) { ops_out[(nops >> 4) - 1] = word; word = 0; }
     };
-    const int *corner = tab + ((size_t)m * W + n) * 3;
+    const T *corner = tab + ((size_t)m * W + n) * 3;
     *cost_out = min(min(corner[0], corner[1]), corner[2]);
     int i = m, j = n, level = 0;
     while (status == 0) {
@@ -1085,15 +1180,28 @@ __global__ void replay_walk_kernel(const SchemeDev sc, const uint8_t *s1, int m,
         // the shortcut tests (:542-581) follow every move except the first one, so a boundary
         // cell reached by the very first move is still ranked once (18 more draws)
         if (n_eval >= 2 && (i == 0 || j == 0)) break;
-        const int *c = tab + ((size_t)i * W + j) * 3;
-        long long v0 = c[0], v1 = c[1], v2 = c[2];
-        if (level == 1) { v0 += o; v2 += o; } else if (level == 2) { v0 += o; v1 += o; }
-        const long long lo = min(min(v0, v1), v2);
-        const int t0 = v0 == lo, t1 = v1 == lo, t2 = v2 == lo;
+        const T *c = tab + ((size_t)i * W + j) * 3;
         // Python's negative index wraps: seq[-1] is the last letter (only at a boundary cell)
         const int ai = i >= 1 ? i - 1 : m - 1, bj = j >= 1 ? j - 1 : n - 1;
+        ACC v0 = c[0], v1 = c[1], v2 = c[2];
+        if (C::exact_adds) {
+            if (n_eval > 0) {
+                if (level == 0) {
+                    const ACC st = cs.sub(s1[ai], s2[bj]);
+                    v0 += st; v1 += st; v2 += st;
+                } else {
+                    const ACC g = cs.gh(s2[bj]);
+                    const ACC og = o + g;
+                    if (level == 1) { v0 += og; v1 += g; v2 += og; } else { v0 += og; v1 += og; v2 += g; }
+                }
+            }
+        } else {
+            if (level == 1) { v0 += o; v2 += o; } else if (level == 2) { v0 += o; v1 += o; }
+        }
+        const ACC lo = min(min(v0, v1), v2);
+        const int t0 = v0 == lo, t1 = v1 == lo, t2 = v2 == lo;
         const int is_match = s1[ai] == s2[bj];
-        const unsigned d = draws[n_eval] >> (is_match ? 0 : 8);
+        const unsigned d = draws ? draws[n_eval] >> (is_match ? 0 : 8) : 0u;
         ++n_eval;
         int k;
         if (t0 && t1 && t2) k = (int)(d & 3u);                       // options (0, 1, 2)
@@ -1146,9 +1254,9 @@ extern "C" int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const 
     CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dd, draws, (size_t)n_draws * 2, cudaMemcpyHostToDevice, st));
-    values_kernel<<<1, 1024, 0, st>>>(ctx->sc, d1, (int)m, d2, (int)n, 0, dt);
+    values_kernel<IntCosts><<<1, 1024, 0, st>>>(IntCosts{ctx->sc}, d1, (int)m, d2, (int)n, 0, dt);
     CK(cudaGetLastError());
-    replay_walk_kernel<<<1, 32, 0, st>>>(ctx->sc, d1, (int)m, d2, (int)n, dt, dd, dops,
+    replay_walk_kernel<IntCosts><<<1, 32, 0, st>>>(IntCosts{ctx->sc}, d1, (int)m, d2, (int)n, dt, dd, dops,
                                          (long long *)(dmisc + 2), dmisc, dmisc + 1, dmisc + 4);
     CK(cudaGetLastError());
     int hm[8] = {};
@@ -1162,6 +1270,107 @@ extern "C" int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const 
     *out_n_ops = nops;
     CK(cudaMemcpy(out_ops, dops, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
     cudaFree(d1); cudaFree(d2); cudaFree(dt); cudaFree(dd); cudaFree(dops); cudaFree(dmisc);
+    return GA_OK;
+}
+
+// ------------------------------------------------------------------ float-valued penalties (f64)
+// SURVEY.md section 8 row f2.  The scheme travels with the call (it is not the ctx's integer
+// scheme).  One pair; value table in HBM (24 B per cell), value-ranking walk as above.
+struct F64Pair {
+    uint8_t *d1 = nullptr, *d2 = nullptr;
+    double *dsch = nullptr, *dt = nullptr;
+    uint16_t *dd = nullptr;
+    uint32_t *dops = nullptr;
+    int *dmisc = nullptr;
+    ~F64Pair() { cudaFree(d1); cudaFree(d2); cudaFree(dsch); cudaFree(dt); cudaFree(dd); cudaFree(dops); cudaFree(dmisc); }
+};
+
+static int f64_setup(ga_ctx *ctx, F64Pair &w, F64Costs &c, int32_t A, const double *sub, const double *gap_h,
+                     const double *gap_v, double gap_open, double max_cost, const uint8_t *s1, int64_t m,
+                     const uint8_t *s2, int64_t n, cudaStream_t st) {
+    for (int64_t k = 0; k < m; ++k) if (s1[k] >= A) return fail(ctx, GA_E_ARG, "seq_1 letter index outside the alphabet");
+    for (int64_t k = 0; k < n; ++k) if (s2[k] >= A) return fail(ctx, GA_E_ARG, "seq_2 letter index outside the alphabet");
+    const size_t nsch = (size_t)A * A + 2 * (size_t)A;
+    std::vector<double> h(nsch);
+    memcpy(h.data(), sub, sizeof(double) * A * A);
+    memcpy(h.data() + (size_t)A * A, gap_h, sizeof(double) * A);
+    memcpy(h.data() + (size_t)A * A + A, gap_v, sizeof(double) * A);
+    for (double v : h) if (!(v == v) || v - v != 0.0) return fail(ctx, GA_E_ARG, "costs must be finite");
+    if (!(gap_open == gap_open) || gap_open - gap_open != 0.0 || !(max_cost == max_cost) || max_cost - max_cost != 0.0)
+        return fail(ctx, GA_E_ARG, "costs must be finite");
+    CK(cudaMalloc(&w.d1, m));
+    CK(cudaMalloc(&w.d2, n));
+    CK(cudaMalloc(&w.dsch, nsch * sizeof(double)));
+    CK(cudaMalloc(&w.dt, (size_t)(m + 1) * (n + 1) * 3 * sizeof(double)));
+    CK(cudaMemcpyAsync(w.d1, s1, m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w.d2, s2, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w.dsch, h.data(), nsch * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // h goes out of scope with the caller's frame only, but keep it simple
+    c = F64Costs{A, w.dsch, w.dsch + (size_t)A * A, w.dsch + (size_t)A * A + A, gap_open, max_cost};
+    return GA_OK;
+}
+
+extern "C" int ga_fill_values_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h,
+                                  const double *gap_v, double gap_open, double max_cost, const uint8_t *s1,
+                                  int64_t m, const uint8_t *s2, int64_t n, int keep_boundary, double *table) {
+    if (!ctx) return GA_E_ARG;
+    if (!sub || !gap_h || !gap_v || !s1 || !s2 || !table || A < 1 || A > 250 || m < 1 || n < 1 ||
+        (m + 1) * (n + 1) > (int64_t)50'000'000)
+        return fail(ctx, GA_E_ARG, "ga_fill_values_f64: single pairs up to 5e7 table cells");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    F64Pair w;
+    F64Costs c;
+    int rc = f64_setup(ctx, w, c, A, sub, gap_h, gap_v, gap_open, max_cost, s1, m, s2, n, st);
+    if (rc) return rc;
+    const size_t tb = (size_t)(m + 1) * (n + 1) * 3 * sizeof(double);
+    if (keep_boundary) CK(cudaMemcpyAsync(w.dt, table, tb, cudaMemcpyHostToDevice, st));
+    values_kernel<F64Costs><<<1, 1024, 0, st>>>(c, w.d1, (int)m, w.d2, (int)n, keep_boundary, w.dt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(table, w.dt, tb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GA_OK;
+}
+
+extern "C" int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
+                            double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2,
+                            int64_t n, const uint16_t *draws, int64_t n_draws, double *out_cost,
+                            uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
+    if (!ctx) return GA_E_ARG;
+    if (!sub || !gap_h || !gap_v || !s1 || !s2 || !out_cost || !out_ops || !out_n_ops || !out_n_eval ||
+        !out_status || A < 1 || A > 250 || m < 1 || n < 1 || (draws && n_draws < m + n) ||
+        (m + 1) * (n + 1) > (int64_t)50'000'000)
+        return fail(ctx, GA_E_ARG, "ga_align_f64: single pairs up to 5e7 table cells, m+n draws or none");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    F64Pair w;
+    F64Costs c;
+    int rc = f64_setup(ctx, w, c, A, sub, gap_h, gap_v, gap_open, max_cost, s1, m, s2, n, st);
+    if (rc) return rc;
+    const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
+    CK(cudaMalloc(&w.dops, ops_words * 4));
+    CK(cudaMalloc(&w.dmisc, 64));
+    if (draws) {
+        CK(cudaMalloc(&w.dd, (size_t)n_draws * 2));
+        CK(cudaMemcpyAsync(w.dd, draws, (size_t)n_draws * 2, cudaMemcpyHostToDevice, st));
+    }
+    values_kernel<F64Costs><<<1, 1024, 0, st>>>(c, w.d1, (int)m, w.d2, (int)n, 0, w.dt);
+    CK(cudaGetLastError());
+    // dmisc: [0] n_eval, [1] status, [2..3] n_ops (int64), [4..5] cost (f64)
+    replay_walk_kernel<F64Costs><<<1, 32, 0, st>>>(c, w.d1, (int)m, w.d2, (int)n, w.dt, w.dd, w.dops,
+                                                         (long long *)(w.dmisc + 2), w.dmisc, w.dmisc + 1,
+                                                         (double *)(w.dmisc + 4));
+    CK(cudaGetLastError());
+    int hm[8] = {};
+    CK(cudaMemcpyAsync(hm, w.dmisc, sizeof hm, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long nops = 0;
+    memcpy(&nops, hm + 2, 8);
+    memcpy(out_cost, hm + 4, 8);
+    *out_n_eval = hm[0];
+    *out_status = hm[1];
+    *out_n_ops = nops;
+    CK(cudaMemcpy(out_ops, w.dops, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
     return GA_OK;
 }
 

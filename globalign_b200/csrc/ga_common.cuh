@@ -69,7 +69,13 @@ struct UniformTiles {
     int M, N;             // the common lengths
     int pair_lo, pair_hi; // pairs of the chunk
     long long u4;         // direction-code words (uint4) per tile
+    long long ops_stride; // bytes of a pair's packed-ops slice when the offset arrays are implicit
 };
+
+// Offset arrays may be absent (nullptr) for fixed-length batches: pair p then starts at p * len.
+__device__ __forceinline__ long long pair_off(const long long *__restrict__ off, long long p, long long len) {
+    return off ? off[p] : p * len;
+}
 
 __device__ __forceinline__ TileDesc tile_desc(const TileDesc *tiles, const UniformTiles &ut, int tile, int ppt) {
     if (tiles) return tiles[tile];

@@ -129,14 +129,14 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         const bool haveB = PACKED && lane_ok && ibx < td.n_pairs;
         const int pA = td.first_pair + min(ia, td.n_pairs - 1);
         const int pB = td.first_pair + min(ibx, td.n_pairs - 1);
-        const long long a1 = off1[pA], a2 = off2[pA];
-        const int mA = (int)(off1[pA + 1] - a1), nA = (int)(off2[pA + 1] - a2);
+        const long long a1 = pair_off(off1, pA, ut.M), a2 = pair_off(off2, pA, ut.N);
+        const int mA = (int)(pair_off(off1, pA + 1, ut.M) - a1), nA = (int)(pair_off(off2, pA + 1, ut.N) - a2);
         long long b1 = a1;
         int mB = mA, nB = nA;
         if (PACKED) {
-            b1 = off1[pB];
-            mB = (int)(off1[pB + 1] - b1);
-            nB = (int)(off2[pB + 1] - off2[pB]);
+            b1 = pair_off(off1, pB, ut.M);
+            mB = (int)(pair_off(off1, pB + 1, ut.M) - b1);
+            nB = (int)(pair_off(off2, pB + 1, ut.N) - pair_off(off2, pB, ut.N));
         }
         const unsigned bigA = (unsigned)(sc.max_cost + 1) * (unsigned)max(mA, nA);
         const unsigned bigB = (unsigned)(sc.max_cost + 1) * (unsigned)max(mB, nB);
@@ -150,8 +150,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         for (int q = 0; q < L::IPW; ++q) {
             const int qa = td.first_pair + min(q * L::PPI, td.n_pairs - 1);
             const int qb = td.first_pair + min(q * L::PPI + (PACKED ? 1 : 0), td.n_pairs - 1);
-            const long long oa = off2[qa], ob = off2[qb];
-            const int na = (int)(off2[qa + 1] - oa), nb = (int)(off2[qb + 1] - ob);
+            const long long oa = pair_off(off2, qa, ut.N), ob = pair_off(off2, qb, ut.N);
+            const int na = (int)(pair_off(off2, qa + 1, ut.N) - oa), nb = (int)(pair_off(off2, qb + 1, ut.N) - ob);
             BT *row = sb + (size_t)q * sb_stride;
             for (int c = lane; c < sb_len; c += 32) {
                 const unsigned va = c < na ? ld_letter(s2, oa + c, sc.seq_bits) : padb;

@@ -45,15 +45,15 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const int item = within / L::PPI;
     const int half = within - item * L::PPI;
     const TileDesc td = tile_desc(tiles, ut, tile, L::PPT);
-    const long long a1 = off1[p], a2 = off2[p];
-    const int m = (int)(off1[p + 1] - a1), n = (int)(off2[p + 1] - a2);
+    const long long a1 = pair_off(off1, p, ut.M), a2 = pair_off(off2, p, ut.N);
+    const int m = (int)(pair_off(off1, p + 1, ut.M) - a1), n = (int)(pair_off(off2, p + 1, ut.N) - a2);
     const int nsteps = td.N + G - 1;
     const int nB2 = (nsteps + 1) / 2;
     const uint32_t *cw = codes + 4 * td.code_off;
     const int lane0 = item * G;
     const int hshift = (PACKED && half) ? 16 : 0;
 
-    uint32_t *ow = reinterpret_cast<uint32_t *>(out_ops + ops_off[p]);
+    uint32_t *ow = reinterpret_cast<uint32_t *>(out_ops + pair_off(ops_off, p, ut.ops_stride));
     uint32_t word = 0;
     int nops = 0;
     auto emit = [&](int op) {

@@ -20,7 +20,7 @@ import numpy as np
 from . import _native
 from .batch import ReferenceUndefinedError, render
 from .conclude import AlignmentResults, final_cost_to_score
-from .lowering import DenseScheme
+from .lowering import DenseScheme, DenseSchemeF64, is_integral
 from .start import get_max_val, make_matrix, validate_and_transform_args
 
 __all__ = ["find_global_alignment", "make_dp_array", "dp_array_forward", "dp_array_backward", "main"]
@@ -88,7 +88,21 @@ def _align_one_replay(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: 
 LONG_PAIR_CELLS = 1 << 22
 
 
+def _align_one_f64(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost, device: int = 0):
+    """Float-valued penalties: f64 value table + value-ranking walk on the GPU."""
+    dense = DenseSchemeF64(costing_mat, gap_open_cost)
+    ctx = _native.default_context(device)
+    cost, ops, _n_eval, status = ctx.align_f64(dense, dense.encode(seq_1), dense.encode(seq_2))
+    if status != 0:
+        raise ReferenceUndefinedError(
+            "the reference's traceback leaves the DP table for this input: it raises IndexError "
+            "or wraps to negative indices there")
+    return ops, cost
+
+
 def _align_one(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: int, device: int = 0):
+    if not is_integral(costing_mat, gap_open_cost):
+        return _align_one_f64(seq_1, seq_2, costing_mat, gap_open_cost, device)
     dense = DenseScheme(costing_mat, gap_open_cost)
     ctx = _native.default_context(device)
     ctx.set_scheme(dense)
@@ -176,10 +190,24 @@ def make_dp_array(seq_1: str, seq_2: str, costing_mat: dict, max_cost: int, gap_
 def dp_array_forward(dp_array, seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost):
     """Fill ``dp_array`` in place on the GPU, starting from the boundary row and
     column already present in it (as the reference's own test does)."""
-    dense = DenseScheme(costing_mat, gap_open_cost)
-    ctx = _native.default_context(0)
-    ctx.set_scheme(dense)
     m, n = len(seq_1), len(seq_2)
+    ctx = _native.default_context(0)
+    boundary = [v for j in range(n + 1) for v in dp_array[0][j]] + [v for i in range(m + 1) for v in dp_array[i][0]]
+    if not is_integral(costing_mat, gap_open_cost) or any(int(v) != v for v in boundary):
+        dense = DenseSchemeF64(costing_mat, gap_open_cost)
+        table = np.zeros((m + 1, n + 1, 3), dtype=np.float64)
+        for j in range(n + 1):
+            table[0, j] = dp_array[0][j]
+        for i in range(m + 1):
+            table[i, 0] = dp_array[i][0]
+        ctx.fill_values_f64(dense, dense.encode(seq_1), dense.encode(seq_2), table, keep_boundary=True)
+        for i in range(1, m + 1):
+            row = dp_array[i]
+            for j in range(1, n + 1):
+                row[j] = tuple(float(v) for v in table[i, j])
+        return None
+    dense = DenseScheme(costing_mat, gap_open_cost)
+    ctx.set_scheme(dense)
     table = np.zeros((m + 1, n + 1, 3), dtype=np.int32)
     for j in range(n + 1):
         table[0, j] = dp_array[0][j]

@@ -15,6 +15,13 @@ import numpy as np
 GAP = "-"
 
 
+def is_integral(costing_mat: dict, gap_open_cost) -> bool:
+    """True when every cost is a whole number -- what the reference's entry point always produces
+    (start.py:51-69,121-133,423); False selects the f64 path."""
+    vals = [v for row in costing_mat.values() for v in row.values()] + [gap_open_cost]
+    return all(int(v) == v for v in vals)
+
+
 class DenseScheme:
     def __init__(self, costing_mat: dict, gap_open_cost: int, letters=None):
         self.letters = [k for k in costing_mat if k != GAP] if letters is None else list(letters)
@@ -59,3 +66,23 @@ class DenseScheme:
         except UnicodeEncodeError:
             pass
         return np.fromiter((idx[ch] for ch in seq), dtype=np.uint8, count=len(seq))
+
+
+class DenseSchemeF64(DenseScheme):
+    """The same lowering in float64, for costing matrices with fractional entries (reachable in
+    the reference only through its inner functions; globaligner.py:371,761)."""
+
+    def __init__(self, costing_mat: dict, gap_open_cost, letters=None):
+        self.letters = [k for k in costing_mat if k != GAP] if letters is None else list(letters)
+        A = len(self.letters)
+        if A < 1 or A > 250:
+            raise RuntimeError(f"the GPU path supports alphabets of 1..250 letters, got {A}")
+        self.A = A
+        self.index = {ch: k for k, ch in enumerate(self.letters)}
+        self.sub = np.array([[costing_mat[x][y] for y in self.letters] for x in self.letters],
+                            dtype=np.float64).reshape(A * A)
+        self.gap_h = np.array([costing_mat[GAP][y] for y in self.letters], dtype=np.float64)
+        self.gap_v = np.array([costing_mat[x][GAP] for x in self.letters], dtype=np.float64)
+        self.gap_open = float(gap_open_cost)
+        self.max_cost = float(max(max(row.values()) for row in costing_mat.values()))
+        self._lut = None

@@ -103,6 +103,14 @@ int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off, const 
                    const int64_t *out_ops_off, int32_t *out_ops_len, int32_t *out_status,
                    uint32_t flags);
 
+/* The same for a fixed-length batch (every seq_1 has m letters, every seq_2 n letters -- the
+ * usual shape of sequencing reads): no offset arrays; pair p's letters start at p*m / p*n and
+ * its packed-ops slice at byte p * (ceil((m+n)/4) rounded up to a multiple of 4).  Saves the
+ * host-side scan of the offset arrays and their upload. */
+int ga_align_batch_uniform(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                           int64_t n_pairs, int32_t *out_cost, uint8_t *out_ops, int32_t *out_ops_len,
+                           int32_t *out_status, uint32_t flags);
+
 /* Same work on DEVICE-resident buffers, split into planning (host side: reads
  * the two offset arrays, sizes scratch, uploads tile metadata) and running
  * (only kernels; asynchronous on the ctx stream).  d_* are device pointers the
@@ -177,6 +185,26 @@ int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2,
 int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                     const uint16_t *draws, int64_t n_draws, int32_t *out_cost, uint8_t *out_ops,
                     int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status);
+
+/* Float-valued penalties.  The reference's entry point coerces every score
+ * and cost with int() (start.py:51-69,121-133,423), but its inner functions take floats when
+ * called directly (type hints globaligner.py:371,761).  These two calls serve that case for
+ * ONE pair in f64, adding and comparing in the reference's own order (min over the three
+ * predecessors, then the step cost; :359-363), so the doubles are bit-identical to CPython's.
+ * The scheme travels with the call: sub[a*A+b] = costing_mat[a][b], gap_h[b] = costing_mat["-"][b],
+ * gap_v[a] = costing_mat[a]["-"], max_cost = get_max_val(costing_mat).
+ *   ga_fill_values_f64: the table dp_array_forward leaves ((m+1)*(n+1)*3 doubles; keep_boundary as
+ *     in ga_fill_values).
+ *   ga_align_f64: cost + traceback ranking VALUES as dp_array_backward does (:425-581);
+ *     draws == NULL -> canonical order (first-listed option of every tie), else as ga_align_replay.
+ * Not a throughput path: (m+1)*(n+1) <= 5e7. */
+int ga_fill_values_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
+                       double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2,
+                       int64_t n, int keep_boundary, double *table);
+int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
+                 double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                 const uint16_t *draws, int64_t n_draws, double *out_cost, uint8_t *out_ops,
+                 int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status);
 
 /* Integer-ALU roofline microbenchmark (no memory traffic): giga-instructions/s the
  * device retires of one instruction kind.  Throughput modes (8 independent chains per

@@ -137,8 +137,24 @@ def _candidates(cell, level, o):
     return (cell[0] + o, cell[1] + o, cell[2])
 
 
-def tied_minima(cell, level, o):
-    v = _candidates(cell, level, o)
+def _candidates_exact(cell, level, o, cm, a, b, first):
+    """The same for float-valued costs, where the common addend DOES matter: exactly the sums
+    the reference forms (globaligner.py:490-510) -- nothing at the first evaluation (:425-435);
+    on level 0 cm[a][b] on all three; on levels 1 and 2 cm["-"][b] (the "-" row on both), with
+    gap_open_cost added to it first on the entries whose level differs."""
+    if first:
+        return tuple(cell)
+    if level == 0:
+        add = (cm[a][b],) * 3
+    elif level == 1:
+        add = (o + cm[GAP][b], cm[GAP][b], o + cm[GAP][b])
+    else:
+        add = (o + cm[GAP][b], o + cm[GAP][b], cm[GAP][b])
+    return tuple(sum(cs) for cs in zip(cell, add))
+
+
+def tied_minima(cell, level, o, exact=None):
+    v = _candidates(cell, level, o) if exact is None else _candidates_exact(cell, level, o, *exact)
     lo = min(v)
     return tuple(k for k in range(3) if v[k] == lo)
 
@@ -148,11 +164,12 @@ def first_listed(options):
     return options[0]
 
 
-def walk(table, seq_1, seq_2, gap_open_cost, choose=first_listed):
+def walk(table, seq_1, seq_2, gap_open_cost, choose=first_listed, cm=None):
     """Return (ops, cost): ops in walk order (end of alignment first).
 
     `choose` receives the tuple of tied minimal levels (ascending) and picks
-    one.  Raises IndexError-like ValueError where the reference would leave the
+    one.  `cm`: pass the costing matrix when costs are floats (see _candidates_exact).
+    Raises IndexError-like ValueError where the reference would leave the
     table (only possible outside the domain max(m, n) > gap_open_cost).
     """
     m, n = len(seq_1), len(seq_2)
@@ -166,7 +183,10 @@ def walk(table, seq_1, seq_2, gap_open_cost, choose=first_listed):
         # (:425-458); later ones are loop iterations (:475-537).
         if (i == 0 and j == 0) or i < 0 or j < 0:
             raise ValueError("walk left the table (reference-undefined input)")
-        k = choose(tied_minima(table[i][j], level, o))
+        # cm given: float-valued costs, rank the reference's exact sums (seq[i-1] wraps at i == 0
+        # like Python's negative index)
+        exact = None if cm is None else (cm, seq_1[i - 1], seq_2[j - 1], steps == 0)
+        k = choose(tied_minima(table[i][j], level, o, exact))
         # A boundary cell can only be evaluated right after the first move
         # (when m == 1 or n == 1).  Inside the parity domain it always picks the
         # boundary-consistent level; anything else sends the reference to

@@ -482,3 +482,99 @@ def test_pipeline_variants_on_mixed_length_batches():
             assert np.array_equal(x, y) and np.array_equal(x, z)
         assert np.array_equal(only[0], whole[0])
     ctx.close()
+
+
+@pytest.mark.parametrize("m,n,bits", [(150, 150, 8), (150, 150, 2), (37, 91, 4), (300, 280, 2), (1, 5, 8), (700, 40, 8)])
+def test_fixed_length_entry_point_equals_offset_array_call(m, n, bits):
+    """ga_align_batch_uniform (implicit offsets) returns byte-identical costs, ops, lengths and
+    status to ga_align_batch on the same fixed-length batch, also when the scratch limit forces
+    several chunks."""
+    rng = np.random.default_rng(m * 1000 + n)
+    n_pairs = 3001
+    s1 = rng.integers(0, 4, size=m * n_pairs, dtype=np.uint8)
+    s2 = rng.integers(0, 4, size=n * n_pairs, dtype=np.uint8)
+    # make most pairs similar so the walks are not trivial
+    if m == n:
+        keep = rng.random(m * n_pairs) < 0.9
+        s2 = np.where(keep, s1, s2).astype(np.uint8)
+    off1 = np.arange(n_pairs + 1, dtype=np.int64) * m
+    off2 = np.arange(n_pairs + 1, dtype=np.int64) * n
+    dense = batch.Scheme(mismatch_cost=3, gap_extension_cost=2, gap_open_cost=4).dense_for(list("ACGT"))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    p1, p2 = _native.pack_letters(s1, bits), _native.pack_letters(s2, bits)
+    fl = _native.seq_flag(bits)
+    for limit in (64 << 30, 24 << 20):
+        ctx.set_scratch_limit(limit)
+        cost, ops, ops_off, ops_len, status = ctx.align_batch(p1, off1, p2, off2, flags=fl)
+        ucost, uops, stride, ulen, ustatus = ctx.align_batch_uniform(p1, m, p2, n, n_pairs, flags=fl)
+        assert np.array_equal(ops_off, np.arange(n_pairs + 1) * stride)
+        assert np.array_equal(cost, ucost) and np.array_equal(ops_len, ulen) and np.array_equal(status, ustatus)
+        for p in (0, 1, 1500, n_pairs - 1):
+            assert np.array_equal(_native.unpack_ops(ops, int(ops_off[p]), int(ops_len[p])),
+                                  _native.unpack_ops(uops, p * stride, int(ulen[p])))
+        nb = (ops_len + 3) // 4
+        a = ops[:len(uops)].reshape(n_pairs, stride)
+        b = uops.reshape(n_pairs, stride)
+        mask = np.arange(stride)[None, :] < nb[:, None]
+        assert np.array_equal(a[mask], b[mask])
+    # cost-only form
+    c2 = ctx.align_batch_uniform(p1, m, p2, n, n_pairs, flags=fl | _native.GA_F_COST_ONLY)[0]
+    assert np.array_equal(c2, cost)
+    # against the oracle on a few pairs
+    k = 64
+    ref = c_oracle.align_batch(s1[:k * m], off1[:k + 1], s2[:k * n], off2[:k + 1], _oracle_dense(dense), 4)
+    assert np.array_equal(ref[3], cost[:k])
+    for p in range(k):
+        if ref[4][p] == 0:
+            assert np.array_equal(ref[0][ref[1][p]:ref[1][p] + ref[2][p]],
+                                  _native.unpack_ops(uops, p * stride, int(ulen[p])))
+
+
+def test_float_penalties_through_the_seam_functions():
+    """SURVEY.md 8f, f2 / north_star: float-valued penalties.  The tolerance north_star allows is
+    1e-6 relative on scores with identical alignments where there are no ties; the f64 kernels
+    add in the reference's order, so this test demands MORE: bit-identical doubles (SHA-256 of
+    the table bytes) and identical alignments including ties, against vectors generated by the
+    reference's own make_dp_array / dp_array_forward / dp_array_backward
+    (tests/golden/make_float_golden.py)."""
+    import hashlib
+    import struct
+    from globalign_b200 import globaligner as GA
+
+    cases = golden("float_cases.json")
+    for r in cases:
+        s1, s2, cm, o = r["seq_1"], r["seq_2"], r["cm"], r["o"]
+        dp = GA.make_dp_array(s1, s2, cm, r["max_cost"], o)
+        GA.dp_array_forward(dp, s1, s2, cm, o)
+        h = hashlib.sha256()
+        for row in dp:
+            for cell in row:
+                h.update(struct.pack("<3d", *(float(v) for v in cell)))
+        assert h.hexdigest() == r["table_sha256"]
+        a1, mid, a2, cost = GA.dp_array_backward(dp, s1, s2, cm, o)
+        assert [a1, mid, a2, float(cost)] == r["out"]
+        assert abs(cost - r["out"][3]) <= 1e-6 * max(1.0, abs(r["out"][3]))   # the stated tolerance
+
+
+def test_float_walk_with_replayed_draws_and_argument_checks():
+    from globalign_b200 import lowering
+    cm = {x: {y: (0.0 if x == y else 1.5) for y in "AC-"} for x in "AC-"}
+    cm["-"]["A"] = cm["-"]["C"] = cm["A"]["-"] = cm["C"]["-"] = 0.75
+    dense = lowering.DenseSchemeF64(cm, 0.5)
+    ctx = _native.default_context(0)
+    s1, s2 = dense.encode("ACCA"), dense.encode("ACA")
+    c0, ops0, ne0, st0 = ctx.align_f64(dense, s1, s2)
+    assert st0 == 0 and c0 == 1.25
+    # all-zero draws = first option everywhere = canonical
+    c1, ops1, ne1, st1 = ctx.align_f64(dense, s1, s2, draws=np.zeros(len(s1) + len(s2), dtype=np.uint16))
+    assert (c1, list(ops1), ne1, st1) == (c0, list(ops0), ne0, st0)
+    # draws choosing option 1 at every tie = the oracle walking with that rule
+    from oracle import py_oracle
+    c2, ops2, _, st2 = ctx.align_f64(dense, s1, s2, draws=np.full(len(s1) + len(s2), 0x5555, dtype=np.uint16))
+    tab = py_oracle.fill("ACCA", "ACA", cm, 0.5)
+    want, wcost = py_oracle.walk(tab, "ACCA", "ACA", 0.5, choose=lambda opts: opts[min(1, len(opts) - 1)], cm=cm)
+    assert st2 == 0 and c2 == wcost == c0 and list(ops2) == list(want) and list(ops2) != list(ops0)
+    bad = lowering.DenseSchemeF64(cm, float("nan"))
+    with pytest.raises(RuntimeError):
+        ctx.align_f64(bad, s1, s2)

@@ -128,3 +128,25 @@ def test_verify_path_rejects_non_canonical():
         assert (rc == 0) == (ops == list(cops))
         hits += rc != 0
     assert hits > 50
+
+
+def test_float_penalty_golden_vectors():
+    """float costs reach the reference's inner functions only; the oracle
+    reproduces the reference's doubles bit for bit (SHA-256 of the table's IEEE-754 bytes) and its
+    alignments, ranking the reference's exact sums (a common addend can change float ranks)."""
+    import hashlib
+    import struct
+
+    cases = golden("float_cases.json")
+    assert len(cases) >= 200
+    for r in cases:
+        tab = py_oracle.fill(r["seq_1"], r["seq_2"], r["cm"], r["o"])
+        h = hashlib.sha256()
+        for row in tab:
+            for cell in row:
+                h.update(struct.pack("<3d", *(float(v) for v in cell)))
+        assert h.hexdigest() == r["table_sha256"]
+        for i, j, vals in r["cells"]:
+            assert [float(v) for v in tab[i][j]] == vals          # tolerance: none (bit-exact)
+        ops, cost = py_oracle.walk(tab, r["seq_1"], r["seq_2"], r["o"], cm=r["cm"])
+        assert list(py_oracle.render(ops, r["seq_1"], r["seq_2"])) + [float(cost)] == r["out"]
