@@ -22,6 +22,7 @@ GA_F_COST_ONLY = 2
 GA_F_SERIAL = 4
 GA_F_SEQ_4BIT = 8
 GA_F_SEQ_2BIT = 16
+GA_F_KEEP_ORDER = 32
 T_H2D, T_FILL, T_WALK, T_D2H, T_TOTAL, T_COUNT = 0, 1, 2, 3, 4, 5
 
 #: every symbol include/globalign_b200.h declares (checked by the CPU tests)

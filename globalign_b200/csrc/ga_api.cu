@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <functional>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -28,31 +29,33 @@ struct KernelCfg {
     bool simple;
     const void *fill_fn;
     void (*launch_fill)(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
-                        const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const uint8_t *s1,
+                        const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const int *perm,
+                        const uint8_t *s1,
                         const long long *off1, const uint8_t *s2, const long long *off2,
                         uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost, int persistent);
     void (*launch_walk)(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, const UniformTiles &ut, int pair_lo,
-                        int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
+                        int n_pairs, const int *perm, const uint8_t *s1, const long long *off1, const uint8_t *s2,
                         const long long *off2, const uint32_t *codes, uint8_t *out_ops,
                         const long long *ops_off, int *out_len, int *out_status);
 };
 
 template <bool P, bool S, int R, int G>
 static void launch_fill_t(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
-                          const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const uint8_t *s1,
+                          const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const int *perm,
+                          const uint8_t *s1,
                           const long long *off1, const uint8_t *s2, const long long *off2,
                           uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost,
                           int persistent) {
-    fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, ut, n_tiles, counter, s1, off1, s2, off2,
+    fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, ut, n_tiles, counter, perm, s1, off1, s2, off2,
                                                      codes, bnd, bnd_stride, sb_stride, out_cost, persistent);
 }
 template <bool P, int R, int G>
 static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *tiles, const UniformTiles &ut, int pair_lo,
-                          int n_pairs, const uint8_t *s1, const long long *off1, const uint8_t *s2,
+                          int n_pairs, const int *perm, const uint8_t *s1, const long long *off1, const uint8_t *s2,
                           const long long *off2, const uint32_t *codes, uint8_t *out_ops,
                           const long long *ops_off, int *out_len, int *out_status) {
     const int grid = (n_pairs + 127) / 128;
-    walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, ut, pair_lo, n_pairs, s1, off1, s2, off2, codes,
+    walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, ut, pair_lo, n_pairs, perm, s1, off1, s2, off2, codes,
                                                out_ops, ops_off, out_len, out_status);
 }
 template <bool P, bool S, int R, int G>
@@ -77,6 +80,13 @@ static const std::vector<KernelCfg> &registry() {
         make_cfg<true, true, 16, 16>("fill_p16_r16_g16"),
         make_cfg<true, true, 8, 32>("fill_p16_r8_g32"),
         make_cfg<true, true, 16, 32>("fill_p16_r16_g32"),
+        // packed unsigned 16-bit, two pairs per register, table-driven schemes (proteins up to
+        // ~1000 residues under BLOSUM62)
+        make_cfg<true, false, 8, 8>("fill_p16t_r8_g8"),
+        make_cfg<true, false, 8, 16>("fill_p16t_r8_g16"),
+        make_cfg<true, false, 8, 32>("fill_p16t_r8_g32"),
+        make_cfg<true, false, 12, 32>("fill_p16t_r12_g32"),
+        make_cfg<true, false, 16, 32>("fill_p16t_r16_g32"),
         // int32, simple schemes (compare instead of table)
         make_cfg<false, true, 8, 8>("fill_i32s_r8_g8"),
         make_cfg<false, true, 8, 16>("fill_i32s_r8_g16"),
@@ -133,6 +143,8 @@ struct ga_ctx {
     const KernelCfg *cfg = nullptr;
     int64_t n_pairs = 0;
     std::vector<TileDesc> tiles;
+    std::vector<int> perm;             // pair order of a ragged plan (empty: identity)
+    DevBuf d_perm;
     std::vector<Chunk> chunks;
     int sb_stride = 0, bnd_stride = 0, grid = 0;
     size_t smem = 0;
@@ -253,7 +265,7 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->d_sub4, &ctx->d_gh4t, &ctx->d_gv4t, &ctx->d_gvraw, &ctx->d_ghraw,
-                      &ctx->d_tiles, &ctx->d_codes[0], &ctx->d_codes[1], &ctx->d_bnd[0], &ctx->d_bnd[1],
+                      &ctx->d_tiles, &ctx->d_perm, &ctx->d_codes[0], &ctx->d_codes[1], &ctx->d_bnd[0], &ctx->d_bnd[1],
                       &ctx->d_counter, &ctx->d_s1,
                       &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
                       &ctx->d_opsoff, &ctx->d_len, &ctx->d_status, &ctx->l_colsum, &ctx->l_rowsum,
@@ -378,9 +390,17 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
         const long long vmax = big + (std::min(Mp, Np) + 2) * sc.max_cost + 3LL * sc.o;
         return 4 * vmax + 3 < 32767 && 4LL * sc.mm < 65536;
     };
+    // The packed table kernels compare UNSIGNED halves and give padded rows and columns a zero-cost
+    // letter, so padded cells only copy values: h <= big + o (a path of max(i,j) steps plus one
+    // gap open), L / U <= h + o + max_cost, their inputs d1 / d2 one more step cost.
+    auto fits16u = [&]() {
+        const long long big = (long long)(sc.max_cost + 1) * std::max(maxM, maxN);
+        return 4 * (big + 2LL * sc.o + 2LL * sc.max_cost) + 3 <= 65535 && sc.A <= 64;
+    };
     if (const char *force = getenv("GA_FORCE_CFG")) {      // tests and tuning
         const KernelCfg *c = find_cfg(force);
-        if (!c || (c->simple && !sc.simple) || (c->lay.packed && !fits16(c))) return nullptr;
+        if (!c || (c->simple && !sc.simple)) return nullptr;
+        if (c->lay.packed && !(c->simple ? fits16(c) : fits16u())) return nullptr;
         return c;
     }
     if (sc.simple) {
@@ -394,6 +414,9 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
         }
         return find_cfg(maxM <= 64 ? "fill_i32s_r8_g8" : maxM <= 128 ? "fill_i32s_r8_g16" : "fill_i32s_r8_g32");
     }
+    if (!(flags & GA_F_FORCE_GENERIC) && fits16u())
+        return find_cfg(maxM <= 64 ? "fill_p16t_r8_g8" : maxM <= 128 ? "fill_p16t_r8_g16"
+                        : maxM <= 256 ? "fill_p16t_r8_g32" : "fill_p16t_r16_g32");
     return find_cfg(maxM <= 64 ? "fill_i32t_r8_g8" : maxM <= 128 ? "fill_i32t_r8_g16" : "fill_i32t_r8_g32");
 }
 
@@ -484,67 +507,36 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     }
     if (!cfg->simple && ctx->sc.A > 64)
         return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
-    // tiles: consecutive groups of PPT pairs
+    // tiles: consecutive groups of PPT positions of the pair order
     const int64_t n_tiles = (n_pairs + L.PPT - 1) / L.PPT;
     const bool uniform = (minM == maxM && minN == maxN);
     ctx->chunks.clear();
-    std::vector<long long> tile_u4;
-    long long total_u4 = 0, biggest = 0, uni_u4 = 0;
-    if (uniform) {
-        // every tile is the same: no descriptor array, the kernels compute them (UniformTiles)
-        uni_u4 = tile_code_u4(maxM, maxN, L.G, L.BAND, L.NW);
-        total_u4 = uni_u4 * n_tiles;
-        biggest = uni_u4;
-        ctx->tiles.clear();
-    } else {
-        ctx->tiles.resize((size_t)n_tiles);
-        tile_u4.resize((size_t)n_tiles);
-        long long part_total[8] = {}, part_big[8] = {};
-        TileDesc *tiles = ctx->tiles.data();
-        parallel_for(n_tiles, [&](int tid, int64_t tlo, int64_t thi) {
-            long long tot = 0, big = 0;
-            for (int64_t t = tlo; t < thi; ++t) {
-                TileDesc &td = tiles[t];
-                const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
-                int M = 0, N = 0;
-                for (int64_t p = lo; p < hi; ++p) {
-                    M = std::max<int>(M, (int)(s1_off[p + 1] - s1_off[p]));
-                    N = std::max<int>(N, (int)(s2_off[p + 1] - s2_off[p]));
-                }
-                tile_u4[(size_t)t] = tile_code_u4(M, N, L.G, L.BAND, L.NW);
-                tot += tile_u4[(size_t)t];
-                big = std::max(big, tile_u4[(size_t)t]);
-                td.first_pair = (int)lo;
-                td.n_pairs = (int)(hi - lo);
-                td.M = M;
-                td.N = N;
-            }
-            part_total[tid] = tot;
-            part_big[tid] = big;
-        });
-        for (int k = 0; k < 8; ++k) { total_u4 += part_total[k]; biggest = std::max(biggest, part_big[k]); }
-    }
-    ht.lap("plan: tiles");
+    ctx->perm.clear();
     // Chunks: the direction codes of a chunk live in one of two scratch buffers, so
     // the walk of chunk c overlaps the fill of chunk c+1.  Large batches are cut into
     // ~4 chunks (more if the scratch limit requires); GA_F_SERIAL keeps one stream
     // and as few chunks as the limit allows.
     const bool serial = (flags & GA_F_SERIAL) != 0;
     const long long hard_u4 = std::max<long long>((serial ? ctx->scratch_limit : ctx->scratch_limit / 2) / 16, 1);
-    if (biggest > hard_u4)
-        return fail(ctx, GA_E_NOMEM, "one tile needs %lld bytes of direction codes, above the scratch limit", biggest * 16);
-    long long limit_u4 = hard_u4;
-    if (!serial) {
+    long long total_u4 = 0, uni_u4 = 0, max_chunk_u4 = 0;
+    auto soft_limit = [&](long long total) {
+        if (serial) return hard_u4;
         const long long min_u4 = ((long long)1 << 30) / 16;            // do not cut below 1 GiB of codes
         // measured on 1M x (150 x 150): device-resident runs are fastest with 2-4 chunks (fewer
         // fill tails), the host-buffer path with ~8 (finer overlap of copies and kernels)
         int want_chunks = ctx->plan_for_io ? 8 : 4;
         if (const char *e = getenv("GA_CHUNKS")) want_chunks = std::max(1, atoi(e));
-        limit_u4 = std::min(hard_u4, std::max(min_u4, (total_u4 + want_chunks - 1) / want_chunks));
-    }
-    Chunk cur{0, 0, 0, 0, 0};
-    long long max_chunk_u4 = 0;
+        return std::min(hard_u4, std::max(min_u4, (total + want_chunks - 1) / want_chunks));
+    };
     if (uniform) {
+        // every tile is the same: no descriptor array, the kernels compute them (UniformTiles)
+        uni_u4 = tile_code_u4(maxM, maxN, L.G, L.BAND, L.NW);
+        total_u4 = uni_u4 * n_tiles;
+        ctx->tiles.clear();
+        if (uni_u4 > hard_u4)
+            return fail(ctx, GA_E_NOMEM, "one tile needs %lld bytes of direction codes, above the scratch limit", uni_u4 * 16);
+        const long long limit_u4 = soft_limit(total_u4);
+        ht.lap("plan: tiles");
         const int64_t per_chunk = std::max<int64_t>(1, limit_u4 / uni_u4);       // tiles per chunk
         for (int64_t t = 0; t < n_tiles; t += per_chunk) {
             const int64_t thi = std::min(n_tiles, t + per_chunk);
@@ -554,22 +546,127 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
             max_chunk_u4 = std::max(max_chunk_u4, c.code_u4);
         }
     } else {
-        for (int64_t t = 0; t < n_tiles; ++t) {
-            const long long u4 = tile_u4[(size_t)t];
-            if (cur.code_u4 + u4 > limit_u4 && cur.code_u4 > 0) {
-                cur.tile_hi = (int)t;
-                cur.pair_hi = (int)(t * L.PPT);
-                ctx->chunks.push_back(cur);
-                max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
-                cur = Chunk{(int)t, 0, (int)(t * L.PPT), 0, 0};
-            }
-            ctx->tiles[(size_t)t].code_off = cur.code_u4;
-            cur.code_u4 += u4;
+        // Ragged batch.  (1) Cut the batch, in the caller's order, into chunks of whole tiles by
+        // an estimate of each pair's share of direction codes (chunks stay contiguous pair ranges
+        // so that their results can be copied out as slices).  (2) Inside each chunk order the
+        // pairs by length, longest first: the pairs of a tile -- and the two pairs packed into one
+        // register -- then have nearly the same lengths, and the padding to the tile's longest
+        // pair mostly disappears.  (3) Form tiles over that order.  If a chunk ends up above the
+        // scratch limit (the estimate ignores padding) the cut is redone with a lower target.
+        const bool sort_pairs = !(flags & GA_F_KEEP_ORDER) && (L.PPT > 1 || maxM > L.BAND);
+        std::vector<double> est((size_t)n_pairs);
+        double est_total = 0;
+        {
+            double part[8] = {};
+            parallel_for(n_pairs, [&](int tid, int64_t lo, int64_t hi) {
+                double tot = 0;
+                for (int64_t p = lo; p < hi; ++p) {
+                    est[(size_t)p] = (double)tile_code_u4((int)(s1_off[p + 1] - s1_off[p]), (int)(s2_off[p + 1] - s2_off[p]),
+                                                         L.G, L.BAND, L.NW) / L.PPT;
+                    tot += est[(size_t)p];
+                }
+                part[tid] = tot;
+            });
+            for (double v : part) est_total += v;
         }
-        cur.tile_hi = (int)n_tiles;
-        cur.pair_hi = (int)n_pairs;
-        ctx->chunks.push_back(cur);
-        max_chunk_u4 = std::max(max_chunk_u4, cur.code_u4);
+        ctx->tiles.resize((size_t)n_tiles);
+        if (sort_pairs) ctx->perm.resize((size_t)n_pairs);
+        TileDesc *tiles = ctx->tiles.data();
+        double target = (double)soft_limit((long long)(est_total * 1.02) + 1);
+        for (int attempt = 0;; ++attempt) {
+            ctx->chunks.clear();
+            {   // (1)
+                Chunk cur{0, 0, 0, 0, 0};
+                double acc = 0;
+                for (int64_t t = 0; t < n_tiles; ++t) {
+                    double e = 0;
+                    const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
+                    for (int64_t p = lo; p < hi; ++p) e += est[(size_t)p];
+                    if (acc + e > target && acc > 0) {
+                        cur.tile_hi = (int)t;
+                        cur.pair_hi = (int)lo;
+                        ctx->chunks.push_back(cur);
+                        cur = Chunk{(int)t, 0, (int)lo, 0, 0};
+                        acc = 0;
+                    }
+                    acc += e;
+                }
+                cur.tile_hi = (int)n_tiles;
+                cur.pair_hi = (int)n_pairs;
+                ctx->chunks.push_back(cur);
+            }
+            // (2) + (3), chunks in parallel
+            const int64_t n_chunks = (int64_t)ctx->chunks.size();
+            std::atomic<int64_t> next{0};
+            auto work = [&]() {
+                std::vector<uint64_t> keys;
+                for (;;) {
+                    const int64_t c = next.fetch_add(1);
+                    if (c >= n_chunks) break;
+                    Chunk &ch = ctx->chunks[(size_t)c];
+                    if (sort_pairs) {
+                        keys.resize((size_t)(ch.pair_hi - ch.pair_lo));
+                        for (int64_t p = ch.pair_lo; p < ch.pair_hi; ++p) {
+                            const uint64_t m = (uint64_t)(s1_off[p + 1] - s1_off[p]), n = (uint64_t)(s2_off[p + 1] - s2_off[p]);
+                            // m < 2^25, n < 2^16, position in the chunk < 2^23 or ties keep any order
+                            keys[(size_t)(p - ch.pair_lo)] = (m << 39) | (n << 23) | (uint64_t)((p - ch.pair_lo) & 0x7fffff);
+                        }
+                        std::sort(keys.begin(), keys.end(), std::greater<uint64_t>());
+                        if (keys.size() <= 0x800000) {
+                            for (size_t k = 0; k < keys.size(); ++k)
+                                ctx->perm[(size_t)ch.pair_lo + k] = ch.pair_lo + (int)(keys[k] & 0x7fffff);
+                        } else {   // positions do not fit the key: sort an index array instead
+                            std::vector<int> idx(keys.size());
+                            for (size_t k = 0; k < idx.size(); ++k) idx[k] = ch.pair_lo + (int)k;
+                            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+                                const int64_t mx = s1_off[x + 1] - s1_off[x], my = s1_off[y + 1] - s1_off[y];
+                                if (mx != my) return mx > my;
+                                return s2_off[x + 1] - s2_off[x] > s2_off[y + 1] - s2_off[y];
+                            });
+                            std::copy(idx.begin(), idx.end(), ctx->perm.begin() + ch.pair_lo);
+                        }
+                    }
+                    long long u4sum = 0;
+                    for (int64_t t = ch.tile_lo; t < ch.tile_hi; ++t) {
+                        TileDesc &td = tiles[t];
+                        const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
+                        int M = 0, N = 0;
+                        for (int64_t k = lo; k < hi; ++k) {
+                            const int64_t p = sort_pairs ? ctx->perm[(size_t)k] : k;
+                            M = std::max<int>(M, (int)(s1_off[p + 1] - s1_off[p]));
+                            N = std::max<int>(N, (int)(s2_off[p + 1] - s2_off[p]));
+                        }
+                        td.first_pair = (int)lo;
+                        td.n_pairs = (int)(hi - lo);
+                        td.M = M;
+                        td.N = N;
+                        td.code_off = u4sum;
+                        u4sum += tile_code_u4(M, N, L.G, L.BAND, L.NW);
+                    }
+                    ch.code_u4 = u4sum;
+                }
+            };
+            {
+                const int nt = (int)std::min<int64_t>(8, n_chunks);
+                std::vector<std::thread> th;
+                for (int k = 1; k < nt; ++k) th.emplace_back(work);
+                work();
+                for (auto &t : th) t.join();
+            }
+            total_u4 = 0;
+            max_chunk_u4 = 0;
+            for (const Chunk &ch : ctx->chunks) {
+                total_u4 += ch.code_u4;
+                max_chunk_u4 = std::max(max_chunk_u4, ch.code_u4);
+            }
+            if (max_chunk_u4 <= hard_u4) break;
+            bool single = false;
+            for (const Chunk &ch : ctx->chunks) single = single || (ch.code_u4 > hard_u4 && ch.tile_hi - ch.tile_lo == 1);
+            if (single || attempt >= 12)
+                return fail(ctx, GA_E_NOMEM, "one tile needs more direction-code scratch than the scratch limit allows");
+            target = std::min(target, (double)hard_u4) * 0.7;
+        }
+        ht.lap("plan: tiles");
     }
 
     ht.lap("plan: chunks");
@@ -579,7 +676,11 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     ctx->bnd_stride = maxN + 8;
     const size_t elt = L.packed ? 4 : 1;
     size_t table = 0;
-    if (!cfg->simple) table = (((size_t)(ctx->sc.A + 1) * ctx->sc.A + ctx->sc.A) * 4 + 15) & ~(size_t)15;
+    if (!cfg->simple) {
+        const size_t A = (size_t)ctx->sc.A;
+        table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
+                         : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
+    }
     ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
     if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
     CK(cudaFuncSetAttribute(cfg->fill_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
@@ -590,6 +691,7 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     ctx->grid = (int)std::min<long long>(want_blocks, (long long)per_sm * ctx->sm_count);
     int rc;
     if (!uniform && (rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
+    if (!ctx->perm.empty() && (rc = ensure(ctx, ctx->d_perm, (size_t)n_pairs * sizeof(int)))) return rc;
     ht.lap("plan: occupancy query");
     const int n_bufs = (serial || ctx->chunks.size() == 1) ? 1 : 2;
     for (int b = 0; b < n_bufs; ++b) {
@@ -600,6 +702,9 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     if (!uniform) {
         CK(cudaMemcpyAsync(ctx->d_tiles.p, ctx->tiles.data(), (size_t)n_tiles * sizeof(TileDesc),
                            cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->perm.empty())
+            CK(cudaMemcpyAsync(ctx->d_perm.p, ctx->perm.data(), (size_t)n_pairs * sizeof(int),
+                               cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // ctx->tiles may be re-planned by the caller
     }
     ht.lap("plan: scratch + tile upload");
@@ -694,8 +799,9 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         const int grid = persistent ? std::min(ctx->grid, (n_tiles + 3) / 4) : (n_tiles + 3) / 4;
         const TileDesc *d_tiles = ctx->uniform ? nullptr : (const TileDesc *)ctx->d_tiles.p + ch.tile_lo;
         const UniformTiles ut{ctx->uniM, ctx->uniN, ch.pair_lo, ch.pair_hi, ctx->uni_u4, ctx->uni_ops_stride};
+        const int *d_perm = ctx->perm.empty() ? nullptr : (const int *)ctx->d_perm.p;
         cfg->launch_fill(grid, ctx->smem, sF, ctx->sc, d_tiles, ut,
-                         n_tiles, (int *)ctx->d_counter.p + c, d_s1, (const long long *)d_s1_off, d_s2,
+                         n_tiles, (int *)ctx->d_counter.p + c, d_perm, d_s1, (const long long *)d_s1_off, d_s2,
                          (const long long *)d_s2_off, (uint4 *)ctx->d_codes[b].p, (int2 *)ctx->d_bnd[b].p,
                          ctx->bnd_stride, ctx->sb_stride, d_cost, persistent ? 1 : 0);
         CK(cudaGetLastError());
@@ -703,7 +809,7 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         if (sW != sF) CK(cudaStreamWaitEvent(sW, E.f1, 0));
         CK(cudaEventRecord(E.w0, sW));
         if (!cost_only) {
-            cfg->launch_walk(sW, ctx->sc, d_tiles, ut, ch.pair_lo, np,
+            cfg->launch_walk(sW, ctx->sc, d_tiles, ut, ch.pair_lo, np, d_perm,
                              d_s1, (const long long *)d_s1_off, d_s2, (const long long *)d_s2_off,
                              (const uint32_t *)ctx->d_codes[b].p, d_ops, (const long long *)d_ops_off,
                              d_len, d_status);

@@ -50,7 +50,7 @@ struct SchemeDev {
 
 struct TileDesc {
     long long code_off;  // start of this tile's direction codes, in uint4 units (chunk-relative)
-    int first_pair;      // first pair of the tile
+    int first_pair;      // position of the tile's first pair in the pair order (see pair_at)
     int n_pairs;         // pairs in the tile (<= items per warp * pairs per item)
     int M, N;            // longest seq_1 / seq_2 in the tile
 };
@@ -76,6 +76,11 @@ struct UniformTiles {
 __device__ __forceinline__ long long pair_off(const long long *__restrict__ off, long long p, long long len) {
     return off ? off[p] : p * len;
 }
+
+// Tiles hold consecutive positions of the planner's pair ORDER; `perm` maps a position to the
+// pair's index in the caller's arrays (nullptr: identity).  The planner orders the pairs of a
+// chunk by length so that the pairs sharing a tile (and, packed, a register) are alike.
+__device__ __forceinline__ int pair_at(const int *__restrict__ perm, int k) { return perm ? perm[k] : k; }
 
 __device__ __forceinline__ TileDesc tile_desc(const TileDesc *tiles, const UniformTiles &ut, int tile, int ppt) {
     if (tiles) return tiles[tile];

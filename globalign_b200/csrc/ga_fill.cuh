@@ -37,11 +37,14 @@
 
 namespace ga {
 
-template <bool PACKED>
+// VOps<PACKED, UNSIGNED16>: the min / add-min flavour.  Packed SIMPLE kernels compare signed
+// halves (values < 2^15); the packed TABLE kernels compare unsigned halves, which doubles the
+// range (values < 2^16) -- what 1000-residue proteins under BLOSUM62 need: 4 * 16 * 1000 = 64000.
+template <bool PACKED, bool UNS = false>
 struct VOps;
 
-template <>
-struct VOps<false> {
+template <bool UNS>
+struct VOps<false, UNS> {
     static constexpr unsigned TAGM = 3u;
     static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
         return (unsigned)__vimin3_s32((int)a, (int)b, (int)c);
@@ -53,7 +56,19 @@ struct VOps<false> {
 };
 
 template <>
-struct VOps<true> {
+struct VOps<true, true> {
+    static constexpr unsigned TAGM = 0x00030003u;
+    static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
+        return __vimin3_u16x2(a, b, c);
+    }
+    static __device__ __forceinline__ unsigned addmin(unsigned a, unsigned b, unsigned c) {
+        return __viaddmin_u16x2(a, b, c);                             // per half: min(a + b, c)
+    }
+    static __device__ __forceinline__ unsigned pk(unsigned lo, unsigned hi) { return lo | (hi << 16); }
+};
+
+template <>
+struct VOps<true, false> {
     static constexpr unsigned TAGM = 0x00030003u;
     static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) {
         return __vimin3_s16x2(a, b, c);
@@ -67,22 +82,42 @@ struct VOps<true> {
 template <bool PACKED, bool SIMPLE, int R, int G>
 __global__ void __launch_bounds__(128)
 fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const UniformTiles ut, int n_tiles,
-            int *tile_counter,
+            int *tile_counter, const int *__restrict__ perm,
             const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
             const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
             uint4 *__restrict__ codes, int2 *bnd, int bnd_stride, int sb_stride,
             int *__restrict__ out_cost, int persistent) {
     using L = Lay<PACKED, R, G>;
-    using V = VOps<PACKED>;
+    constexpr bool PT = PACKED && !SIMPLE;       // packed table kernel: two pairs per register, costs from tables
+    using V = VOps<PACKED, PT>;
     using BT = typename std::conditional<PACKED, uint32_t, uint8_t>::type;
-    static_assert(!PACKED || SIMPLE, "the packed 16-bit kernel is for simple schemes");
     static_assert(G >= 1 && G <= 32 && R >= 1, "bad configuration");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *s_sub = reinterpret_cast<int *>(smem_raw);
     int *s_gh = s_sub;
     size_t table_bytes = 0;
-    if (!SIMPLE) {
+    const int AP = sc.A + 1;                     // PT: letters 0..A-1 plus the zero-cost padding letter A
+    unsigned pt_lo = 0, pt_hi = 0;               // PT: shared-space byte addresses of the two tables
+    if (PT) {
+        // transposed [b][a], padding letter A in both directions (all zero, so padded cells only
+        // copy values and every half stays below 2^16); s_hi is the same table shifted into the
+        // upper half so that d0 = diag + s_lo[..] + s_hi[..] is one three-input add
+        unsigned *s_lo = reinterpret_cast<unsigned *>(smem_raw);
+        unsigned *s_hi = s_lo + AP * AP;
+        s_gh = reinterpret_cast<int *>(s_hi + AP * AP);
+        for (int k = threadIdx.x; k < AP * AP; k += blockDim.x) {
+            const int b = k / AP, a = k - b * AP;
+            const unsigned v = (a < sc.A && b < sc.A) ? (unsigned)sc.sub4[a * sc.A + b] : 0u;
+            s_lo[k] = v;
+            s_hi[k] = v << 16;
+        }
+        for (int k = threadIdx.x; k < AP; k += blockDim.x) s_gh[k] = k < sc.A ? sc.gh4t[k] : 1;
+        table_bytes = ((size_t)(2 * AP * AP + AP) * 4 + 15) & ~(size_t)15;
+        pt_lo = (unsigned)__cvta_generic_to_shared(s_lo);
+        pt_hi = (unsigned)__cvta_generic_to_shared(s_hi);
+        __syncthreads();
+    } else if (!SIMPLE) {
         const int n_sub = (sc.A + 1) * sc.A;
         s_gh = s_sub + n_sub;
         for (int k = threadIdx.x; k < n_sub; k += blockDim.x) s_sub[k] = sc.sub4[k];
@@ -104,7 +139,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const unsigned mm4 = 4u * sc.mm;
     const unsigned ghTc = V::pk(4u * sc.gh + 1u, 4u * sc.gh + 1u);
     const unsigned gvTc = V::pk(4u * sc.gv + 2u, 4u * sc.gv + 2u);
-    const unsigned padb = SIMPLE ? (unsigned)PAD_B : 0u;
+    const unsigned padb = SIMPLE ? (unsigned)PAD_B : (PT ? (unsigned)sc.A : 0u);
     // a*k+b forms that must stay IMADs (FMA pipe); see SchemeDev::k_one
     const unsigned K1 = sc.k_one, K4 = sc.k_four, KM1 = sc.k_minus_one;
 
@@ -127,8 +162,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         const int ia = my_item * L::PPI, ibx = ia + (PACKED ? 1 : 0);
         const bool haveA = lane_ok && ia < td.n_pairs;
         const bool haveB = PACKED && lane_ok && ibx < td.n_pairs;
-        const int pA = td.first_pair + min(ia, td.n_pairs - 1);
-        const int pB = td.first_pair + min(ibx, td.n_pairs - 1);
+        const int pA = pair_at(perm, td.first_pair + min(ia, td.n_pairs - 1));
+        const int pB = pair_at(perm, td.first_pair + min(ibx, td.n_pairs - 1));
         const long long a1 = pair_off(off1, pA, ut.M), a2 = pair_off(off2, pA, ut.N);
         const int mA = (int)(pair_off(off1, pA + 1, ut.M) - a1), nA = (int)(pair_off(off2, pA + 1, ut.N) - a2);
         long long b1 = a1;
@@ -148,8 +183,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         // ---- stage the seq_2 letters of every item of the tile in shared memory
         __syncwarp();
         for (int q = 0; q < L::IPW; ++q) {
-            const int qa = td.first_pair + min(q * L::PPI, td.n_pairs - 1);
-            const int qb = td.first_pair + min(q * L::PPI + (PACKED ? 1 : 0), td.n_pairs - 1);
+            const int qa = pair_at(perm, td.first_pair + min(q * L::PPI, td.n_pairs - 1));
+            const int qb = pair_at(perm, td.first_pair + min(q * L::PPI + (PACKED ? 1 : 0), td.n_pairs - 1));
             const long long oa = pair_off(off2, qa, ut.N), ob = pair_off(off2, qb, ut.N);
             const int na = (int)(pair_off(off2, qa + 1, ut.N) - oa), nb = (int)(pair_off(off2, qb + 1, ut.N) - ob);
             BT *row = sb + (size_t)q * sb_stride;
@@ -172,11 +207,46 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
 
         const int npass = (td.M + L::BAND - 1) / L::BAND;
         int colbase = sc.o;    // TABLE: o + sum of gap_v over the rows of earlier passes
+        int colbaseB = sc.o;   // PT: the same for pair B
         for (int p = 0; p < npass; ++p) {
             const int ib = p * L::BAND + g * R;    // DP row just above my first row
             unsigned aw[R], gvT[R], hl[R], Lp[R];
+            unsigned awB[PT ? R : 1];              // PT: byte offset of pair B's row letter in a table row
             int colv[R + 1];                       // column-0 value of rows ib .. ib+R (level 2)
-            if (SIMPLE) {
+            int colvB[PT ? R + 1 : 1];             // PT: the same for pair B (per-letter gap costs)
+            if (PT) {
+                int mineA = 0, mineB = 0, gvrA[R], gvrB[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = ib + r;
+                    const int la = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
+                    const int lb = row < mB ? (int)ld_letter(s1, b1 + row, sc.seq_bits) : sc.A;
+                    aw[r] = 4u * (unsigned)la;
+                    awB[r] = 4u * (unsigned)lb;
+                    gvT[r] = (unsigned)sc.gv4t[la] | ((unsigned)sc.gv4t[lb] << 16);
+                    gvrA[r] = sc.gv_raw[la];
+                    gvrB[r] = sc.gv_raw[lb];
+                    mineA += gvrA[r];
+                    mineB += gvrB[r];
+                }
+                int inclA = mineA, inclB = mineB;  // inclusive scans over the lanes of my group
+#pragma unroll
+                for (int d = 1; d < G; d <<= 1) {
+                    const int va = __shfl_up_sync(FULL, inclA, d), vb = __shfl_up_sync(FULL, inclB, d);
+                    if (g >= d) { inclA += va; inclB += vb; }
+                }
+                const int totA = __shfl_sync(FULL, inclA, grp * G + G - 1);
+                const int totB = __shfl_sync(FULL, inclB, grp * G + G - 1);
+                colv[0] = colbase + inclA - mineA;
+                colvB[0] = colbaseB + inclB - mineB;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    colv[r + 1] = colv[r] + gvrA[r];
+                    colvB[r + 1] = colvB[r] + gvrB[r];
+                }
+                colbase += totA;
+                colbaseB += totB;
+            } else if (SIMPLE) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int row = ib + r;
@@ -217,14 +287,17 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned c = (unsigned)colv[r + 1];
-                hl[r] = V::pk(min(bigA, c), min(bigB, c)) << 2;                // min(D(i,0))
-                Lp[r] = V::pk(min(bigA, c + sc.o), min(bigB, c + sc.o)) << 2;  // level-1 candidate
+                const unsigned cB = PT ? (unsigned)colvB[r + 1] : c;
+                hl[r] = V::pk(min(bigA, c), min(bigB, cB)) << 2;                // min(D(i,0))
+                Lp[r] = V::pk(min(bigA, c + sc.o), min(bigB, cB + sc.o)) << 2;  // level-1 candidate
             }
             unsigned rh_prev = 0;                  // h(ib, 0): diagonal input of my first row at j = 1
-            if (ib != 0) rh_prev = V::pk(min(bigA, (unsigned)colv[0]), min(bigB, (unsigned)colv[0])) << 2;
+            if (ib != 0)
+                rh_prev = V::pk(min(bigA, (unsigned)colv[0]), min(bigB, (unsigned)(PT ? colvB[0] : colv[0]))) << 2;
 
             unsigned hb = 0, ub = 0, bv = 0;
             int rowj = sc.o;                       // TABLE: running row-0 value (pass 0, lane g == 0)
+            int rowjB = sc.o;                      // PT: the same for pair B
             int2 nxt = make_int2(0, 0);
             if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
             uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::WPP * 32) + lane;
@@ -242,15 +315,23 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                     if (g == 0) {
                         bin = bnew;
                         if (p == 0) {
-                            unsigned rj;           // row-0 value at column t+1 (level 1)
-                            if (SIMPLE) {
-                                rj = (unsigned)(sc.o + sc.gh * (t + 1));
+                            unsigned rj, rjB;      // row-0 value at column t+1 (level 1)
+                            if (PT) {
+                                // the padding letter A costs nothing: past the end of a pair the
+                                // running value stays put (those columns are never read back)
+                                const unsigned la = bnew & 0xFFFFu, lb = bnew >> 16;
+                                if (la < (unsigned)sc.A) rowj += sc.gh_raw[la];
+                                if (lb < (unsigned)sc.A) rowjB += sc.gh_raw[lb];
+                                rj = (unsigned)rowj;
+                                rjB = (unsigned)rowjB;
+                            } else if (SIMPLE) {
+                                rj = rjB = (unsigned)(sc.o + sc.gh * (t + 1));
                             } else {
                                 rowj += sc.gh_raw[bnew];
-                                rj = (unsigned)rowj;
+                                rj = rjB = (unsigned)rowj;
                             }
-                            rh = V::pk(min(bigA, rj), min(bigB, rj)) << 2;
-                            ru = V::pk(min(bigA, rj + sc.o), min(bigB, rj + sc.o)) << 2;
+                            rh = V::pk(min(bigA, rj), min(bigB, rjB)) << 2;
+                            ru = V::pk(min(bigA, rj + sc.o), min(bigB, rjB + sc.o)) << 2;
                         } else {
                             rh = (unsigned)nxt.x;
                             ru = (unsigned)nxt.y;
@@ -263,14 +344,28 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                     if (lane_ok && j >= 1 && j <= td.N) {
                         unsigned diag = rh_prev, up = ru;
                         rh_prev = rh;
-                        const unsigned ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
+                        unsigned ghT, rowA = 0, rowB = 0;
+                        if (PT) {
+                            const unsigned la = bv & 0xFFFFu, lb = bv >> 16;
+                            ghT = (unsigned)s_gh[la] | ((unsigned)s_gh[lb] << 16);
+                            rowA = pt_lo + la * (unsigned)(4 * AP);
+                            rowB = pt_hi + lb * (unsigned)(4 * AP);
+                        } else {
+                            ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
+                        }
                         unsigned acc[L::NW];
 #pragma unroll
                         for (int x = 0; x < L::NW; ++x) acc[x] = 0u;
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             unsigned d0;
-                            if (PACKED) {
+                            if (PT) {
+                                // two table loads (address adds as IMADs) and one three-input add
+                                unsigned sa, sb2;
+                                asm("ld.shared.u32 %0, [%1];" : "=r"(sa) : "r"(aw[r] * K1 + rowA));
+                                asm("ld.shared.u32 %0, [%1];" : "=r"(sb2) : "r"(awB[r] * K1 + rowB));
+                                d0 = diag + sa + sb2;
+                            } else if (PACKED) {
                                 d0 = __vminu2(aw[r] ^ bv, 0x00010001u) * mm4 + diag;
                             } else if (SIMPLE) {
                                 d0 = diag + (aw[r] != bv ? mm4 : 0u);

@@ -30,7 +30,7 @@ __device__ __forceinline__ int first_min3(long long v0, long long v1, long long 
 template <bool PACKED, int R, int G>
 __global__ void __launch_bounds__(128)
 walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const UniformTiles ut, int pair_lo,
-            int n_pairs,
+            int n_pairs, const int *__restrict__ perm,
             const uint8_t *__restrict__ s1, const long long *__restrict__ off1,
             const uint8_t *__restrict__ s2, const long long *__restrict__ off2,
             const uint32_t *__restrict__ codes, uint8_t *__restrict__ out_ops,
@@ -39,8 +39,8 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     using L = Lay<PACKED, R, G>;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_pairs) return;
-    const int p = pair_lo + k;                 // global pair index
-    const int tile = k / L::PPT;               // tiles hold PPT consecutive pairs of the chunk
+    const int p = pair_at(perm, pair_lo + k);  // the pair's index in the caller's arrays
+    const int tile = k / L::PPT;               // tiles hold PPT consecutive positions of the chunk's order
     const int within = k - tile * L::PPT;
     const int item = within / L::PPI;
     const int half = within - item * L::PPI;

@@ -67,7 +67,9 @@ enum {
     GA_F_COST_ONLY = 2,       /* skip the traceback walk (ops / ops_len untouched) */
     GA_F_SERIAL = 4,          /* one stream, no fill/walk/copy overlap (isolated kernel timing) */
     GA_F_SEQ_4BIT = 8,        /* s1/s2 are 4-bit packed letter streams (alphabet <= 16) */
-    GA_F_SEQ_2BIT = 16        /* s1/s2 are 2-bit packed letter streams (alphabet <= 4) */
+    GA_F_SEQ_2BIT = 16,       /* s1/s2 are 2-bit packed letter streams (alphabet <= 4) */
+    GA_F_KEEP_ORDER = 32      /* ragged batches: form tiles in the caller's pair order instead of ordering
+                                 each chunk's pairs by length first (results are the same either way) */
 };
 
 /* phases reported by ga_get_timing (milliseconds, CUDA events on the ctx stream) */

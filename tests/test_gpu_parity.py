@@ -18,6 +18,7 @@ PACKED_CFGS = ["fill_p16_r5_g32", "fill_p16_r10_g16", "fill_p16_r15_g10", "fill_
                "fill_p16_r16_g16", "fill_p16_r8_g32", "fill_p16_r16_g32"]
 I32S_CFGS = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
 I32T_CFGS = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]
+P16T_CFGS = ["fill_p16t_r8_g8", "fill_p16t_r8_g16", "fill_p16t_r8_g32", "fill_p16t_r12_g32", "fill_p16t_r16_g32"]
 
 
 @pytest.fixture(autouse=True)
@@ -200,17 +201,17 @@ def test_simple_scheme_kernels(cfg):
     ctx.close()
 
 
-@pytest.mark.parametrize("cfg", I32T_CFGS)
+@pytest.mark.parametrize("cfg", I32T_CFGS + P16T_CFGS)
 def test_table_scheme_kernels(cfg):
     rng = random.Random(zlib.crc32(cfg.encode()))
-    R, G = 8, int(cfg.split("_g")[1])
+    R, G = int(cfg.split("_r")[1].split("_")[0]), int(cfg.split("_g")[1])
     os.environ["GA_FORCE_CFG"] = cfg
     ctx = _native.Context(0)
     for trial in range(4):
         A = rng.choice([3, 5, 20, 24])
         dense = _table_dense(rng, A, rng.randint(0, 12))
         ctx.set_scheme(dense)
-        data = _random_batch(rng, 301, A, int(R * G * (2.3 if trial % 2 else 1.0)), 260)
+        data = _random_batch(rng, 301, A, min(int(R * G * (2.3 if trial % 2 else 1.0)), 900), 260)
         out = ctx.align_batch(*data)
         assert ctx.plan_info()["fill_kernel"] == cfg
         _compare_with_oracle(*data, dense, out)
@@ -228,7 +229,44 @@ def test_automatic_kernel_choice():
     assert ctx.plan_batch(long_dna.off1, long_dna.off2)["packed16"] is False
     prot = synth.protein_varlen(8, 3000)
     ctx.set_scheme(batch.Scheme(**synth.SCHEMES["cfg3"]).dense_for(sorted(synth.AMINO)))
-    assert ctx.plan_batch(prot.off1, prot.off2)["fill_kernel"].startswith("fill_i32t")
+    # proteins up to 1000 residues under BLOSUM62 fit the unsigned packed table kernels ...
+    assert ctx.plan_batch(prot.off1, prot.off2)["fill_kernel"].startswith("fill_p16t")
+    assert ctx.plan_batch(prot.off1, prot.off2, flags=_native.GA_F_FORCE_GENERIC)["fill_kernel"].startswith("fill_i32t")
+    # ... longer ones do not: 4 * 16 * 1100 > 65535
+    off = np.array([0, 1100, 2200], dtype=np.int64)
+    assert ctx.plan_batch(off, off)["fill_kernel"].startswith("fill_i32t")
+    ctx.close()
+
+
+def test_packed_table_kernel_at_the_edge_of_its_value_range():
+    """1000 x 1000 under BLOSUM62 (gap open 10): 4 * (16000 + 50) + 3 = 64203 of 65535.  Worst
+    cases for the magnitude of the values: unrelated sequences, all-W vs all-C-like mismatches
+    at the highest cost, and one-letter sequences against long ones (sentinel-derived values)."""
+    rng = random.Random(99)
+    dense = batch.Scheme(**synth.SCHEMES["cfg3"]).dense_for(sorted(synth.AMINO))
+    A = dense.A
+    worst = int(np.argmax(dense.sub.reshape(A, A).max(axis=1)))
+    worst_b = int(np.argmax(dense.sub.reshape(A, A)[worst]))
+    seqs = [([worst] * 1000, [worst_b] * 1000),
+            ([rng.randrange(A) for _ in range(1000)], [rng.randrange(A) for _ in range(1000)]),
+            ([rng.randrange(A)], [rng.randrange(A) for _ in range(1000)]),
+            ([rng.randrange(A) for _ in range(1000)], [rng.randrange(A)]),
+            ([worst] * 1000, [worst_b] * 11),
+            ([worst] * 997, [worst] * 1000),
+            ([rng.randrange(A) for _ in range(513)], [rng.randrange(A) for _ in range(1000)])]
+    s1, s2, o1, o2 = [], [], [0], [0]
+    for a, b in seqs:
+        s1 += a
+        s2 += b
+        o1.append(len(s1))
+        o2.append(len(s2))
+    data = (np.array(s1, dtype=np.uint8), np.array(o1, dtype=np.int64),
+            np.array(s2, dtype=np.uint8), np.array(o2, dtype=np.int64))
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    out = ctx.align_batch(*data)
+    assert ctx.plan_info()["fill_kernel"] == "fill_p16t_r16_g32"
+    _compare_with_oracle(*data, dense, out)
     ctx.close()
 
 
@@ -478,8 +516,9 @@ def test_pipeline_variants_on_mixed_length_batches():
         assert ctx.plan_info()["n_chunks"] >= 5
         serial = ctx.align_batch(*data, flags=_native.GA_F_SERIAL)
         only = ctx.align_batch(*data, flags=_native.GA_F_COST_ONLY)
-        for x, y, z in zip(whole, chunked, serial):
-            assert np.array_equal(x, y) and np.array_equal(x, z)
+        kept = ctx.align_batch(*data, flags=_native.GA_F_KEEP_ORDER)     # tiles in the caller's order
+        for x, y, z, k in zip(whole, chunked, serial, kept):
+            assert np.array_equal(x, y) and np.array_equal(x, z) and np.array_equal(x, k)
         assert np.array_equal(only[0], whole[0])
     ctx.close()
 
