@@ -109,6 +109,26 @@ struct Lay {
     static constexpr int BAND = G * R;                 // DP rows per pass
 };
 
+// Rows per lane of a tile's LAST pass.  Multi-pass configurations (G = 32, R divisible by 4)
+// run it with R/4, R/2, 3R/4 or R rows per lane, whichever is the smallest that holds the
+// rows left over after the full passes; the direction codes of that pass use
+// ceil(rows / RPW) words per plane per step.  Fill and walk kernels share this function.
+template <int R, int G>
+struct TailRows {
+    static constexpr bool ON = (G == 32) && (R % 4 == 0) && (R >= 8);
+    static constexpr int Q1 = ON ? R / 4 : R, Q2 = ON ? R / 2 : R, Q3 = ON ? 3 * R / 4 : R;
+};
+template <int R, int G>
+__host__ __device__ inline int tail_rows(int M) {
+    if (!TailRows<R, G>::ON) return R;
+    const int band = R * G;
+    const int left = M - ((M - 1) / band) * band;        // 1 .. band rows in the last pass
+    const int need = (left + G - 1) / G;
+    return need <= TailRows<R, G>::Q1 ? TailRows<R, G>::Q1
+           : need <= TailRows<R, G>::Q2 ? TailRows<R, G>::Q2
+           : need <= TailRows<R, G>::Q3 ? TailRows<R, G>::Q3 : R;
+}
+
 // Runtime mirror of Lay<> for host-side planning.
 struct LayInfo {
     int packed, R, G, RPW, WPP, NW, S, NQ, IPW, PPI, PPT, BAND;

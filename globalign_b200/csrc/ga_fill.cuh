@@ -201,221 +201,238 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         __syncwarp();
 
         // where the final cell (m, n) of each pair lives
-        const int pmA = (mA - 1) / L::BAND, gmA = ((mA - 1) % L::BAND) / R, rmA = (mA - 1) % R;
-        const int pmB = (mB - 1) / L::BAND, gmB = ((mB - 1) % L::BAND) / R, rmB = (mB - 1) % R;
+        // (the tile's last pass may run with fewer rows per lane, see tail_rows)
+        const int npass = (td.M + L::BAND - 1) / L::BAND;
+        const int rt_last = tail_rows<R, G>(td.M);
+        const int pmA = (mA - 1) / L::BAND, pmB = (mB - 1) / L::BAND;
+        const int rpA = pmA == npass - 1 ? rt_last : R, rpB = pmB == npass - 1 ? rt_last : R;
+        const int gmA = ((mA - 1) % L::BAND) / rpA, rmA = ((mA - 1) % L::BAND) % rpA;
+        const int gmB = ((mB - 1) % L::BAND) / rpB, rmB = ((mB - 1) % L::BAND) % rpB;
         unsigned costA = 0, costB = 0;
 
-        const int npass = (td.M + L::BAND - 1) / L::BAND;
         int colbase = sc.o;    // TABLE: o + sum of gap_v over the rows of earlier passes
         int colbaseB = sc.o;   // PT: the same for pair B
         for (int p = 0; p < npass; ++p) {
-            const int ib = p * L::BAND + g * R;    // DP row just above my first row
-            unsigned aw[R], gvT[R], hl[R], Lp[R];
-            unsigned awB[PT ? R : 1];              // PT: byte offset of pair B's row letter in a table row
-            int colv[R + 1];                       // column-0 value of rows ib .. ib+R (level 2)
-            int colvB[PT ? R + 1 : 1];             // PT: the same for pair B (per-letter gap costs)
-            if (PT) {
-                int mineA = 0, mineB = 0, gvrA[R], gvrB[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int row = ib + r;
-                    const int la = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
-                    const int lb = row < mB ? (int)ld_letter(s1, b1 + row, sc.seq_bits) : sc.A;
-                    aw[r] = 4u * (unsigned)la;
-                    awB[r] = 4u * (unsigned)lb;
-                    gvT[r] = (unsigned)sc.gv4t[la] | ((unsigned)sc.gv4t[lb] << 16);
-                    gvrA[r] = sc.gv_raw[la];
-                    gvrB[r] = sc.gv_raw[lb];
-                    mineA += gvrA[r];
-                    mineB += gvrB[r];
-                }
-                int inclA = mineA, inclB = mineB;  // inclusive scans over the lanes of my group
-#pragma unroll
-                for (int d = 1; d < G; d <<= 1) {
-                    const int va = __shfl_up_sync(FULL, inclA, d), vb = __shfl_up_sync(FULL, inclB, d);
-                    if (g >= d) { inclA += va; inclB += vb; }
-                }
-                const int totA = __shfl_sync(FULL, inclA, grp * G + G - 1);
-                const int totB = __shfl_sync(FULL, inclB, grp * G + G - 1);
-                colv[0] = colbase + inclA - mineA;
-                colvB[0] = colbaseB + inclB - mineB;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    colv[r + 1] = colv[r] + gvrA[r];
-                    colvB[r + 1] = colvB[r] + gvrB[r];
-                }
-                colbase += totA;
-                colbaseB += totB;
-            } else if (SIMPLE) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int row = ib + r;
-                    const unsigned la = row < mA ? ld_letter(s1, a1 + row, sc.seq_bits) : (unsigned)PAD_A;
-                    if (PACKED) {
-                        const unsigned lb = row < mB ? ld_letter(s1, b1 + row, sc.seq_bits) : (unsigned)PAD_A;
-                        aw[r] = la | (lb << 16);
-                    } else {
-                        aw[r] = la;
+            auto run_pass = [&](auto rt_c) {
+                constexpr int RT = decltype(rt_c)::value;          // DP rows per lane in this pass
+                constexpr int WPPT = (RT + L::RPW - 1) / L::RPW;   // code words per plane per step
+                constexpr int NWT = 2 * WPPT;
+                const int ib = p * L::BAND + g * RT;    // DP row just above my first row
+                unsigned aw[RT], gvT[RT], hl[RT], Lp[RT];
+                unsigned awB[PT ? RT : 1];              // PT: byte offset of pair B's row letter in a table row
+                int colv[RT + 1];                       // column-0 value of rows ib .. ib+R (level 2)
+                int colvB[PT ? RT + 1 : 1];             // PT: the same for pair B (per-letter gap costs)
+                if (PT) {
+                    int mineA = 0, mineB = 0, gvrA[RT], gvrB[RT];
+    #pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const int row = ib + r;
+                        const int la = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
+                        const int lb = row < mB ? (int)ld_letter(s1, b1 + row, sc.seq_bits) : sc.A;
+                        aw[r] = 4u * (unsigned)la;
+                        awB[r] = 4u * (unsigned)lb;
+                        gvT[r] = (unsigned)sc.gv4t[la] | ((unsigned)sc.gv4t[lb] << 16);
+                        gvrA[r] = sc.gv_raw[la];
+                        gvrB[r] = sc.gv_raw[lb];
+                        mineA += gvrA[r];
+                        mineB += gvrB[r];
                     }
-                    gvT[r] = gvTc;
-                }
-#pragma unroll
-                for (int r = 0; r <= R; ++r) colv[r] = sc.o + sc.gv * (ib + r);
-            } else {
-                int mine = 0, gvr[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int row = ib + r;
-                    const int a = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
-                    aw[r] = (unsigned)(a * sc.A);
-                    gvT[r] = (unsigned)sc.gv4t[a];
-                    gvr[r] = sc.gv_raw[a];
-                    mine += gvr[r];
-                }
-                int incl = mine;                   // inclusive scan over the lanes of my group
-#pragma unroll
-                for (int d = 1; d < G; d <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, d);
-                    if (g >= d) incl += v;
-                }
-                const int band_total = __shfl_sync(FULL, incl, grp * G + G - 1);
-                colv[0] = colbase + incl - mine;
-#pragma unroll
-                for (int r = 0; r < R; ++r) colv[r + 1] = colv[r] + gvr[r];
-                colbase += band_total;
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const unsigned c = (unsigned)colv[r + 1];
-                const unsigned cB = PT ? (unsigned)colvB[r + 1] : c;
-                hl[r] = V::pk(min(bigA, c), min(bigB, cB)) << 2;                // min(D(i,0))
-                Lp[r] = V::pk(min(bigA, c + sc.o), min(bigB, cB + sc.o)) << 2;  // level-1 candidate
-            }
-            unsigned rh_prev = 0;                  // h(ib, 0): diagonal input of my first row at j = 1
-            if (ib != 0)
-                rh_prev = V::pk(min(bigA, (unsigned)colv[0]), min(bigB, (unsigned)(PT ? colvB[0] : colv[0]))) << 2;
-
-            unsigned hb = 0, ub = 0, bv = 0;
-            int rowj = sc.o;                       // TABLE: running row-0 value (pass 0, lane g == 0)
-            int rowjB = sc.o;                      // PT: the same for pair B
-            int2 nxt = make_int2(0, 0);
-            if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
-            uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::WPP * 32) + lane;
-
-            for (int tb = 0; tb < nTB; ++tb) {
-                unsigned stg[L::S * L::NW];
-#pragma unroll
-                for (int u = 0; u < L::S; ++u) {
-                    const int t = tb * L::S + u;
-                    const int j = t - g + 1;
-                    unsigned rh = __shfl_up_sync(FULL, hb, 1);
-                    unsigned ru = __shfl_up_sync(FULL, ub, 1);
-                    unsigned bin = __shfl_up_sync(FULL, bv, 1);
-                    const unsigned bnew = (unsigned)myb[t];
-                    if (g == 0) {
-                        bin = bnew;
-                        if (p == 0) {
-                            unsigned rj, rjB;      // row-0 value at column t+1 (level 1)
-                            if (PT) {
-                                // the padding letter A costs nothing: past the end of a pair the
-                                // running value stays put (those columns are never read back)
-                                const unsigned la = bnew & 0xFFFFu, lb = bnew >> 16;
-                                if (la < (unsigned)sc.A) rowj += sc.gh_raw[la];
-                                if (lb < (unsigned)sc.A) rowjB += sc.gh_raw[lb];
-                                rj = (unsigned)rowj;
-                                rjB = (unsigned)rowjB;
-                            } else if (SIMPLE) {
-                                rj = rjB = (unsigned)(sc.o + sc.gh * (t + 1));
-                            } else {
-                                rowj += sc.gh_raw[bnew];
-                                rj = rjB = (unsigned)rowj;
-                            }
-                            rh = V::pk(min(bigA, rj), min(bigB, rjB)) << 2;
-                            ru = V::pk(min(bigA, rj + sc.o), min(bigB, rjB + sc.o)) << 2;
+                    int inclA = mineA, inclB = mineB;  // inclusive scans over the lanes of my group
+    #pragma unroll
+                    for (int d = 1; d < G; d <<= 1) {
+                        const int va = __shfl_up_sync(FULL, inclA, d), vb = __shfl_up_sync(FULL, inclB, d);
+                        if (g >= d) { inclA += va; inclB += vb; }
+                    }
+                    const int totA = __shfl_sync(FULL, inclA, grp * G + G - 1);
+                    const int totB = __shfl_sync(FULL, inclB, grp * G + G - 1);
+                    colv[0] = colbase + inclA - mineA;
+                    colvB[0] = colbaseB + inclB - mineB;
+    #pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        colv[r + 1] = colv[r] + gvrA[r];
+                        colvB[r + 1] = colvB[r] + gvrB[r];
+                    }
+                    colbase += totA;
+                    colbaseB += totB;
+                } else if (SIMPLE) {
+    #pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const int row = ib + r;
+                        const unsigned la = row < mA ? ld_letter(s1, a1 + row, sc.seq_bits) : (unsigned)PAD_A;
+                        if (PACKED) {
+                            const unsigned lb = row < mB ? ld_letter(s1, b1 + row, sc.seq_bits) : (unsigned)PAD_A;
+                            aw[r] = la | (lb << 16);
                         } else {
-                            rh = (unsigned)nxt.x;
-                            ru = (unsigned)nxt.y;
-                            nxt = __ldcg(my_bnd + min(t + 2, td.N));
+                            aw[r] = la;
                         }
+                        gvT[r] = gvTc;
                     }
-                    bv = bin;
-#pragma unroll
-                    for (int x = 0; x < L::NW; ++x) stg[u * L::NW + x] = 0u;
-                    if (lane_ok && j >= 1 && j <= td.N) {
-                        unsigned diag = rh_prev, up = ru;
-                        rh_prev = rh;
-                        unsigned ghT, rowA = 0, rowB = 0;
-                        if (PT) {
-                            const unsigned la = bv & 0xFFFFu, lb = bv >> 16;
-                            ghT = (unsigned)s_gh[la] | ((unsigned)s_gh[lb] << 16);
-                            rowA = pt_lo + la * (unsigned)(4 * AP);
-                            rowB = pt_hi + lb * (unsigned)(4 * AP);
-                        } else {
-                            ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
-                        }
-                        unsigned acc[L::NW];
-#pragma unroll
-                        for (int x = 0; x < L::NW; ++x) acc[x] = 0u;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            unsigned d0;
-                            if (PT) {
-                                // two table loads (address adds as IMADs) and one three-input add
-                                unsigned sa, sb2;
-                                asm("ld.shared.u32 %0, [%1];" : "=r"(sa) : "r"(aw[r] * K1 + rowA));
-                                asm("ld.shared.u32 %0, [%1];" : "=r"(sb2) : "r"(awB[r] * K1 + rowB));
-                                d0 = diag + sa + sb2;
-                            } else if (PACKED) {
-                                d0 = __vminu2(aw[r] ^ bv, 0x00010001u) * mm4 + diag;
-                            } else if (SIMPLE) {
-                                d0 = diag + (aw[r] != bv ? mm4 : 0u);
-                            } else {
-                                d0 = diag + (unsigned)s_sub[aw[r] + bv];
-                            }
-                            const unsigned d1 = Lp[r] * K1 + ghT;            // IMAD
-                            const unsigned d2 = up * K1 + gvT[r];            // IMAD
-                            const unsigned hq = V::min3(d0, d1, d2);
-                            const unsigned Lq = V::addmin(hq, o4, d1);
-                            const unsigned Uq = V::addmin(hq, o4, d2);
-                            const int w = r / L::RPW;
-                            // plane 0: c0.  A code word takes at most RPW inserts, so a half
-                            // never shifts into its neighbour.
-                            const unsigned th = hq & V::TAGM;                 // LOP3
-                            acc[w] = acc[w] * K4 + th;                       // IMAD
-                            // plane 1: bit 0 (of each half) from Lq, bit 1 from Uq
-                            constexpr unsigned B0 = V::TAGM & 0x55555555u;
-                            const unsigned lu = ((Lq & B0) | (Uq & ~B0)) & V::TAGM;   // 2 x LOP3
-                            acc[L::WPP + w] = acc[L::WPP + w] * K4 + lu;     // IMAD
-                            diag = hl[r];
-                            hl[r] = th * KM1 + hq;                           // hq - tag, IMAD
-                            Lp[r] = Lq & ~V::TAGM;
-                            up = Uq & ~V::TAGM;
-                        }
-                        hb = hl[R - 1];
-                        ub = up;
-#pragma unroll
-                        for (int x = 0; x < L::NW; ++x) stg[u * L::NW + x] = acc[x];
-                        if (G * R < td.M && g == G - 1 && p + 1 < npass)
-                            __stcg(my_bnd + j, make_int2((int)hb, (int)ub));
-                        if (j == nA && p == pmA && g == gmA) {
-#pragma unroll
-                            for (int r = 0; r < R; ++r)
-                                if (r == rmA) costA = hl[r];
-                        }
-                        if (PACKED && j == nB && p == pmB && g == gmB) {
-#pragma unroll
-                            for (int r = 0; r < R; ++r)
-                                if (r == rmB) costB = hl[r];
-                        }
+    #pragma unroll
+                    for (int r = 0; r <= RT; ++r) colv[r] = sc.o + sc.gv * (ib + r);
+                } else {
+                    int mine = 0, gvr[RT];
+    #pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const int row = ib + r;
+                        const int a = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
+                        aw[r] = (unsigned)(a * sc.A);
+                        gvT[r] = (unsigned)sc.gv4t[a];
+                        gvr[r] = sc.gv_raw[a];
+                        mine += gvr[r];
                     }
+                    int incl = mine;                   // inclusive scan over the lanes of my group
+    #pragma unroll
+                    for (int d = 1; d < G; d <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incl, d);
+                        if (g >= d) incl += v;
+                    }
+                    const int band_total = __shfl_sync(FULL, incl, grp * G + G - 1);
+                    colv[0] = colbase + incl - mine;
+    #pragma unroll
+                    for (int r = 0; r < RT; ++r) colv[r + 1] = colv[r] + gvr[r];
+                    colbase += band_total;
                 }
-                // one 128-bit store per row-word: both planes of the two staged steps; lane-adjacent
-#pragma unroll
-                for (int w = 0; w < L::WPP; ++w)
-                    cbase[(size_t)(tb * L::WPP + w) * 32] =
-                        make_uint4(stg[w], stg[L::NW + w], stg[L::WPP + w], stg[L::NW + L::WPP + w]);
-            }
-            __syncwarp();
+    #pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const unsigned c = (unsigned)colv[r + 1];
+                    const unsigned cB = PT ? (unsigned)colvB[r + 1] : c;
+                    hl[r] = V::pk(min(bigA, c), min(bigB, cB)) << 2;                // min(D(i,0))
+                    Lp[r] = V::pk(min(bigA, c + sc.o), min(bigB, cB + sc.o)) << 2;  // level-1 candidate
+                }
+                unsigned rh_prev = 0;                  // h(ib, 0): diagonal input of my first row at j = 1
+                if (ib != 0)
+                    rh_prev = V::pk(min(bigA, (unsigned)colv[0]), min(bigB, (unsigned)(PT ? colvB[0] : colv[0]))) << 2;
+
+                unsigned hb = 0, ub = 0, bv = 0;
+                int rowj = sc.o;                       // TABLE: running row-0 value (pass 0, lane g == 0)
+                int rowjB = sc.o;                      // PT: the same for pair B
+                int2 nxt = make_int2(0, 0);
+                if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
+                uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::WPP * 32) + lane;
+
+                for (int tb = 0; tb < nTB; ++tb) {
+                    unsigned stg[L::S * NWT];
+    #pragma unroll
+                    for (int u = 0; u < L::S; ++u) {
+                        const int t = tb * L::S + u;
+                        const int j = t - g + 1;
+                        unsigned rh = __shfl_up_sync(FULL, hb, 1);
+                        unsigned ru = __shfl_up_sync(FULL, ub, 1);
+                        unsigned bin = __shfl_up_sync(FULL, bv, 1);
+                        const unsigned bnew = (unsigned)myb[t];
+                        if (g == 0) {
+                            bin = bnew;
+                            if (p == 0) {
+                                unsigned rj, rjB;      // row-0 value at column t+1 (level 1)
+                                if (PT) {
+                                    // the padding letter A costs nothing: past the end of a pair the
+                                    // running value stays put (those columns are never read back)
+                                    const unsigned la = bnew & 0xFFFFu, lb = bnew >> 16;
+                                    if (la < (unsigned)sc.A) rowj += sc.gh_raw[la];
+                                    if (lb < (unsigned)sc.A) rowjB += sc.gh_raw[lb];
+                                    rj = (unsigned)rowj;
+                                    rjB = (unsigned)rowjB;
+                                } else if (SIMPLE) {
+                                    rj = rjB = (unsigned)(sc.o + sc.gh * (t + 1));
+                                } else {
+                                    rowj += sc.gh_raw[bnew];
+                                    rj = rjB = (unsigned)rowj;
+                                }
+                                rh = V::pk(min(bigA, rj), min(bigB, rjB)) << 2;
+                                ru = V::pk(min(bigA, rj + sc.o), min(bigB, rjB + sc.o)) << 2;
+                            } else {
+                                rh = (unsigned)nxt.x;
+                                ru = (unsigned)nxt.y;
+                                nxt = __ldcg(my_bnd + min(t + 2, td.N));
+                            }
+                        }
+                        bv = bin;
+    #pragma unroll
+                        for (int x = 0; x < NWT; ++x) stg[u * NWT + x] = 0u;
+                        if (lane_ok && j >= 1 && j <= td.N) {
+                            unsigned diag = rh_prev, up = ru;
+                            rh_prev = rh;
+                            unsigned ghT, rowA = 0, rowB = 0;
+                            if (PT) {
+                                const unsigned la = bv & 0xFFFFu, lb = bv >> 16;
+                                ghT = (unsigned)s_gh[la] | ((unsigned)s_gh[lb] << 16);
+                                rowA = pt_lo + la * (unsigned)(4 * AP);
+                                rowB = pt_hi + lb * (unsigned)(4 * AP);
+                            } else {
+                                ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
+                            }
+                            unsigned acc[NWT];
+    #pragma unroll
+                            for (int x = 0; x < NWT; ++x) acc[x] = 0u;
+    #pragma unroll
+                            for (int r = 0; r < RT; ++r) {
+                                unsigned d0;
+                                if (PT) {
+                                    // two table loads (address adds as IMADs) and one three-input add
+                                    unsigned sa, sb2;
+                                    asm("ld.shared.u32 %0, [%1];" : "=r"(sa) : "r"(aw[r] * K1 + rowA));
+                                    asm("ld.shared.u32 %0, [%1];" : "=r"(sb2) : "r"(awB[r] * K1 + rowB));
+                                    d0 = diag + sa + sb2;
+                                } else if (PACKED) {
+                                    d0 = __vminu2(aw[r] ^ bv, 0x00010001u) * mm4 + diag;
+                                } else if (SIMPLE) {
+                                    d0 = diag + (aw[r] != bv ? mm4 : 0u);
+                                } else {
+                                    d0 = diag + (unsigned)s_sub[aw[r] + bv];
+                                }
+                                const unsigned d1 = Lp[r] * K1 + ghT;            // IMAD
+                                const unsigned d2 = up * K1 + gvT[r];            // IMAD
+                                const unsigned hq = V::min3(d0, d1, d2);
+                                const unsigned Lq = V::addmin(hq, o4, d1);
+                                const unsigned Uq = V::addmin(hq, o4, d2);
+                                const int w = r / L::RPW;
+                                // plane 0: c0.  A code word takes at most RPW inserts, so a half
+                                // never shifts into its neighbour.
+                                const unsigned th = hq & V::TAGM;                 // LOP3
+                                acc[w] = acc[w] * K4 + th;                       // IMAD
+                                // plane 1: bit 0 (of each half) from Lq, bit 1 from Uq
+                                constexpr unsigned B0 = V::TAGM & 0x55555555u;
+                                const unsigned lu = ((Lq & B0) | (Uq & ~B0)) & V::TAGM;   // 2 x LOP3
+                                acc[WPPT + w] = acc[WPPT + w] * K4 + lu;     // IMAD
+                                diag = hl[r];
+                                hl[r] = th * KM1 + hq;                           // hq - tag, IMAD
+                                Lp[r] = Lq & ~V::TAGM;
+                                up = Uq & ~V::TAGM;
+                            }
+                            hb = hl[RT - 1];
+                            ub = up;
+    #pragma unroll
+                            for (int x = 0; x < NWT; ++x) stg[u * NWT + x] = acc[x];
+                            if (g == G - 1 && p + 1 < npass)
+                                __stcg(my_bnd + j, make_int2((int)hb, (int)ub));
+                            if (j == nA && p == pmA && g == gmA) {
+    #pragma unroll
+                                for (int r = 0; r < RT; ++r)
+                                    if (r == rmA) costA = hl[r];
+                            }
+                            if (PACKED && j == nB && p == pmB && g == gmB) {
+    #pragma unroll
+                                for (int r = 0; r < RT; ++r)
+                                    if (r == rmB) costB = hl[r];
+                            }
+                        }
+                    }
+                    // one 128-bit store per row-word: both planes of the two staged steps; lane-adjacent
+    #pragma unroll
+                    for (int w = 0; w < WPPT; ++w)
+                        cbase[(size_t)(tb * WPPT + w) * 32] =
+                            make_uint4(stg[w], stg[NWT + w], stg[WPPT + w], stg[NWT + WPPT + w]);
+                }
+                __syncwarp();
+                    };
+            // The last pass of a tile covers only the rows that are left: it runs with the
+            // smallest of R/4, R/2, 3R/4, R rows per lane that holds them (tail_rows), so a
+            // 600-row pair costs 512 + 96 rows of work instead of 1024.
+            const int rt = p == npass - 1 ? rt_last : R;
+            if (!TailRows<R, G>::ON || rt == R) run_pass(std::integral_constant<int, R>{});
+            else if (rt == TailRows<R, G>::Q3) run_pass(std::integral_constant<int, TailRows<R, G>::Q3>{});
+            else if (rt == TailRows<R, G>::Q2) run_pass(std::integral_constant<int, TailRows<R, G>::Q2>{});
+            else run_pass(std::integral_constant<int, TailRows<R, G>::Q1>{});
         }
         if (haveA && g == gmA) out_cost[pA] = (int)((PACKED ? (costA & 0xFFFFu) : costA) >> 2);
         if (haveB && g == gmB) out_cost[pB] = (int)((costB >> 16) >> 2);

@@ -60,18 +60,32 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         word |= (uint32_t)op << (2 * (nops & 15));
         if ((++nops & 15) == 0) { ow[(nops >> 4) - 1] = word; word = 0; }
     };
+    // the tile's last pass may hold fewer rows per lane (tail_rows, shared with the fill kernel)
+    const int last_pass = (td.M - 1) / L::BAND;
+    const int rt_last = tail_rows<R, G>(td.M);
+    const int wpp_last = (rt_last + L::RPW - 1) / L::RPW;
+    const float inv_rt_last = 1.0f / (float)rt_last;
     auto code_at = [&](int i, int j, int level) -> int {
         const int row = i - 1;
         const int pass = row / L::BAND;
         const int rem = row - pass * L::BAND;
-        const int g = rem / R;
-        const int r = rem - g * R;
+        int g, rp, wpp;
+        if (TailRows<R, G>::ON && pass == last_pass) {
+            rp = rt_last;
+            wpp = wpp_last;
+            g = __float2int_rz(((float)rem + 0.5f) * inv_rt_last);    // rem / rp, exact for rem < 2^15
+        } else {
+            rp = R;
+            wpp = L::WPP;
+            g = rem / R;
+        }
+        const int r = rem - g * rp;
         const int t = (j - 1) + g;
         const int w = r / L::RPW;
-        const int rows_in_word = min(L::RPW, R - w * L::RPW);
+        const int rows_in_word = min(L::RPW, rp - w * L::RPW);
         const int sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
         // 128-bit word (pass, 2-step block, row-word, lane) = {p0 s0, p0 s1, p1 s0, p1 s1}
-        const size_t q = ((((size_t)pass * nB2 + (t >> 1)) * L::WPP + w) * 32 + lane0 + g) * 4 + (t & 1);
+        const size_t q = ((((size_t)pass * nB2 * L::WPP + (size_t)(t >> 1) * wpp) + w) * 32 + lane0 + g) * 4 + (t & 1);
         auto plane = [&](int pl) -> unsigned { return (cw[q + 2 * pl] >> sh) & 3u; };
         if (level != 0) {
             const unsigned lu = plane(1);
