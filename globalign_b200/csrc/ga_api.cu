@@ -509,6 +509,26 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
     // tiles: consecutive groups of PPT positions of the pair order
     const int64_t n_tiles = (n_pairs + L.PPT - 1) / L.PPT;
+    // launch geometry (before the chunks are cut: their number depends on how many warps are resident)
+    const int warps = 4;
+    ctx->sb_stride = ((maxN + L.G - 1 + L.S + 1 + 16) + 15) & ~15;
+    ctx->bnd_stride = maxN + 8;
+    const size_t elt = L.packed ? 4 : 1;
+    size_t table = 0;
+    if (!cfg->simple) {
+        const size_t A = (size_t)ctx->sc.A;
+        table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
+                         : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
+    }
+    ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
+    if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
+    CK(cudaFuncSetAttribute(cfg->fill_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg->fill_fn, 128, ctx->smem));
+    if (per_sm < 1) return fail(ctx, GA_E_ARG, "fill kernel does not fit on an SM");
+    const long long want_blocks = (n_tiles + warps - 1) / warps;
+    if (const char *e = getenv("GA_FILL_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // experiments
+    ctx->grid = (int)std::min<long long>(want_blocks, (long long)per_sm * ctx->sm_count);
     const bool uniform = (minM == maxM && minN == maxN);
     ctx->chunks.clear();
     ctx->perm.clear();
@@ -519,15 +539,30 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     const bool serial = (flags & GA_F_SERIAL) != 0;
     const long long hard_u4 = std::max<long long>((serial ? ctx->scratch_limit : ctx->scratch_limit / 2) / 16, 1);
     long long total_u4 = 0, uni_u4 = 0, max_chunk_u4 = 0;
-    auto soft_limit = [&](long long total) {
-        if (serial) return hard_u4;
-        const long long min_u4 = ((long long)1 << 30) / 16;            // do not cut below 1 GiB of codes
-        // measured on 1M x (150 x 150): device-resident runs are fastest with 2-4 chunks (fewer
-        // fill tails), the host-buffer path with ~8 (finer overlap of copies and kernels)
-        int want_chunks = ctx->plan_for_io ? 8 : 4;
-        if (const char *e = getenv("GA_CHUNKS")) want_chunks = std::max(1, atoi(e));
-        return std::min(hard_u4, std::max(min_u4, (total + want_chunks - 1) / want_chunks));
-    };
+    // Where to cut, as cumulative fractions of the batch.  Every chunk boundary costs a fill tail
+    // (warps idle until the slowest tile of the chunk is done), and the walk of a chunk only
+    // overlaps the next fill in the gaps the persistent fill blocks leave, so chunks must hold
+    // many tiles per resident warp (>= ~12; measured on cfg2 and cfg3, tools/probe_cfg3.py):
+    // device-resident runs get 1-4 equal chunks.  The host-buffer call also hides its copies
+    // behind the kernels: a small first chunk (its upload is all that precedes the first fill),
+    // a small last chunk (its download is all that follows the last walk), the rest as above.
+    std::vector<double> cuts;
+    {
+        const double tiles_per_warp = (double)n_tiles / std::max(1, ctx->grid * warps);
+        // a boundary costs more when tiles and walks are long (cfg3: ~0.4 ms, cfg2: ~0.05 ms)
+        const double depth = (ctx->plan_for_io && maxM + maxN <= 512) ? 8.0 : 12.0;
+        int mid = (int)std::max(1.0, std::min(ctx->plan_for_io ? 6.0 : 4.0, tiles_per_warp / depth + 0.5));
+        if (const char *e = getenv("GA_CHUNKS")) mid = std::max(1, atoi(e));
+        if (serial) {
+            cuts = {1.0};
+        } else if (ctx->plan_for_io && tiles_per_warp >= 16.0 && !getenv("GA_CHUNKS")) {
+            cuts.push_back(0.125);
+            for (int k = 1; k <= mid; ++k) cuts.push_back(0.125 + 0.75 * k / mid);
+            cuts.push_back(1.0);
+        } else {
+            for (int k = 1; k <= mid; ++k) cuts.push_back((double)k / mid);
+        }
+    }
     if (uniform) {
         // every tile is the same: no descriptor array, the kernels compute them (UniformTiles)
         uni_u4 = tile_code_u4(maxM, maxN, L.G, L.BAND, L.NW);
@@ -535,15 +570,21 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         ctx->tiles.clear();
         if (uni_u4 > hard_u4)
             return fail(ctx, GA_E_NOMEM, "one tile needs %lld bytes of direction codes, above the scratch limit", uni_u4 * 16);
-        const long long limit_u4 = soft_limit(total_u4);
         ht.lap("plan: tiles");
-        const int64_t per_chunk = std::max<int64_t>(1, limit_u4 / uni_u4);       // tiles per chunk
-        for (int64_t t = 0; t < n_tiles; t += per_chunk) {
-            const int64_t thi = std::min(n_tiles, t + per_chunk);
-            Chunk c{(int)t, (int)thi, (int)(t * L.PPT), (int)std::min<int64_t>(n_pairs, thi * L.PPT),
-                    (thi - t) * uni_u4};
-            ctx->chunks.push_back(c);
-            max_chunk_u4 = std::max(max_chunk_u4, c.code_u4);
+        const int64_t max_tiles = std::max<int64_t>(1, hard_u4 / uni_u4);        // tiles per chunk the scratch allows
+        int64_t t = 0;
+        for (size_t k = 0; k < cuts.size() && t < n_tiles; ++k) {
+            const int64_t stop = k + 1 == cuts.size() ? n_tiles
+                                 : std::min<int64_t>(n_tiles, std::max<int64_t>(t + 1, (int64_t)(cuts[k] * (double)n_tiles + 0.5)));
+            const int64_t parts = (stop - t + max_tiles - 1) / max_tiles;        // split further if above the limit
+            for (int64_t q = 0; q < parts; ++q) {
+                const int64_t thi = q + 1 == parts ? stop : t + (stop - t) / (parts - q);
+                Chunk c{(int)t, (int)thi, (int)(t * L.PPT), (int)std::min<int64_t>(n_pairs, thi * L.PPT),
+                        (thi - t) * uni_u4};
+                ctx->chunks.push_back(c);
+                max_chunk_u4 = std::max(max_chunk_u4, c.code_u4);
+                t = thi;
+            }
         }
     } else {
         // Ragged batch.  (1) Cut the batch, in the caller's order, into chunks of whole tiles by
@@ -572,22 +613,26 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         ctx->tiles.resize((size_t)n_tiles);
         if (sort_pairs) ctx->perm.resize((size_t)n_pairs);
         TileDesc *tiles = ctx->tiles.data();
-        double target = (double)soft_limit((long long)(est_total * 1.02) + 1);
+        double target = (double)hard_u4 * 0.98;          // estimated codes a chunk may hold
         for (int attempt = 0;; ++attempt) {
             ctx->chunks.clear();
             {   // (1)
                 Chunk cur{0, 0, 0, 0, 0};
-                double acc = 0;
+                double acc = 0, done = 0;
+                size_t k = 0;
                 for (int64_t t = 0; t < n_tiles; ++t) {
                     double e = 0;
                     const int64_t lo = t * L.PPT, hi = std::min<int64_t>(n_pairs, lo + L.PPT);
                     for (int64_t p = lo; p < hi; ++p) e += est[(size_t)p];
-                    if (acc + e > target && acc > 0) {
+                    const bool at_cut = k + 1 < cuts.size() && done + acc >= cuts[k] * est_total;
+                    if ((at_cut || acc + e > target) && acc > 0) {
                         cur.tile_hi = (int)t;
                         cur.pair_hi = (int)lo;
                         ctx->chunks.push_back(cur);
                         cur = Chunk{(int)t, 0, (int)lo, 0, 0};
+                        done += acc;
                         acc = 0;
+                        while (k + 1 < cuts.size() && done >= cuts[k] * est_total) ++k;
                     }
                     acc += e;
                 }
@@ -599,31 +644,45 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
             const int64_t n_chunks = (int64_t)ctx->chunks.size();
             std::atomic<int64_t> next{0};
             auto work = [&]() {
-                std::vector<uint64_t> keys;
+                std::vector<int> tmp;
+                std::vector<size_t> hist;
                 for (;;) {
                     const int64_t c = next.fetch_add(1);
                     if (c >= n_chunks) break;
                     Chunk &ch = ctx->chunks[(size_t)c];
                     if (sort_pairs) {
-                        keys.resize((size_t)(ch.pair_hi - ch.pair_lo));
-                        for (int64_t p = ch.pair_lo; p < ch.pair_hi; ++p) {
-                            const uint64_t m = (uint64_t)(s1_off[p + 1] - s1_off[p]), n = (uint64_t)(s2_off[p + 1] - s2_off[p]);
-                            // m < 2^25, n < 2^16, position in the chunk < 2^23 or ties keep any order
-                            keys[(size_t)(p - ch.pair_lo)] = (m << 39) | (n << 23) | (uint64_t)((p - ch.pair_lo) & 0x7fffff);
-                        }
-                        std::sort(keys.begin(), keys.end(), std::greater<uint64_t>());
-                        if (keys.size() <= 0x800000) {
-                            for (size_t k = 0; k < keys.size(); ++k)
-                                ctx->perm[(size_t)ch.pair_lo + k] = ch.pair_lo + (int)(keys[k] & 0x7fffff);
-                        } else {   // positions do not fit the key: sort an index array instead
-                            std::vector<int> idx(keys.size());
-                            for (size_t k = 0; k < idx.size(); ++k) idx[k] = ch.pair_lo + (int)k;
-                            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+                        // order by (m, n) descending: two stable counting passes (n, then m), O(pairs)
+                        const size_t cnt = (size_t)(ch.pair_hi - ch.pair_lo);
+                        int *out = ctx->perm.data() + ch.pair_lo;
+                        if (maxM <= (1 << 20)) {
+                            tmp.resize(cnt);
+                            hist.assign((size_t)std::max(maxM, maxN) + 2, 0);
+                            for (size_t k = 0; k < cnt; ++k) {
+                                const int64_t p = ch.pair_lo + (int64_t)k;
+                                ++hist[(size_t)(maxN - (s2_off[p + 1] - s2_off[p])) + 1];
+                            }
+                            for (size_t v = 1; v < hist.size(); ++v) hist[v] += hist[v - 1];
+                            for (size_t k = 0; k < cnt; ++k) {
+                                const int64_t p = ch.pair_lo + (int64_t)k;
+                                tmp[hist[(size_t)(maxN - (s2_off[p + 1] - s2_off[p]))]++] = (int)p;
+                            }
+                            hist.assign(hist.size(), 0);
+                            for (size_t k = 0; k < cnt; ++k) {
+                                const int64_t p = tmp[k];
+                                ++hist[(size_t)(maxM - (s1_off[p + 1] - s1_off[p])) + 1];
+                            }
+                            for (size_t v = 1; v < hist.size(); ++v) hist[v] += hist[v - 1];
+                            for (size_t k = 0; k < cnt; ++k) {
+                                const int64_t p = tmp[k];
+                                out[hist[(size_t)(maxM - (s1_off[p + 1] - s1_off[p]))]++] = (int)p;
+                            }
+                        } else {
+                            for (size_t k = 0; k < cnt; ++k) out[k] = ch.pair_lo + (int)k;
+                            std::stable_sort(out, out + cnt, [&](int x, int y) {
                                 const int64_t mx = s1_off[x + 1] - s1_off[x], my = s1_off[y + 1] - s1_off[y];
                                 if (mx != my) return mx > my;
                                 return s2_off[x + 1] - s2_off[x] > s2_off[y + 1] - s2_off[y];
                             });
-                            std::copy(idx.begin(), idx.end(), ctx->perm.begin() + ch.pair_lo);
                         }
                     }
                     long long u4sum = 0;
@@ -664,31 +723,12 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
             for (const Chunk &ch : ctx->chunks) single = single || (ch.code_u4 > hard_u4 && ch.tile_hi - ch.tile_lo == 1);
             if (single || attempt >= 12)
                 return fail(ctx, GA_E_NOMEM, "one tile needs more direction-code scratch than the scratch limit allows");
-            target = std::min(target, (double)hard_u4) * 0.7;
+            target *= 0.7;
         }
         ht.lap("plan: tiles");
     }
 
     ht.lap("plan: chunks");
-    // launch geometry
-    const int warps = 4;
-    ctx->sb_stride = ((maxN + L.G - 1 + L.S + 1 + 16) + 15) & ~15;
-    ctx->bnd_stride = maxN + 8;
-    const size_t elt = L.packed ? 4 : 1;
-    size_t table = 0;
-    if (!cfg->simple) {
-        const size_t A = (size_t)ctx->sc.A;
-        table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
-                         : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
-    }
-    ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
-    if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
-    CK(cudaFuncSetAttribute(cfg->fill_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg->fill_fn, 128, ctx->smem));
-    if (per_sm < 1) return fail(ctx, GA_E_ARG, "fill kernel does not fit on an SM");
-    const long long want_blocks = (n_tiles + warps - 1) / warps;
-    ctx->grid = (int)std::min<long long>(want_blocks, (long long)per_sm * ctx->sm_count);
     int rc;
     if (!uniform && (rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
     if (!ctx->perm.empty() && (rc = ensure(ctx, ctx->d_perm, (size_t)n_pairs * sizeof(int)))) return rc;
