@@ -50,8 +50,9 @@ class BatchAlignment:
         self.seqs_1, self.seqs_2 = seqs_1, seqs_2
         self.cost, self.ops, self.ops_off, self.ops_len, self.status = cost, ops, ops_off, ops_len, status
         self._scheme = scheme
-        m = np.fromiter((len(s) for s in seqs_1), dtype=np.int64, count=len(seqs_1))
-        n = np.fromiter((len(s) for s in seqs_2), dtype=np.int64, count=len(seqs_2))
+        # (ASCII upper-casing keeps lengths: measure the caller's strings, not the lazy view)
+        m = np.fromiter(map(len, getattr(seqs_1, "_seqs", seqs_1)), dtype=np.int64, count=len(seqs_1))
+        n = np.fromiter(map(len, getattr(seqs_2, "_seqs", seqs_2)), dtype=np.int64, count=len(seqs_2))
         self.score = final_cost_to_score(cost.astype(np.int64), m, n, scheme.max_score)
 
     def __len__(self):
@@ -131,6 +132,101 @@ class Scheme:
         return DenseScheme(cm, self.gap_open_cost)
 
 
+_GAP_MSG = ("The current implementation does not allow for '-' characters in the sequences "
+            "because they are used internally for gaps.  Please replace this character in "
+            "your sequences.")
+
+
+def _lower_batch(seqs_1, seqs_2, limit, scheme):
+    """Pair by pair: the checks of validate_and_transform_args (start.py:209-232), upper-casing
+    and encoding.  Handles any str (non-ASCII letters, case mappings that change length)."""
+    up1, up2 = [], []
+    for s1, s2 in zip(seqs_1, seqs_2):
+        start.check_seq_lengths(s1, s2, limit)
+        if GAP in s1 or GAP in s2:
+            raise RuntimeError(_GAP_MSG)
+        up1.append(s1.upper())
+        up2.append(s2.upper())
+    alphabet = sorted(set().union(*map(set, up1), *map(set, up2)))
+    dense = scheme.dense_for(alphabet)
+    enc1 = [dense.encode(s) for s in up1]
+    enc2 = [dense.encode(s) for s in up2]
+    off1 = np.zeros(len(up1) + 1, dtype=np.int64)
+    off2 = np.zeros(len(up2) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in enc1], out=off1[1:])
+    np.cumsum([len(x) for x in enc2], out=off2[1:])
+    return up1, up2, dense, np.concatenate(enc1), off1, np.concatenate(enc2), off2
+
+
+def _lower_ascii_batch(seqs_1, seqs_2, limit, scheme):
+    """The same for all-ASCII input without a Python-level loop over the pairs: the sequences are
+    joined, upper-cased and mapped through one 256-entry table (large read sets spend their time
+    here, not on the GPU).  -> None when a sequence is not ASCII (the caller then goes pair by
+    pair); raises exactly what the per-pair path raises, for the first offending pair."""
+    n = len(seqs_1)
+    try:
+        j1, j2 = "".join(seqs_1), "".join(seqs_2)
+    except TypeError:
+        return None
+    if not (j1.isascii() and j2.isascii()):
+        return None
+    m_len = np.fromiter(map(len, seqs_1), dtype=np.int64, count=n)
+    n_len = np.fromiter(map(len, seqs_2), dtype=np.int64, count=n)
+    bad = ~(m_len * n_len < limit) | (m_len * n_len == 0)
+    first_bad = int(np.argmax(bad)) if bad.any() else n
+    if GAP in j1 or GAP in j2:
+        for k in range(first_bad):           # only when there is a '-' somewhere
+            if GAP in seqs_1[k] or GAP in seqs_2[k]:
+                raise RuntimeError(_GAP_MSG)
+    if first_bad < n:
+        start.check_seq_lengths(seqs_1[first_bad], seqs_2[first_bad], limit)
+    e1, e2 = j1.encode("ascii"), j2.encode("ascii")
+    # the letters that occur (upper-cased), found with bytes.translate at C speed: delete what is
+    # known, look at the start of what is left, repeat
+    known = set()
+    for e in (e1, e2):
+        rest = e
+        while rest:
+            known |= set(rest[:4096].upper())
+            both = bytes(known) + bytes(known).lower()
+            rest = rest.translate(None, both)
+    alphabet = [chr(c) for c in sorted(known)]                      # sorted by code point, like sorted(set)
+    dense = scheme.dense_for(alphabet)
+    table = bytearray(256)
+    for ch, k in dense.index.items():
+        if ord(ch) < 128:
+            table[ord(ch)] = k
+            table[ord(ch.lower())] = k                               # case folding and encoding in one pass
+    table = bytes(table)
+    cat1 = np.frombuffer(e1.translate(table), dtype=np.uint8)
+    cat2 = np.frombuffer(e2.translate(table), dtype=np.uint8)
+    off1 = np.zeros(n + 1, dtype=np.int64)
+    off2 = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(m_len, out=off1[1:])
+    np.cumsum(n_len, out=off2[1:])
+    up1 = _LazyUpper(seqs_1)
+    up2 = _LazyUpper(seqs_2)
+    return up1, up2, dense, cat1, off1, cat2, off2
+
+
+class _LazyUpper:
+    """Sequence view that upper-cases on access (BatchAlignment renders pairs lazily)."""
+
+    def __init__(self, seqs):
+        self._seqs = seqs
+
+    def __len__(self):
+        return len(self._seqs)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [s.upper() for s in self._seqs[k]]
+        return self._seqs[k].upper()
+
+    def __iter__(self):
+        return (s.upper() for s in self._seqs)
+
+
 def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=None,
                            scoring_mat_name=None, scoring_mat_path=None, match_score=None,
                            mismatch_score=None, mismatch_cost=None, gap_open_score=None,
@@ -145,30 +241,23 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=
     if len(seqs_1) != len(seqs_2) or len(seqs_1) == 0:
         raise RuntimeError("seqs_1 and seqs_2 must be non-empty and of equal length")
     limit = start.MAX_SEQ_LEN_PRODUCT if max_seq_len_prod is None else max_seq_len_prod
-    up1, up2 = [], []
-    for s1, s2 in zip(seqs_1, seqs_2):
-        start.check_seq_lengths(s1, s2, limit)
-        if GAP in s1 or GAP in s2:
-            raise RuntimeError(
-                "The current implementation does not allow for '-' characters in the sequences "
-                "because they are used internally for gaps.  Please replace this character in "
-                "your sequences.")
-        up1.append(s1.upper())
-        up2.append(s2.upper())
     scheme = Scheme(scoring_mat_name, scoring_mat_path, match_score, mismatch_score, mismatch_cost,
                     gap_open_score, gap_open_cost, gap_extension_score, gap_extension_cost)
-    alphabet = sorted(set().union(*map(set, up1), *map(set, up2)))
-    dense = scheme.dense_for(alphabet)
-    enc1 = [dense.encode(s) for s in up1]
-    enc2 = [dense.encode(s) for s in up2]
-    off1 = np.zeros(len(up1) + 1, dtype=np.int64)
-    off2 = np.zeros(len(up2) + 1, dtype=np.int64)
-    np.cumsum([len(x) for x in enc1], out=off1[1:])
-    np.cumsum([len(x) for x in enc2], out=off2[1:])
+    lowered = _lower_ascii_batch(seqs_1, seqs_2, limit, scheme)
+    if lowered is None:
+        lowered = _lower_batch(seqs_1, seqs_2, limit, scheme)
+    up1, up2, dense, cat1, off1, cat2, off2 = lowered
     ctx = _native.default_context(device)
     ctx.set_scheme(dense)
-    cost, ops, ops_off, ops_len, status = ctx.align_batch(
-        np.concatenate(enc1), off1, np.concatenate(enc2), off2)
+    n_pairs = len(off1) - 1
+    m0, n0 = int(off1[1]), int(off2[1])
+    if n_pairs > 1 and off1[-1] == m0 * n_pairs and off2[-1] == n0 * n_pairs and \
+            np.array_equal(off1, np.arange(n_pairs + 1) * m0) and np.array_equal(off2, np.arange(n_pairs + 1) * n0):
+        # fixed-length batch (reads of one length): the entry point without offset arrays
+        cost, ops, stride, ops_len, status = ctx.align_batch_uniform(cat1, m0, cat2, n0, n_pairs)
+        ops_off = np.arange(n_pairs + 1, dtype=np.int64) * stride
+    else:
+        cost, ops, ops_off, ops_len, status = ctx.align_batch(cat1, off1, cat2, off2)
     return BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme)
 
 

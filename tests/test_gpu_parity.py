@@ -100,6 +100,17 @@ def test_batched_string_api():
         assert [a.seq_1_aligned, a.middle_part, a.seq_2_aligned, a.cost, a.score] == rec["out"]
         one = find_global_alignment(**rec["kw"])
         assert one.scoring_mat == a.scoring_mat and one.costing_mat == a.costing_mat
+    # a fixed-length, mixed-case batch goes through the entry point without offset arrays
+    rng = random.Random(3)
+    s1 = ["".join(rng.choice("ACGTacgt") for _ in range(60)) for _ in range(300)]
+    s2 = [x[:20] + "".join(rng.choice("ACGT") for _ in range(8)) + x[28:] for x in s1]
+    kw = dict(match_score=2, mismatch_score=-3, gap_open_score=-10, gap_extension_score=-1)
+    res = batch.find_global_alignments(s1, s2, **kw)
+    for k in range(0, 300, 17):
+        one = find_global_alignment(seq_1=s1[k], seq_2=s2[k], **kw)
+        a = res[k]
+        assert (a.seq_1_aligned, a.middle_part, a.seq_2_aligned, a.cost, a.score) == \
+            (one.seq_1_aligned, one.middle_part, one.seq_2_aligned, one.cost, one.score)
 
 
 # ------------------------------------------------------------------ the seam functions

@@ -1,5 +1,7 @@
 """Host-side logic (scheme handling, validation, result object, lowering, synthetic data)
 against the golden dumps of the reference.  CPU only."""
+import random
+
 import numpy as np
 import pytest
 
@@ -182,3 +184,31 @@ def test_batched_fasta_ingestion(tmp_path):
     (tmp_path / "odd.fa").write_text(">a\nAC\n>b\nAC\n>c\nAC\n")
     with pytest.raises(RuntimeError):
         batch.read_pairs_from_fasta(tmp_path / "odd.fa")
+
+
+def test_vectorised_batch_lowering_equals_pair_by_pair():
+    """batch._lower_ascii_batch (join + bytes.translate, no per-pair Python loop) must produce the
+    same alphabet, letter codes, offsets, upper-cased sequences and the same first error as the
+    pair-by-pair path that mirrors validate_and_transform_args (start.py:209-232, :643)."""
+    import numpy as np
+    from globalign_b200 import batch
+
+    sch = batch.Scheme(match_score=2, mismatch_score=-3, gap_open_score=-10, gap_extension_score=-1)
+    rng = random.Random(5)
+    big = [("".join(rng.choice("ACGTacgtNn") for _ in range(rng.randint(1, 80))),
+            "".join(rng.choice("ACGTacgtRy") for _ in range(rng.randint(1, 80)))) for _ in range(3000)]
+    cases = [big, [("AC-T", "ACGT")], [("", "A")], [("A" * 5000, "C" * 5000)],
+             [("ACGT", "ACGT"), ("A-", "C"), ("", "A")], [("ACGT", "ACGT"), ("", "A"), ("A-", "C")],
+             [("acgt", "ACGU")], [("a", "N")], [("Z*x", "zz")], [("ACGT", "ACGT")] * 7]
+    for pairs in cases:
+        got = []
+        for fn in (batch._lower_ascii_batch, batch._lower_batch):
+            try:
+                out = fn([x for x, _ in pairs], [y for _, y in pairs], start.MAX_SEQ_LEN_PRODUCT, sch)
+                got.append(("ok", out[2].letters, out[2].sub.tolist(), out[3].tolist(), out[4].tolist(),
+                            out[5].tolist(), out[6].tolist(), list(out[0]), list(out[1])))
+            except Exception as e:
+                got.append((type(e).__name__, str(e)))
+        assert got[0] == got[1]
+    # non-ASCII input is left to the pair-by-pair path
+    assert batch._lower_ascii_batch(["ACGé"], ["ACG"], start.MAX_SEQ_LEN_PRODUCT, sch) is None
