@@ -1,5 +1,8 @@
 // K4: traceback walk over the direction codes (sm_100a).
 //
+// (Measured and rejected: prefetch.global.L2 of the cell 8 diagonal steps ahead made the walk
+// 14 % slower, 1.26 -> 1.44 ms per 1M 150 x 150 pairs -- it is bound by DRAM sectors, not latency.)
+//
 // Replaces the reference's dp_array_backward (globaligner.py:395-593),
 // cost_ranks_dispatcher (:595-685, canonical = first listed option) and the four
 // take_* emitters (:688-753).  One thread walks one pair: at cell (i, j) with
@@ -65,7 +68,8 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const int rt_last = tail_rows<R, G>(td.M);
     const int wpp_last = (rt_last + L::RPW - 1) / L::RPW;
     const float inv_rt_last = 1.0f / (float)rt_last;
-    auto code_at = [&](int i, int j, int level) -> int {
+    // index (in 32-bit words) of cell (i, j)'s plane-0 entry and the shift of its 2 bits
+    auto locate = [&](int i, int j, int &sh) -> size_t {
         const int row = i - 1;
         const int pass = row / L::BAND;
         const int rem = row - pass * L::BAND;
@@ -83,9 +87,13 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         const int t = (j - 1) + g;
         const int w = r / L::RPW;
         const int rows_in_word = min(L::RPW, rp - w * L::RPW);
-        const int sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
+        sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
         // 128-bit word (pass, 2-step block, row-word, lane) = {p0 s0, p0 s1, p1 s0, p1 s1}
-        const size_t q = ((((size_t)pass * nB2 * L::WPP + (size_t)(t >> 1) * wpp) + w) * 32 + lane0 + g) * 4 + (t & 1);
+        return ((((size_t)pass * nB2 * L::WPP + (size_t)(t >> 1) * wpp) + w) * 32 + lane0 + g) * 4 + (t & 1);
+    };
+    auto code_at = [&](int i, int j, int level) -> int {
+        int sh;
+        const size_t q = locate(i, j, sh);
         auto plane = [&](int pl) -> unsigned { return (cw[q + 2 * pl] >> sh) & 3u; };
         if (level != 0) {
             const unsigned lu = plane(1);
