@@ -494,6 +494,8 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         if ((flags & GA_F_SEQ_2BIT) && (flags & GA_F_SEQ_4BIT)) return fail(ctx, GA_E_ARG, "choose one sequence packing");
         if (ctx->sc.A > (1 << bits)) return fail(ctx, GA_E_ARG, "alphabet of %d letters does not fit %d-bit packed sequences", ctx->sc.A, bits);
         ctx->sc.seq_bits = bits;
+        const char *e = getenv("GA_CODE_PAIRS");
+        ctx->sc.code_pairs = e ? (atoi(e) != 0) : 1;
     }
     ht.lap("plan: scan pairs");
     const KernelCfg *cfg = choose_cfg(ctx, maxM, maxN, flags);

@@ -16,9 +16,11 @@
 //     that skewed (step, lane) order.  The fill stages 2 steps in registers and
 //     writes, per row-word w (8 or 16 rows of a lane), one 128-bit word =
 //     {plane 0 step 0, plane 0 step 1, plane 1 step 0, plane 1 step 1}; these are
-//     laid out [pass][2-step block][row-word][lane 0..31], so every store
-//     instruction of a warp writes 512 contiguous bytes and the traceback walk
-//     finds both planes of two consecutive steps of a cell's row-word in 16 bytes.
+//     laid out [pass][pair of 2-step blocks][row-word][lane 0..31][block of the pair]:
+//     the traceback walk, bound by DRAM sectors, finds both planes of FOUR
+//     consecutive steps of a cell's row-word in one 32-byte sector, and a store
+//     instruction of a warp writes the 16-byte halves of 32 consecutive sectors
+//     (the other halves follow one block later and merge in L2).
 //     (Measured alternatives: 8 steps of a lane per 32-byte sector made the walk
 //     2.4x faster but its strided stores cost the fill 12 %; a 4-step unrolled
 //     body cost the fill 6 % -- both rejected.)
@@ -45,6 +47,7 @@ struct SchemeDev {
     // pipe) instead of IADD3/LOP3/LEA (ALU pipe): the ALU pipe is the bottleneck of
     // the cell update (profiles/README.md), the FMA pipe would otherwise idle.
     unsigned k_one, k_four, k_minus_one;
+    int code_pairs;      // direction-code layout: 1 = two consecutive 2-step blocks of a lane per 32-byte sector
     int seq_bits;        // letters per input byte: 8 (one letter per byte), 4 or 2 (bit-packed stream)
 };
 
@@ -137,7 +140,8 @@ struct LayInfo {
 __host__ __device__ inline long long tile_code_u4(int M, int N, int G, int BAND, int NW) {
     const long long npass = (M + BAND - 1) / BAND;
     const long long nb2 = (N + G - 1 + 1) / 2;
-    return npass * nb2 * (NW / 2) * 32;
+    const long long nb4 = (nb2 + 1) / 2;                 // 2-step blocks are stored in pairs
+    return npass * nb4 * 2 * (NW / 2) * 32;
 }
 template <bool PACKED, int R, int G>
 inline LayInfo lay_info() {

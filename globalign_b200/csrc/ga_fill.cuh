@@ -308,7 +308,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                 int rowjB = sc.o;                      // PT: the same for pair B
                 int2 nxt = make_int2(0, 0);
                 if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
-                uint4 *cbase = codes + td.code_off + (size_t)p * nTB * (L::WPP * 32) + lane;
+                uint4 *cbase = codes + td.code_off + (size_t)p * ((nTB + 1) / 2) * (L::WPP * 64);
 
                 for (int tb = 0; tb < nTB; ++tb) {
                     unsigned stg[L::S * NWT];
@@ -417,11 +417,15 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                             }
                         }
                     }
-                    // one 128-bit store per row-word: both planes of the two staged steps; lane-adjacent
+                    // one 128-bit store per row-word: both planes of the two staged steps.
+                    // sc.code_pairs: blocks 2k and 2k+1 of a lane share a 32-byte sector (4 steps per
+                    // sector for the walk); otherwise the words of a block are lane-adjacent.
     #pragma unroll
-                    for (int w = 0; w < WPPT; ++w)
-                        cbase[(size_t)(tb * WPPT + w) * 32] =
-                            make_uint4(stg[w], stg[NWT + w], stg[WPPT + w], stg[NWT + WPPT + w]);
+                    for (int w = 0; w < WPPT; ++w) {
+                        const size_t at = sc.code_pairs ? (size_t)((tb >> 1) * WPPT + w) * 64 + 2 * lane + (tb & 1)
+                                                        : (size_t)(tb * WPPT + w) * 32 + lane;
+                        cbase[at] = make_uint4(stg[w], stg[NWT + w], stg[WPPT + w], stg[NWT + WPPT + w]);
+                    }
                 }
                 __syncwarp();
                     };

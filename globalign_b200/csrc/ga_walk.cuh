@@ -51,7 +51,7 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const long long a1 = pair_off(off1, p, ut.M), a2 = pair_off(off2, p, ut.N);
     const int m = (int)(pair_off(off1, p + 1, ut.M) - a1), n = (int)(pair_off(off2, p + 1, ut.N) - a2);
     const int nsteps = td.N + G - 1;
-    const int nB2 = (nsteps + 1) / 2;
+    const int nB4 = ((nsteps + 1) / 2 + 1) / 2;     // pairs of 2-step blocks
     const uint32_t *cw = codes + 4 * td.code_off;
     const int lane0 = item * G;
     const int hshift = (PACKED && half) ? 16 : 0;
@@ -88,8 +88,12 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         const int w = r / L::RPW;
         const int rows_in_word = min(L::RPW, rp - w * L::RPW);
         sh = 2 * (rows_in_word - 1 - (r - w * L::RPW)) + hshift;
-        // 128-bit word (pass, 2-step block, row-word, lane) = {p0 s0, p0 s1, p1 s0, p1 s1}
-        return ((((size_t)pass * nB2 * L::WPP + (size_t)(t >> 1) * wpp) + w) * 32 + lane0 + g) * 4 + (t & 1);
+        // 128-bit word (pass, block pair, row-word, lane, block of the pair) = {p0 s0, p0 s1, p1 s0, p1 s1}
+        const int tb = t >> 1;
+        const size_t pass0 = (size_t)pass * nB4 * L::WPP * 64;            // uint4 words before this pass
+        const size_t u4 = sc.code_pairs ? pass0 + ((size_t)(tb >> 1) * wpp + w) * 64 + 2 * (lane0 + g) + (tb & 1)
+                                        : pass0 + ((size_t)tb * wpp + w) * 32 + lane0 + g;
+        return u4 * 4 + (t & 1);
     };
     auto code_at = [&](int i, int j, int level) -> int {
         int sh;

@@ -19,8 +19,9 @@ def layout(R, G, rows_per_word):
     nw = 2 * wpp                            # words per step: plane 0 = c0, plane 1 = (bL, bU)
     # The fill stages 2 steps and stores, per row-word w, one uint4 =
     # (plane 0, step 0), (plane 0, step 1), (plane 1, step 0), (plane 1, step 1) of that word;
-    # uint4s are laid out [pass][2-step block][row-word][lane]: a warp store is 512 contiguous
-    # bytes and the walker finds both planes of two consecutive steps in 16 bytes.
+    # the CUDA code lays the uint4s out [pass][pair of blocks][row-word][lane][block of the pair]
+    # (four consecutive steps of a lane's row-word per 32-byte sector); the model keeps them in a
+    # dict keyed (pass, block, row-word, lane), the linear address map is checked on the GPU.
     return dict(R=R, G=G, RPW=rows_per_word, WPP=wpp, NW=nw, S=2, NQ=wpp)
 
 

@@ -17,9 +17,13 @@ cost = torch.empty(n, dtype=torch.int32, device=dev); ln = torch.empty_like(cost
 ops = torch.empty(int(oo[-1]) + 16, dtype=torch.uint8, device=dev)
 ctx = _native.Context(0); ctx.set_scheme(dense)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
-for per_sm in ("4", "3", "2"):
+import itertools
+LAY = os.environ.get("PROBE_LAYOUTS")
+combos = [(l, "4") for l in LAY.split(",")] * 3 if LAY else [("1", x) for x in ("4", "3", "2")]
+for lay, per_sm in combos:
+    os.environ["GA_CODE_PAIRS"] = lay
     os.environ["GA_FILL_BLOCKS_PER_SM"] = per_sm
-    for chunks, flags in (("serial", _native.GA_F_SERIAL), ("2", 0), ("4", 0), ("8", 0), ("16", 0)):
+    for chunks, flags in ((("serial", _native.GA_F_SERIAL), ("4", 0)) if LAY else (("serial", _native.GA_F_SERIAL), ("2", 0), ("4", 0), ("8", 0), ("16", 0))):
         if chunks != "serial":
             os.environ["GA_CHUNKS"] = chunks
         info = ctx.plan_batch(b.off1, b.off2, oo, flags=flags)
@@ -35,5 +39,5 @@ for per_sm in ("4", "3", "2"):
         e1.record(stream)
         torch.cuda.synchronize()
         t = ctx.timing()
-        print("blocks/SM", per_sm, "chunks", chunks, info["n_chunks"], "ms/step", round(e0.elapsed_time(e1) / 10, 3),
+        print("code_pairs", lay, "blocks/SM", per_sm, "chunks", chunks, info["n_chunks"], "ms/step", round(e0.elapsed_time(e1) / 10, 3),
               "fill", round(t["fill"], 2), "walk", round(t["walk"], 2), flush=True)
