@@ -108,6 +108,13 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def device_count() -> int:
+    """CUDA devices the library sees (0 when there is none)."""
+    n = C.c_int(0)
+    rc = lib().ga_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
 class Context:
     """One ga_ctx (device + stream + scratch).  Not thread-safe by design."""
 

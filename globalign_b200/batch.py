@@ -227,7 +227,7 @@ class _LazyUpper:
         return (s.upper() for s in self._seqs)
 
 
-def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=None,
+def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max_seq_len_prod=None,
                            scoring_mat_name=None, scoring_mat_path=None, match_score=None,
                            mismatch_score=None, mismatch_cost=None, gap_open_score=None,
                            gap_open_cost=None, gap_extension_score=None, gap_extension_cost=None
@@ -236,7 +236,9 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=
 
     Scheme keywords mean exactly what they mean for ``find_global_alignment``.
     ``max_seq_len_prod`` defaults to the reference's guard (start.py:213); pass a
-    larger number (or ``float('inf')``) to lift it.
+    larger number (or ``float('inf')``) to lift it.  ``devices``: a list of GPU indices to
+    shard the batch over (equal DP cells per GPU, one host thread and context each, results
+    merged in pair order); default: the single GPU ``device``.
     """
     if len(seqs_1) != len(seqs_2) or len(seqs_1) == 0:
         raise RuntimeError("seqs_1 and seqs_2 must be non-empty and of equal length")
@@ -247,17 +249,23 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, max_seq_len_prod=
     if lowered is None:
         lowered = _lower_batch(seqs_1, seqs_2, limit, scheme)
     up1, up2, dense, cat1, off1, cat2, off2 = lowered
-    ctx = _native.default_context(device)
-    ctx.set_scheme(dense)
-    n_pairs = len(off1) - 1
-    m0, n0 = int(off1[1]), int(off2[1])
-    if n_pairs > 1 and off1[-1] == m0 * n_pairs and off2[-1] == n0 * n_pairs and \
-            np.array_equal(off1, np.arange(n_pairs + 1) * m0) and np.array_equal(off2, np.arange(n_pairs + 1) * n0):
-        # fixed-length batch (reads of one length): the entry point without offset arrays
-        cost, ops, stride, ops_len, status = ctx.align_batch_uniform(cat1, m0, cat2, n0, n_pairs)
-        ops_off = np.arange(n_pairs + 1, dtype=np.int64) * stride
+    def on_device(dev, c1, o1, c2, o2):
+        ctx = _native.default_context(dev)
+        ctx.set_scheme(dense)
+        n_pairs = len(o1) - 1
+        m0, n0 = int(o1[1]), int(o2[1])
+        if n_pairs > 1 and o1[-1] == m0 * n_pairs and o2[-1] == n0 * n_pairs and \
+                np.array_equal(o1, np.arange(n_pairs + 1) * m0) and np.array_equal(o2, np.arange(n_pairs + 1) * n0):
+            # fixed-length batch (reads of one length): the entry point without offset arrays
+            cost, ops, stride, ops_len, status = ctx.align_batch_uniform(c1, m0, c2, n0, n_pairs)
+            return cost, ops, np.arange(n_pairs + 1, dtype=np.int64) * stride, ops_len, status
+        return ctx.align_batch(c1, o1, c2, o2)
+
+    if devices is None or len(devices) <= 1:
+        cost, ops, ops_off, ops_len, status = on_device(device if not devices else devices[0], cat1, off1, cat2, off2)
     else:
-        cost, ops, ops_off, ops_len, status = ctx.align_batch(cat1, off1, cat2, off2)
+        from .parallel import align_on_devices
+        cost, ops, ops_off, ops_len, status = align_on_devices(on_device, cat1, off1, cat2, off2, list(devices))
     return BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme)
 
 

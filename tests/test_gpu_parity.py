@@ -628,3 +628,28 @@ def test_float_walk_with_replayed_draws_and_argument_checks():
     bad = lowering.DenseSchemeF64(cm, float("nan"))
     with pytest.raises(RuntimeError):
         ctx.align_f64(bad, s1, s2)
+
+
+def test_two_gpu_sharding():
+    """find_global_alignments(devices=[0, 1]): one host thread + context per GPU, equal-cell
+    shards, merged in pair order -- identical to the single-GPU call."""
+    if _native.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = random.Random(8)
+    s1 = ["".join(rng.choice("ACGT") for _ in range(rng.randint(20, 300))) for _ in range(2000)]
+    s2 = ["".join(ch if rng.random() < 0.9 else rng.choice("ACGT") for ch in x)[:rng.randint(15, 300)] or "A" for x in s1]
+    one = batch.find_global_alignments(s1, s2, gap_open_cost=5)
+    two = batch.find_global_alignments(s1, s2, gap_open_cost=5, devices=[0, 1])
+    assert np.array_equal(one.cost, two.cost) and np.array_equal(one.score, two.score)
+    assert np.array_equal(one.ops_len, two.ops_len) and np.array_equal(one.status, two.status)
+    for k in range(0, 2000, 37):
+        assert np.array_equal(one.ops_of(k), two.ops_of(k))
+        a, b = one[k], two[k]
+        assert (a.seq_1_aligned, a.middle_part, a.seq_2_aligned) == (b.seq_1_aligned, b.middle_part, b.seq_2_aligned)
+    # fixed-length shards take the entry point without offset arrays on every GPU
+    u1 = ["".join(rng.choice("ACGT") for _ in range(100)) for _ in range(1001)]
+    u2 = [x[:50] + x[52:] + "AC" for x in u1]
+    one = batch.find_global_alignments(u1, u2)
+    two = batch.find_global_alignments(u1, u2, devices=[0, 1])
+    assert np.array_equal(one.cost, two.cost)
+    assert all(np.array_equal(one.ops_of(k), two.ops_of(k)) for k in range(0, 1001, 50))

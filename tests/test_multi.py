@@ -72,3 +72,40 @@ def test_bench_shards_are_disjoint_blocks():
     r1 = synth.dna_fixed(per_rank, 150, 2000, first_block=2)
     assert np.array_equal(whole.slice(per_rank, 2 * per_rank).s1, r1.s1)
     assert np.array_equal(whole.slice(per_rank, 2 * per_rank).s2, r1.s2)
+
+
+def test_single_process_sharding_over_devices_merges_in_pair_order():
+    """parallel.align_on_devices: equal-cell contiguous shards, one thread per device, merged
+    outputs identical to one call over the whole batch (checked here with the C oracle standing in
+    for the per-device aligner; the GPU form is tests/test_gpu_parity.py::test_two_gpu_sharding)."""
+    import threading
+    from globalign_b200.batch import Scheme
+    from oracle import c_oracle
+
+    batch = synth.protein_varlen(97, 11)
+    small = batch.slice(0, 97)
+    s1 = (small.s1 % 4).astype(np.uint8)
+    s2 = (small.s2 % 4).astype(np.uint8)
+    sch = Scheme(**synth.SCHEMES["cfg2"])
+    dense = sch.dense_for(list("ACGT"))
+    d = c_oracle.Dense.__new__(c_oracle.Dense)
+    d.A, d.sub, d.gap_h, d.gap_v, d.o, d.max_cost = dense.A, dense.sub, dense.gap_h, dense.gap_v, dense.gap_open, dense.max_cost
+    seen = []
+
+    def fake(dev, a, oa, b, ob):
+        seen.append((dev, threading.get_ident(), len(oa) - 1))
+        ops, ops_off, nops, cost, status = c_oracle.align_batch(a, oa, b, ob, d, 1)
+        return cost, ops, ops_off, nops.astype(np.int32), status
+
+    whole = fake(0, s1, small.off1, s2, small.off2)
+    seen.clear()
+    for devices in ([0], [0, 1], [0, 1, 2, 3, 4, 5, 6, 7]):
+        got = parallel.align_on_devices(fake, s1, small.off1, s2, small.off2, devices)
+        for x, y in zip(whole, got):
+            assert np.array_equal(x, y)
+    shards = parallel.shard_by_cells(small.off1, small.off2, 8)
+    assert shards[0][0] == 0 and shards[-1][1] == 97 and all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+    cells = np.diff(small.off1) * np.diff(small.off2)
+    per = [int(cells[lo:hi].sum()) for lo, hi in shards]
+    assert max(per) - min(per) <= 2 * int(cells.max())          # balanced by cells, not by pairs
+    assert sum(n for _, _, n in seen) == 3 * 97
