@@ -7,8 +7,8 @@
 //     successor's level L, and takes the first-listed minimum c_L
 //     (reference globaligner.py:490-514, tie table :595-685).  Because
 //     c_1 is either c_0 or 1 and c_2 is either c_0 or 2, a cell needs 4 bits:
-//     plane 0 holds c_0 (2 bits), plane 1 holds bL = [c_1 == 1] (bit 0) and
-//     bU = [c_2 == 2] (bit 1);
+//     plane 0 holds c_0 (2 bits), plane 1 holds c_1 ^ c_2 (2 bits; one LOP3 in the
+//     fill, and with c_0 the walker recovers c_1 and c_2);
 //   * a "tile" is the set of pairs one warp fills together.  The warp's 32
 //     lanes are split into groups of G lanes; each lane owns R consecutive DP
 //     rows; a group sweeps the columns of its pair(s) as an anti-diagonal

@@ -26,7 +26,7 @@
 // (since d1 <= d1+o, min(d0+o,d1,d2+o) = min(h+o, d1); the tag of hq carried
 // through the fused add-min VIADDMNMX keeps every tie on the reference's side:
 // Lq's tag is c1 in {c0, 1}, Uq's tag is c2 in {c0, 2}).  Stored per cell: c0 and
-// the two bits bL = Lq & 1, bU = Uq & 2.  The next cells use
+// x = c1 ^ c2 (2 bits), from which the walker recovers c1 and c2.  The next cells use
 //     d0' = h(diag) + sub,  d1' = L(left) + gap_h,  d2' = U(up) + gap_v.
 // The boundary row/column use the reference's finite sentinel
 // (max_cost+1)*max(m,n) so every value equals the reference's.
@@ -390,9 +390,11 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                                 // never shifts into its neighbour.
                                 const unsigned th = hq & V::TAGM;                 // LOP3
                                 acc[w] = acc[w] * K4 + th;                       // IMAD
-                                // plane 1: bit 0 (of each half) from Lq, bit 1 from Uq
-                                constexpr unsigned B0 = V::TAGM & 0x55555555u;
-                                const unsigned lu = ((Lq & B0) | (Uq & ~B0)) & V::TAGM;   // 2 x LOP3
+                                // plane 1: x = tag(Lq) ^ tag(Uq), ONE LOP3.  tag(Lq) is c0 or 1 and tag(Uq) is
+                                // c0 or 2, so together with c0 the walker recovers both (ga_walk.cuh): c0 = 0:
+                                // bit 0 = [c1 == 1], bit 1 = [c2 == 2]; c0 = 1: x != 0 <=> c2 == 2; c0 = 2:
+                                // x != 0 <=> c1 == 1.
+                                const unsigned lu = (Lq ^ Uq) & V::TAGM;
                                 acc[WPPT + w] = acc[WPPT + w] * K4 + lu;     // IMAD
                                 diag = hl[r];
                                 hl[r] = th * KM1 + hq;                           // hq - tag, IMAD

@@ -6,9 +6,9 @@
 // Replaces the reference's dp_array_backward (globaligner.py:395-593),
 // cost_ranks_dispatcher (:595-685, canonical = first listed option) and the four
 // take_* emitters (:688-753).  One thread walks one pair: at cell (i, j) with
-// the successor node on level L it decodes c_L(i, j) -- plane 0 holds c_0; for
-// L = 1 (2) the bit bL (bU) of plane 1 says "take level 1 (2)", otherwise
-// c_L = c_0 -- emits it as the operation, moves, and sets L to it.  Reaching row 0 / column 0 ends the
+// the successor node on level L it decodes c_L(i, j) -- plane 0 holds c_0, plane 1
+// holds c_1 ^ c_2 (c_1 is c_0 or 1, c_2 is c_0 or 2, so the pair is recoverable) --
+// emits it as the operation, moves, and sets L to it.  Reaching row 0 / column 0 ends the
 // walk with a run of gap operations (:542-581).  Operations are emitted in walk
 // order, 16 per 32-bit word.
 //
@@ -99,11 +99,14 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
         int sh;
         const size_t q = locate(i, j, sh);
         auto plane = [&](int pl) -> unsigned { return (cw[q + 2 * pl] >> sh) & 3u; };
-        if (level != 0) {
-            const unsigned lu = plane(1);
-            if (lu & (unsigned)level) return level;      // bL is bit 0 (level 1), bU is bit 1 (level 2)
-        }
-        return (int)plane(0);
+        const int c0 = (int)plane(0);
+        if (level == 0 || c0 == level) return c0;      // c_L is c0 or L
+        // plane 1 holds x = c1 ^ c2 with c1 in {c0, 1}, c2 in {c0, 2}:
+        //   c0 = 0: bit 0 of x = [c1 == 1], bit 1 = [c2 == 2];  otherwise (c0 is the other gap
+        //   level, whose own code equals c0): x != 0 <=> c_L == L
+        const unsigned x = plane(1);
+        const bool take = c0 == 0 ? (x & (unsigned)level) != 0 : x != 0;
+        return take ? level : c0;
     };
 
     int i = m, j = n, level = 0, status = 0;

@@ -16,7 +16,7 @@ TAG = 3
 
 def layout(R, G, rows_per_word):
     wpp = -(-R // rows_per_word)            # words per plane per step
-    nw = 2 * wpp                            # words per step: plane 0 = c0, plane 1 = (bL, bU)
+    nw = 2 * wpp                            # words per step: plane 0 = c0, plane 1 = c1 ^ c2
     # The fill stages 2 steps and stores, per row-word w, one uint4 =
     # (plane 0, step 0), (plane 0, step 1), (plane 1, step 0), (plane 1, step 1) of that word;
     # the CUDA code lays the uint4s out [pass][pair of blocks][row-word][lane][block of the pair]
@@ -107,7 +107,7 @@ def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=1
                         Lq = min(hq + o4, d1)         # VIADDMNMX; tag is c0 or 1
                         Uq = min(hq + o4, d2)         # tag is c0 or 2
                         w = r // L["RPW"]
-                        lu = (Lq & 1) | (Uq & 2)      # bL = "level-1 successor takes level 1", bU likewise
+                        lu = (Lq ^ Uq) & TAG          # c1 ^ c2; with c0 the walker recovers c1 and c2
                         words[w] = words[w] * 4 + (hq & TAG)
                         words[L["WPP"] + w] = words[L["WPP"] + w] * 4 + lu
                         diag = st["hl"][r]
@@ -134,15 +134,13 @@ def fill_model(s1, s2, sub, gap_h, gap_v, o, max_cost, R=4, G=8, rows_per_word=1
 
 def code_at(codes, L, m, i, j, level):
     """Direction at DP cell (i, j) (1-based) for a successor on `level`, as the walker
-    decodes it: c0 from plane 0; for level 1 (2) the bit bL (bU) of plane 1 overrides
-    it with 1 (2)."""
+    decodes it: c0 from plane 0; plane 1 holds c1 ^ c2 (c1 in {c0, 1}, c2 in {c0, 2})."""
     c0 = _plane_at(codes, L, m, i, j, 0)
-    if level == 0:
+    if level == 0 or c0 == level:
         return c0
-    lu = _plane_at(codes, L, m, i, j, 1)
-    if level == 1:
-        return 1 if lu & 1 else c0
-    return 2 if lu & 2 else c0
+    x = _plane_at(codes, L, m, i, j, 1)
+    take = (x & level) != 0 if c0 == 0 else x != 0
+    return level if take else c0
 
 
 def _plane_at(codes, L, m, i, j, plane):
