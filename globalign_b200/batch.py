@@ -288,6 +288,28 @@ def read_pairs_from_fasta(fasta_path, fasta_path_2=None):
     return descs, [a[1] for a in left], [b[1] for b in right]
 
 
+def read_pairs_from_fastq(fastq_path, fastq_path_2=None):
+    """The same for FASTQ (plain or .gz): one file with consecutive records paired (interleaved
+    reads), or two files read in step (R1 / R2).  -> (descs, seqs_1, seqs_2)"""
+    recs = list(start.read_seq_from_fastq(fastq_path))
+    if fastq_path_2 is None:
+        if len(recs) < 2 or len(recs) % 2:
+            raise RuntimeError("the FASTQ file must hold an even, non-zero number of records")
+        left, right = recs[0::2], recs[1::2]
+    else:
+        left, right = recs, list(start.read_seq_from_fastq(fastq_path_2))
+        if len(left) != len(right) or not left:
+            raise RuntimeError("the two FASTQ files must hold the same, non-zero number of records")
+    descs = [(a[0], b[0]) for a, b in zip(left, right)]
+    return descs, [a[1] for a in left], [b[1] for b in right]
+
+
+def find_global_alignments_from_fastq(fastq_path, fastq_path_2=None, **kwargs):
+    """-> (descs, BatchAlignment) for every record pair of the FASTQ file(s)."""
+    descs, s1, s2 = read_pairs_from_fastq(fastq_path, fastq_path_2)
+    return descs, find_global_alignments(s1, s2, **kwargs)
+
+
 def find_global_alignments_from_fasta(fasta_path, fasta_path_2=None, **kwargs):
     """-> (descs, BatchAlignment) for every record pair of the file(s)."""
     descs, s1, s2 = read_pairs_from_fasta(fasta_path, fasta_path_2)

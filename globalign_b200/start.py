@@ -273,6 +273,41 @@ def read_seq_from_fasta(fasta_path: Path):
         yield desc, finish()
 
 
+def _open_text(path):
+    """Plain or gzip-compressed text file (by the .gz suffix)."""
+    path = Path(path)
+    if path.suffix == ".gz":
+        import gzip
+        return gzip.open(path, "rt")
+    return path.open()
+
+
+def read_seq_from_fastq(fastq_path: Path):
+    """Yield (description, SEQUENCE) from a four-line-per-record FASTQ file (plain or .gz).  Not in
+    the reference (it reads FASTA only, :614-688); SURVEY.md 8f, f3 -- sequencing reads, the
+    batched path's natural input, come as FASTQ.  Quality strings are checked for length and
+    dropped (the aligner has no use for them); sequences are upper-cased like the FASTA reader's."""
+    with _open_text(fastq_path) as fh:
+        n = 0
+        while True:
+            head = fh.readline()
+            if not head:
+                break
+            if not head.strip():
+                continue
+            seq, plus, qual = fh.readline().strip(), fh.readline().strip(), fh.readline().strip()
+            n += 1
+            if not head.startswith("@") or not plus.startswith("+"):
+                raise RuntimeError(f"Invalid FASTQ format in record {n}: expected '@' and '+' lines.")
+            if not seq:
+                raise RuntimeError("Empty sequence detected in FASTQ.")
+            if len(qual) != len(seq):
+                raise RuntimeError(f"Invalid FASTQ format in record {n}: quality and sequence lengths differ.")
+            yield head.strip(), seq.upper()
+        if n == 0:
+            raise RuntimeError("Invalid FASTQ format. No records found.")
+
+
 def read_first_2_seqs_from_fasta(fasta_path: Path):
     seqs = []
     for _desc, seq in read_seq_from_fasta(fasta_path):

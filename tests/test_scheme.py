@@ -212,3 +212,33 @@ def test_vectorised_batch_lowering_equals_pair_by_pair():
         assert got[0] == got[1]
     # non-ASCII input is left to the pair-by-pair path
     assert batch._lower_ascii_batch(["ACGé"], ["ACG"], start.MAX_SEQ_LEN_PRODUCT, sch) is None
+
+
+def test_fastq_pair_reader(tmp_path):
+    """FASTQ ingestion for the batched path: interleaved single file, two files
+    read in step, gzip, and the format errors."""
+    import gzip
+    from globalign_b200 import batch
+
+    recs = [("@r1/1", "acgtNN", "IIIIII"), ("@r1/2", "ACGT", "IIII"), ("@r2/1", "GGG", "!!!"), ("@r2/2", "GGCA", "FFFF")]
+    text = "".join(f"{h}\n{s}\n+\n{q}\n" for h, s, q in recs)
+    one = tmp_path / "inter.fastq"
+    one.write_text(text + "\n")
+    descs, s1, s2 = batch.read_pairs_from_fastq(one)
+    assert descs == [("@r1/1", "@r1/2"), ("@r2/1", "@r2/2")] and s1 == ["ACGTNN", "GGG"] and s2 == ["ACGT", "GGCA"]
+    r1, r2 = tmp_path / "R1.fastq.gz", tmp_path / "R2.fastq"
+    with gzip.open(r1, "wt") as fh:
+        fh.write("".join(f"{h}\n{s}\n+\n{q}\n" for h, s, q in recs[0::2]))
+    r2.write_text("".join(f"{h}\n{s}\n+{h[1:]}\n{q}\n" for h, s, q in recs[1::2]))
+    assert batch.read_pairs_from_fastq(r1, r2) == (descs, s1, s2)
+    bad = tmp_path / "bad.fastq"
+    for content in ("", ">x\nACGT\n", "@x\nACGT\n+\nIII\n", "@x\n\n+\n\n", "@x\nACGT\n-\nIIII\n"):
+        bad.write_text(content)
+        with pytest.raises(RuntimeError):
+            list(start.read_seq_from_fastq(bad))
+    odd = tmp_path / "odd.fastq"
+    odd.write_text("@x\nACGT\n+\nIIII\n")
+    with pytest.raises(RuntimeError):
+        batch.read_pairs_from_fastq(odd)
+    with pytest.raises(RuntimeError):
+        batch.read_pairs_from_fastq(one, odd)
