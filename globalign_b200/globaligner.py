@@ -261,8 +261,32 @@ def main(argv=None):
     for name in ("match_score", "mismatch_score", "mismatch_cost", "gap_open_score", "gap_open_cost",
                  "gap_extension_score", "gap_extension_cost"):
         p.add_argument(f"--{name}", required=False)
+    # batch mode (not in the reference, whose CLI aligns the first two FASTA records only):
+    # every consecutive record pair of the FASTA / FASTQ input, one scheme, one GPU batch
+    p.add_argument("--batch", action="store_true",
+                   help="Align every consecutive pair of records of --input_fasta (or of --input_fastq) "
+                        "and write all alignments to --output.")
+    p.add_argument("--input_fastq", required=False)
+    p.add_argument("--input_fastq_2", required=False, help="Second FASTQ file (R2): record k pairs with record k of --input_fastq.")
     args = p.parse_args(argv)
-    find_global_alignment(**vars(args)).write()
+    kw = vars(args)
+    batch_mode, fq1, fq2 = kw.pop("batch"), kw.pop("input_fastq"), kw.pop("input_fastq_2")
+    if not (batch_mode or fq1):
+        find_global_alignment(**kw).write()
+        return None
+    from . import batch
+    scheme_kw = {k: v for k, v in kw.items() if k not in ("input_fasta", "output", "seq_1", "seq_2")}
+    if fq1:
+        descs, res = batch.find_global_alignments_from_fastq(fq1, fq2, **scheme_kw)
+    elif kw["input_fasta"]:
+        descs, res = batch.find_global_alignments_from_fasta(kw["input_fasta"], **scheme_kw)
+    else:
+        raise RuntimeError("--batch needs --input_fasta or --input_fastq")
+    if kw["output"] is None:
+        for k in range(len(res)):
+            print(res[k].__str__(desc_1=descs[k][0], desc_2=descs[k][1]))
+    else:
+        res.write(kw["output"], descs=descs)
     return None
 
 

@@ -442,6 +442,16 @@ def test_fasta_batch_and_batch_writer(tmp_path):
     one = find_global_alignment(input_fasta=str(fa))      # the reference-style call reads the first two records
     assert text.startswith(one.__str__(desc_1=">a0", desc_2=">b0"))
     assert text.count("\nscore: ") == len(recs)
+    # the CLI's batch mode writes the same file; FASTQ input gives the same alignments
+    out2 = tmp_path / "cli.txt"
+    globaligner.main(["--batch", "-i", str(fa), "-o", str(out2)])
+    assert out2.read_text() == text
+    fq = tmp_path / "in.fastq"
+    fq.write_text("".join(f"@a{k}\n{r['kw']['seq_1']}\n+\n{'I' * len(r['kw']['seq_1'])}\n"
+                          f"@b{k}\n{r['kw']['seq_2']}\n+\n{'I' * len(r['kw']['seq_2'])}\n" for k, r in enumerate(recs)))
+    out3 = tmp_path / "cli_fq.txt"
+    globaligner.main(["--input_fastq", str(fq), "-o", str(out3)])
+    assert out3.read_text() == text.replace(">a", "@a").replace(">b", "@b")
 
 
 # ------------------------------------------------------------------ bit-packed sequence input
