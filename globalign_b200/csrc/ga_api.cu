@@ -821,7 +821,7 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         ChunkEvents &E = ctx->cev[c];
         const int b = serial ? 0 : (int)(c & 1);
         cudaStream_t sF = serial ? main : ctx->aux[b], sW = serial ? main : ctx->aux[2 + b];
-        cudaStream_t sIn = ctx->aux[4], sOut = ctx->aux[5];
+        cudaStream_t sOut = ctx->aux[5];
         const int n_tiles = ch.tile_hi - ch.tile_lo, np = ch.pair_hi - ch.pair_lo;
         if (io) {   // the letters are already in flight (ga_align_batch): wait for the piece that
                     // holds this chunk's last letter of either sequence set
@@ -1539,7 +1539,7 @@ __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsi
         b[k] = seed * 3u + threadIdx.x + 11u * k;
         c[k] = seed ^ (threadIdx.x * 5u + k);
     }
-    if (MODE >= 10) {
+    if constexpr (MODE >= 10) {
         unsigned x = a[0], y = b[0], z = c[0];
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -1551,8 +1551,7 @@ __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsi
             }
         }
         out[blockIdx.x * blockDim.x + threadIdx.x] = x ^ y ^ z;
-        return;
-    }
+    } else {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -1583,6 +1582,7 @@ __global__ void __launch_bounds__(256) alu_kernel(unsigned *out, int iters, unsi
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc ^= a[k] ^ b[k] ^ c[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    }
 }
 
 extern "C" int ga_alu_peak(ga_ctx *ctx, int mode, double *gops) {
