@@ -57,7 +57,7 @@ struct LongLane {
 
 __device__ __forceinline__ int2 ld_volatile_int2(const int2 *p) {
     int2 v;
-    asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 
