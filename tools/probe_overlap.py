@@ -20,12 +20,16 @@ stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_s
 import itertools
 LAY = os.environ.get("PROBE_LAYOUTS")
 combos = [(l, "4") for l in LAY.split(",")] * 3 if LAY else [("1", x) for x in ("4", "3", "2")]
+SPLIT = os.environ.get("PROBE_SPLIT")
+if SPLIT:
+    combos = [("1", "4")] * 2
 for lay, per_sm in combos:
     os.environ["GA_CODE_PAIRS"] = lay
     os.environ["GA_FILL_BLOCKS_PER_SM"] = per_sm
-    for chunks, flags in ((("serial", _native.GA_F_SERIAL), ("4", 0)) if LAY else (("serial", _native.GA_F_SERIAL), ("2", 0), ("4", 0), ("8", 0), ("16", 0))):
+    for chunks, flags in ([("4", 0), ("4s", 0), ("8", 0), ("8s", 0), ("16", 0), ("16s", 0)] if SPLIT else (("serial", _native.GA_F_SERIAL), ("4", 0)) if LAY else (("serial", _native.GA_F_SERIAL), ("2", 0), ("4", 0), ("8", 0), ("16", 0))):
+        os.environ["GA_SPLIT_FILL"] = "1" if chunks.endswith("s") else "0"
         if chunks != "serial":
-            os.environ["GA_CHUNKS"] = chunks
+            os.environ["GA_CHUNKS"] = chunks.rstrip("s")
         info = ctx.plan_batch(b.off1, b.off2, oo, flags=flags)
         run = lambda: ctx.run_batch(d["s1"].data_ptr(), d["off1"].data_ptr(), d["s2"].data_ptr(), d["off2"].data_ptr(),
                                     cost.data_ptr(), ops.data_ptr(), d["oo"].data_ptr(), ln.data_ptr(), st.data_ptr())
