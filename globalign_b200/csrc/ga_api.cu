@@ -75,6 +75,12 @@ static KernelCfg make_cfg(const char *name) {
 static const std::vector<KernelCfg> &registry() {
     static const std::vector<KernelCfg> cfgs = {
         // packed 16-bit, two pairs per register (simple schemes, short reads)
+        make_cfg<true, true, 7, 8>("fill_p16_r7_g8"),
+        make_cfg<true, true, 10, 8>("fill_p16_r10_g8"),
+        make_cfg<true, true, 13, 8>("fill_p16_r13_g8"),
+        make_cfg<true, true, 16, 8>("fill_p16_r16_g8"),
+        make_cfg<true, true, 13, 16>("fill_p16_r13_g16"),
+        make_cfg<true, true, 19, 16>("fill_p16_r19_g16"),
         make_cfg<true, true, 5, 32>("fill_p16_r5_g32"),
         make_cfg<true, true, 10, 16>("fill_p16_r10_g16"),
         make_cfg<true, true, 15, 10>("fill_p16_r15_g10"),
@@ -407,10 +413,18 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
     }
     if (sc.simple) {
         if (!(flags & GA_F_FORCE_GENERIC)) {
-            // measured on B200 (tools/tune_cfgs.py): r19_g8 > r15_g10 > r10_g16 for 150-row reads
-            const char *pick = maxM <= 152 ? "fill_p16_r19_g8"
+            // single-pass configurations by rows covered (R x G); measured on B200
+            // (tools/tune_cfgs.py): for 150-row reads r19_g8 > r15_g10 > r10_g16 -- few lanes per
+            // group (short ramp), many rows per lane.  The smallest band that holds the reads wins.
+            const char *pick = maxM <= 56 ? "fill_p16_r7_g8"
+                               : maxM <= 80 ? "fill_p16_r10_g8"
+                               : maxM <= 104 ? "fill_p16_r13_g8"
+                               : maxM <= 128 ? "fill_p16_r16_g8"
+                               : maxM <= 152 ? "fill_p16_r19_g8"
                                : maxM <= 160 ? "fill_p16_r10_g16"
-                               : maxM <= 256 ? "fill_p16_r16_g16" : "fill_p16_r16_g32";
+                               : maxM <= 208 ? "fill_p16_r13_g16"
+                               : maxM <= 256 ? "fill_p16_r16_g16"
+                               : maxM <= 304 ? "fill_p16_r19_g16" : "fill_p16_r16_g32";
             const KernelCfg *c = find_cfg(pick);
             if (fits16(c)) return c;
         }

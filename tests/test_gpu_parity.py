@@ -14,7 +14,8 @@ from util import DenseView, fix_paths, golden, rescore
 
 pytestmark = pytest.mark.gpu
 
-PACKED_CFGS = ["fill_p16_r5_g32", "fill_p16_r10_g16", "fill_p16_r15_g10", "fill_p16_r19_g8",
+PACKED_CFGS = ["fill_p16_r7_g8", "fill_p16_r10_g8", "fill_p16_r13_g8", "fill_p16_r16_g8", "fill_p16_r13_g16", "fill_p16_r19_g16",
+               "fill_p16_r5_g32", "fill_p16_r10_g16", "fill_p16_r15_g10", "fill_p16_r19_g8",
                "fill_p16_r16_g16", "fill_p16_r8_g32", "fill_p16_r16_g32"]
 I32S_CFGS = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
 I32T_CFGS = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]

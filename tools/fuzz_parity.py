@@ -17,7 +17,8 @@ sys.path.insert(0, str(ROOT / "tests"))
 from globalign_b200 import _native, lowering  # noqa: E402
 from oracle import c_oracle  # noqa: E402
 
-PACKED = ["fill_p16_r5_g32", "fill_p16_r10_g16", "fill_p16_r15_g10", "fill_p16_r19_g8", "fill_p16_r16_g16",
+PACKED = ["fill_p16_r7_g8", "fill_p16_r10_g8", "fill_p16_r13_g8", "fill_p16_r16_g8", "fill_p16_r13_g16", "fill_p16_r19_g16",
+               "fill_p16_r5_g32", "fill_p16_r10_g16", "fill_p16_r15_g10", "fill_p16_r19_g8", "fill_p16_r16_g16",
           "fill_p16_r8_g32", "fill_p16_r16_g32"]
 I32S = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
 I32T = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]
