@@ -664,3 +664,28 @@ def test_two_gpu_sharding():
     two = batch.find_global_alignments(u1, u2, devices=[0, 1])
     assert np.array_equal(one.cost, two.cost)
     assert all(np.array_equal(one.ops_of(k), two.ops_of(k)) for k in range(0, 1001, 50))
+
+
+def test_integration_md_ctypes_stub_runs_as_written():
+    """The binding INTEGRATION.md shows a maintainer of the reference is executable: take the code
+    block verbatim (only the library path is made absolute), run the reference's tutorial vectors
+    and a few random golden cases through it."""
+    from pathlib import Path
+    import re
+
+    root = Path(__file__).resolve().parents[1]
+    text = (root / "INTEGRATION.md").read_text()
+    block = re.search(r"## 2\. ctypes stub.*?```python\n(.*?)```", text, re.S).group(1)
+    lib = root / "globalign_b200" / "libglobalign_b200.so"
+    block = block.replace('"libglobalign_b200.so"', repr(str(lib)))
+    ns = {"get_max_val": start.get_max_val}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    gpu_dp = ns["_gpu_dp"]
+    cases = [r for r in golden("random_cases.json") if set(r["kw"]) == {"seq_1", "seq_2"}][:40]
+    cases += [golden("kat.json")["tutorial"][0]]
+    for rec in cases:
+        kw = rec["kw"]
+        s1, s2 = kw["seq_1"].upper(), kw["seq_2"].upper()
+        ref = find_global_alignment(**kw)
+        got = gpu_dp(s1, s2, ref.costing_mat, ref.gap_open_cost)
+        assert list(got) == rec["out"][:4]
