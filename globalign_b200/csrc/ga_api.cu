@@ -136,7 +136,8 @@ struct ga_ctx {
     // pipeline streams: two fill streams (alternating chunks, so the tail of one chunk
     // overlaps the start of the next), two walk streams, copy-in and copy-out
     cudaStream_t aux[6] = {};
-    cudaEvent_t in_piece[8] = {}, in_begin = nullptr;   // host-buffer entry point: upload pieces
+    cudaEvent_t in_piece[32] = {}, in_begin = nullptr;   // host-buffer entry point: upload pieces
+    int in_pieces = 1;                  // pieces of the current call
     std::string err;
     int64_t scratch_limit = (int64_t)64 << 30;
     int sm_count = 0;
@@ -166,6 +167,7 @@ struct ga_ctx {
     long long uni_u4 = 0;
     long long uni_ops_stride = 0;      // bytes per pair of packed ops when offsets are implicit
     DevBuf d_tiles, d_codes[2], d_bnd[2], d_counter;
+    int n_bufs = 1;                    // code buffers of the current plan (1 serial, else 2)
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
     // long-pair path
@@ -574,8 +576,10 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         if (serial) {
             cuts = {1.0};
         } else if (ctx->plan_for_io && tiles_per_warp >= 16.0 && !getenv("GA_CHUNKS")) {
-            cuts.push_back(0.125);
-            for (int k = 1; k <= mid; ++k) cuts.push_back(0.125 + 0.75 * k / mid);
+            double edge = 0.125;                       // share of the first and of the last chunk
+            if (const char *e = getenv("GA_EDGE_CHUNK")) edge = std::min(0.4, std::max(0.01, atof(e)));
+            cuts.push_back(edge);
+            for (int k = 1; k <= mid; ++k) cuts.push_back(edge + (1.0 - 2 * edge) * k / mid);
             cuts.push_back(1.0);
         } else {
             for (int k = 1; k <= mid; ++k) cuts.push_back((double)k / mid);
@@ -751,7 +755,8 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     if (!uniform && (rc = ensure(ctx, ctx->d_tiles, (size_t)n_tiles * sizeof(TileDesc)))) return rc;
     if (!ctx->perm.empty() && (rc = ensure(ctx, ctx->d_perm, (size_t)n_pairs * sizeof(int)))) return rc;
     ht.lap("plan: occupancy query");
-    const int n_bufs = (serial || ctx->chunks.size() == 1) ? 1 : 2;
+    const int n_bufs = (serial || ctx->chunks.size() == 1) ? 1 : (int)std::min<size_t>(2, ctx->chunks.size());
+    ctx->n_bufs = n_bufs;
     for (int b = 0; b < n_bufs; ++b) {
         if ((rc = ensure(ctx, ctx->d_codes[b], (size_t)max_chunk_u4 * 16))) return rc;
         if ((rc = ensure(ctx, ctx->d_bnd[b], (size_t)ctx->grid * warps * L.IPW * ctx->bnd_stride * sizeof(int2)))) return rc;
@@ -805,10 +810,11 @@ extern "C" int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info) {
 }
 
 // Host buffers of the host-buffer entry point (null for ga_run_batch).
-constexpr int IN_PIECES = 8;        // the letters are uploaded in this many pieces, started before planning
+constexpr int MAX_IN_PIECES = 32;   // the letters are uploaded in up to this many pieces (about 1 MB each), started before planning
 
 struct HostIO {
-    int64_t total1 = 0, total2 = 0;     // letters in s1 / s2 (piece k ends at total * (k+1) / IN_PIECES)
+    int64_t total1 = 0, total2 = 0;     // letters in s1 / s2 (piece k ends at total * (k+1) / pieces)
+    int pieces = 1;
     const uint8_t *s1 = nullptr, *s2 = nullptr;
     const int64_t *off1 = nullptr, *off2 = nullptr, *ops_off = nullptr;
     int32_t *cost = nullptr, *len = nullptr, *status = nullptr;
@@ -817,7 +823,9 @@ struct HostIO {
 
 // The chunk pipeline.  For chunk c (buffers / streams chosen by c & 1):
 //   copy-in (host entry only)  ->  fill  ->  walk  ->  copy-out (host entry only)
-// fill(c) waits for walk(c-2) (it reuses that chunk's code buffer); everything is
+// fill(c) waits for walk(c-2) (it reuses that chunk's code buffer).  (Three rotating buffers were
+// measured: the 0.12 ms bubble per pair of chunks disappears from the timeline, GA_DEBUG_TIMELINE=1,
+// but the step time does not change -- fill and walk share the same SM slots either way.)  Everything is
 // bracketed by ev[0] / ev[1] on the caller-visible stream, which finally waits for
 // all auxiliary streams.
 static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_off, const uint8_t *d_s2,
@@ -835,23 +843,25 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
     for (size_t c = 0; c < nc; ++c) {
         const Chunk &ch = ctx->chunks[c];
         ChunkEvents &E = ctx->cev[c];
-        const int b = serial ? 0 : (int)(c & 1);
-        cudaStream_t sF = serial ? main : ctx->aux[b], sW = serial ? main : ctx->aux[2 + b];
+        const int b = serial ? 0 : (int)(c % (size_t)ctx->n_bufs);      // code / boundary buffer
+        const int s2i = (int)(c & 1);                                   // stream pair
+        cudaStream_t sF = serial ? main : ctx->aux[s2i], sW = serial ? main : ctx->aux[2 + s2i];
         cudaStream_t sOut = ctx->aux[5];
         const int n_tiles = ch.tile_hi - ch.tile_lo, np = ch.pair_hi - ch.pair_lo;
         if (io) {   // the letters are already in flight (ga_align_batch): wait for the piece that
                     // holds this chunk's last letter of either sequence set
             const int64_t a1 = io->off1 ? io->off1[ch.pair_hi] : (int64_t)ch.pair_hi * ctx->uniM;
             const int64_t b1 = io->off2 ? io->off2[ch.pair_hi] : (int64_t)ch.pair_hi * ctx->uniN;
-            auto piece_of = [](int64_t end, int64_t total) {
+            const int P = io->pieces;
+            auto piece_of = [P](int64_t end, int64_t total) {
                 int k = 0;
-                while (k < IN_PIECES - 1 && total * (k + 1) / IN_PIECES < end) ++k;
+                while (k < P - 1 && total * (k + 1) / P < end) ++k;
                 return k;
             };
             const int k = std::max(piece_of(a1, io->total1), piece_of(b1, io->total2));
             CK(cudaStreamWaitEvent(sF, ctx->in_piece[k], 0));
         }
-        if (!serial && c >= 2) CK(cudaStreamWaitEvent(sF, ctx->cev[c - 2].w1, 0));   // code buffer free
+        if (!serial && c >= (size_t)ctx->n_bufs) CK(cudaStreamWaitEvent(sF, ctx->cev[c - ctx->n_bufs].w1, 0));   // code buffer free
         CK(cudaEventRecord(E.f0, sF));
         const bool persistent = ctx->persistent || serial;
         const int grid = persistent ? std::min(ctx->grid, (n_tiles + 3) / 4) : (n_tiles + 3) / 4;
@@ -894,7 +904,6 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
             CK(cudaStreamWaitEvent(main, ctx->cev[c].w1, 0));
             if (io) CK(cudaStreamWaitEvent(main, ctx->cev[c].out1, 0));
         }
-        if (io && nc > 2) CK(cudaStreamWaitEvent(main, ctx->cev[nc - 1].out1, 0));
     }
     CK(cudaEventRecord(ctx->ev[1], main));
     ctx->timing_valid = true;
@@ -934,7 +943,21 @@ extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
             d2h += t;
         }
     }
-    if (ctx->timing_io) CK(cudaEventElapsedTime(&h2d, ctx->in_begin, ctx->in_piece[IN_PIECES - 1]));
+    if (ctx->timing_io) CK(cudaEventElapsedTime(&h2d, ctx->in_begin, ctx->in_piece[ctx->in_pieces - 1]));
+    if (getenv("GA_DEBUG_TIMELINE")) {      // per-chunk event times relative to the start of the call (ms)
+        auto at = [&](cudaEvent_t e) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[0], e); return t; };
+        if (ctx->timing_io)
+            fprintf(stderr, "[ga timeline] upload: first piece %.3f, last piece %.3f (%d pieces)\n",
+                    at(ctx->in_piece[0]), at(ctx->in_piece[ctx->in_pieces - 1]), ctx->in_pieces);
+        for (size_t c = 0; c < ctx->chunks.size(); ++c) {
+            const ChunkEvents &E = ctx->cev[c];
+            fprintf(stderr, "[ga timeline] chunk %zu pairs %d: fill %.3f-%.3f walk %.3f-%.3f", c,
+                    ctx->chunks[c].pair_hi - ctx->chunks[c].pair_lo, at(E.f0), at(E.f1), at(E.w0), at(E.w1));
+            if (ctx->timing_io) fprintf(stderr, " copy-out %.3f-%.3f", at(E.out0), at(E.out1));
+            fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "[ga timeline] end %.3f\n", at(ctx->ev[1]));
+    }
     CK(cudaEventElapsedTime(&total, ctx->ev[0], ctx->ev[1]));
     // per-phase sums; with the pipeline on, phases overlap each other, so they add up
     // to more than `total` (the bracketing events on the caller-visible stream)
@@ -988,8 +1011,12 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
         CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, sIn));
         if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
     }
+    // about 1 MB per piece: fine enough that the first chunk waits for little more than its own
+    // letters, coarse enough that small batches are one copy per sequence set
+    const int IN_PIECES = (int)std::max<size_t>(1, std::min<size_t>(MAX_IN_PIECES, (b1 + b2) >> 20));
+    ctx->in_pieces = IN_PIECES;
     auto upload_piece = [&](int k) -> int {
-        // piece k = letters [t*k/8, t*(k+1)/8) -> the bytes that hold them (edges may be sent twice)
+        // piece k = letters [t*k/P, t*(k+1)/P) -> the bytes that hold them (edges may be sent twice)
         const int64_t a0 = (t1 * k / IN_PIECES) * bits / 8, a1 = ((t1 * (k + 1) / IN_PIECES) * bits + 7) / 8;
         const int64_t c0 = (t2 * k / IN_PIECES) * bits / 8, c1 = ((t2 * (k + 1) / IN_PIECES) * bits + 7) / 8;
         if (a1 > a0) CK(cudaMemcpyAsync((uint8_t *)ctx->d_s1.p + a0, s1 + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, sIn));
@@ -999,7 +1026,7 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     };
     // only the first pieces go out before planning: the copy engine works in issue order and the
     // (small) tile-descriptor upload of a non-uniform plan must not queue behind the whole batch
-    constexpr int EARLY = 2;
+    const int EARLY = std::max(1, IN_PIECES / 4);
     for (int k = 0; k < EARLY; ++k)
         if ((rc = upload_piece(k))) return rc;
     ht0.lap("align: enqueue uploads");
@@ -1013,7 +1040,7 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
         if ((rc = upload_piece(k))) return rc;
     ht.lap("align: plan total");
     HostIO io;
-    io.total1 = t1; io.total2 = t2;
+    io.total1 = t1; io.total2 = t2; io.pieces = IN_PIECES;
     io.s1 = s1; io.s2 = s2; io.off1 = s1_off; io.off2 = s2_off; io.ops_off = out_ops_off;
     io.cost = out_cost; io.len = out_ops_len; io.status = out_status; io.ops = out_ops;
     rc = run_pipeline(ctx, (const uint8_t *)ctx->d_s1.p, implicit ? nullptr : (const int64_t *)ctx->d_off1.p,
