@@ -83,9 +83,11 @@ def _align_one_replay(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: 
     return ops, cost
 
 
-#: pairs with at least this many DP cells go to the whole-chip band pipeline with
-#: linear-space traceback (ga_align_long) instead of the one-warp batched kernel
-LONG_PAIR_CELLS = 1 << 22
+#: a single pair with at least this many DP cells goes to the whole-chip band pipeline with
+#: linear-space traceback (ga_align_long) instead of the one-warp batched kernel.  Measured
+#: latency per call (tools/probe_single_pair.py): 300 x 300 0.32 vs 0.34 ms, 1000 x 1000 0.67 vs
+#: 1.54 ms, 2000 x 2000 0.91 vs 5.2 ms -- the band pipeline wins from ~250 k cells on.
+LONG_PAIR_CELLS = 1 << 18
 
 
 def _align_one_f64(seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost, device: int = 0):
