@@ -322,6 +322,26 @@ def run_long(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this rank's host thread to the CPU cores NVML reports as local to its GPU, BEFORE any
+    pinned buffer is allocated (first touch then places the pages on that NUMA node).  With eight
+    ranks the end-to-end copies otherwise cross sockets.  Returns the core count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -334,6 +354,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device: globalign_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else None
     name = args.workload
     n_total = args.pairs * world if args.pairs else DEFAULT_PAIRS[name] * (world if name != "cfg5" else 1)
     scaling = "strong" if (name == "cfg5" and not args.pairs) else "weak"
@@ -503,7 +524,7 @@ def run_ours(args, rank, world, local_rank):
                    "fill_kernel": info["fill_kernel"], "chunks": info["n_chunks"],
                    "pipeline": "walk of chunk c overlaps fill of chunk c+1 (2 fill + 2 walk streams); "
                                "kernels_ms / roofline are from a serial (non-overlapped) plan"},
-        "clocks": clocks, "wall_ms_timed_region": wall_ms,
+        "clocks": clocks, "wall_ms_timed_region": wall_ms, "host_cores_bound_rank0": numa_cores,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms,
                 "input": "%d-bit letters, pinned host memory, %s" % (
