@@ -52,3 +52,12 @@ def test_product_never_imports_oracle():
         assert "import oracle" not in src and "from oracle" not in src, p
     for p in (ROOT / "globalign_b200" / "csrc").glob("*"):
         assert "oracle" not in p.read_text().lower() or p.name == "Makefile", p
+
+
+def test_every_exported_symbol_is_mapped_in_integration_md():
+    """INTEGRATION.md's table (C-ABI entry point <-> reference interface it replaces) names every
+    symbol the header declares."""
+    from pathlib import Path
+    text = (Path(__file__).resolve().parents[1] / "INTEGRATION.md").read_text()
+    missing = [e for e in _native.EXPORTS if e not in text and not (e.startswith("ga_ctx_") and "ga_ctx_*" in text)]
+    assert not missing, missing
