@@ -121,12 +121,16 @@ class Scheme:
     def dense_for(self, alphabet) -> DenseScheme:
         """Dense tables over `alphabet` (sorted letters of the whole batch)."""
         if self.scoring_mat is not None:
-            letters = [k for k in self.costing_mat if k != GAP]
             missing = set(alphabet).difference(self.scoring_mat.keys())
             if missing:
                 raise RuntimeError(
                     f"common_alphabet contains values not in scoring_mat_keys, e.g. {missing}.  "
                     f"Please check your sequences and your scoring matrix.")
+            # tables over the letters that occur (in the matrix's own order): BLOSUM62 has 24 rows,
+            # protein reads use 20 -- smaller tables keep the bank-conflict-free kernel at three
+            # blocks per SM.  max_cost stays the maximum of the WHOLE matrix (globaligner.py:258).
+            present = set(alphabet)
+            letters = [k for k in self.costing_mat if k != GAP and k in present]
             return DenseScheme(self.costing_mat, self.gap_open_cost, letters)
         _, cm = start.simple_scheme_matrices(self.branch, list(alphabet), self.scoring, self.costing)
         return DenseScheme(cm, self.gap_open_cost)

@@ -29,6 +29,7 @@ struct KernelCfg {
     const char *name;
     LayInfo lay;
     bool simple;
+    bool banked;     // packed table kernel with the lane-replicated cost table
     const void *fill_fn;
     void (*launch_fill)(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
                         const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const int *perm,
@@ -41,14 +42,14 @@ struct KernelCfg {
                         const long long *ops_off, int *out_len, int *out_status);
 };
 
-template <bool P, bool S, int R, int G>
+template <bool P, bool S, int R, int G, bool B>
 static void launch_fill_t(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
                           const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const int *perm,
                           const uint8_t *s1,
                           const long long *off1, const uint8_t *s2, const long long *off2,
                           uint4 *codes, int2 *bnd, int bnd_stride, int sb_stride, int *out_cost,
                           int persistent) {
-    fill_kernel<P, S, R, G><<<grid, 128, smem, st>>>(sc, tiles, ut, n_tiles, counter, perm, s1, off1, s2, off2,
+    fill_kernel<P, S, R, G, B><<<grid, 128, smem, st>>>(sc, tiles, ut, n_tiles, counter, perm, s1, off1, s2, off2,
                                                      codes, bnd, bnd_stride, sb_stride, out_cost, persistent);
 }
 template <bool P, int R, int G>
@@ -60,14 +61,15 @@ static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *
     walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, ut, pair_lo, n_pairs, perm, s1, off1, s2, off2, codes,
                                                out_ops, ops_off, out_len, out_status);
 }
-template <bool P, bool S, int R, int G>
+template <bool P, bool S, int R, int G, bool B = false>
 static KernelCfg make_cfg(const char *name) {
     KernelCfg c;
     c.name = name;
     c.lay = lay_info<P, R, G>();
     c.simple = S;
-    c.fill_fn = (const void *)fill_kernel<P, S, R, G>;
-    c.launch_fill = launch_fill_t<P, S, R, G>;
+    c.banked = B;
+    c.fill_fn = (const void *)fill_kernel<P, S, R, G, B>;
+    c.launch_fill = launch_fill_t<P, S, R, G, B>;
     c.launch_walk = launch_walk_t<P, R, G>;
     return c;
 }
@@ -95,6 +97,8 @@ static const std::vector<KernelCfg> &registry() {
         make_cfg<true, false, 8, 32>("fill_p16t_r8_g32"),
         make_cfg<true, false, 12, 32>("fill_p16t_r12_g32"),
         make_cfg<true, false, 16, 32>("fill_p16t_r16_g32"),
+        // ... with the cost table replicated per lane (no shared-memory bank conflicts)
+        make_cfg<true, false, 16, 32, true>("fill_p16b_r16_g32"),
         // int32, simple schemes (compare instead of table)
         make_cfg<false, true, 8, 8>("fill_i32s_r8_g8"),
         make_cfg<false, true, 8, 16>("fill_i32s_r8_g16"),
@@ -432,9 +436,17 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
         }
         return find_cfg(maxM <= 64 ? "fill_i32s_r8_g8" : maxM <= 128 ? "fill_i32s_r8_g16" : "fill_i32s_r8_g32");
     }
-    if (!(flags & GA_F_FORCE_GENERIC) && fits16u())
-        return find_cfg(maxM <= 64 ? "fill_p16t_r8_g8" : maxM <= 128 ? "fill_p16t_r8_g16"
-                        : maxM <= 256 ? "fill_p16t_r8_g32" : "fill_p16t_r16_g32");
+    if (!(flags & GA_F_FORCE_GENERIC) && fits16u()) {
+        if (maxM > 256) {
+            // the lane-replicated table needs (A+1)^2 * 128 bytes per block; it pays (+4.5 % on
+            // cfg3) only while three blocks still fit an SM, i.e. for alphabets of ~20 letters
+            const size_t tab = ((size_t)(sc.A + 1) * (sc.A + 1) * 32 + (sc.A + 1)) * 4;
+            const size_t stage = (size_t)4 * (((size_t)maxN + 32 + 2 + 1 + 16 + 15) & ~(size_t)15) * 4;
+            if (3 * (tab + stage + 1024) <= 224 * 1024) return find_cfg("fill_p16b_r16_g32");
+            return find_cfg("fill_p16t_r16_g32");
+        }
+        return find_cfg(maxM <= 64 ? "fill_p16t_r8_g8" : maxM <= 128 ? "fill_p16t_r8_g16" : "fill_p16t_r8_g32");
+    }
     return find_cfg(maxM <= 64 ? "fill_i32t_r8_g8" : maxM <= 128 ? "fill_i32t_r8_g16" : "fill_i32t_r8_g32");
 }
 
@@ -539,6 +551,7 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         const size_t A = (size_t)ctx->sc.A;
         table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
                          : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
+        if (cfg->banked) table = (((A + 1) * (A + 1) * 32 + (A + 1)) * 4 + 15) & ~(size_t)15;
     }
     ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
     if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
@@ -570,7 +583,8 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     {
         const double tiles_per_warp = (double)n_tiles / std::max(1, ctx->grid * warps);
         // a boundary costs more when tiles and walks are long (cfg3: ~0.4 ms, cfg2: ~0.05 ms)
-        const double depth = (ctx->plan_for_io && maxM + maxN <= 512) ? 8.0 : 12.0;
+        const bool short_pairs = maxM + maxN <= 512;
+        const double depth = short_pairs ? (ctx->plan_for_io ? 8.0 : 12.0) : (ctx->plan_for_io ? 20.0 : 40.0);
         int mid = (int)std::max(1.0, std::min(ctx->plan_for_io ? 6.0 : 4.0, tiles_per_warp / depth + 0.5));
         if (const char *e = getenv("GA_CHUNKS")) mid = std::max(1, atoi(e));
         if (serial) {

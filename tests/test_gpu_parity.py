@@ -19,7 +19,8 @@ PACKED_CFGS = ["fill_p16_r7_g8", "fill_p16_r10_g8", "fill_p16_r13_g8", "fill_p16
                "fill_p16_r16_g16", "fill_p16_r8_g32", "fill_p16_r16_g32"]
 I32S_CFGS = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
 I32T_CFGS = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]
-P16T_CFGS = ["fill_p16t_r8_g8", "fill_p16t_r8_g16", "fill_p16t_r8_g32", "fill_p16t_r12_g32", "fill_p16t_r16_g32"]
+P16T_CFGS = ["fill_p16t_r8_g8", "fill_p16t_r8_g16", "fill_p16t_r8_g32", "fill_p16t_r12_g32", "fill_p16t_r16_g32",
+             "fill_p16b_r16_g32"]
 
 
 @pytest.fixture(autouse=True)
@@ -242,7 +243,8 @@ def test_automatic_kernel_choice():
     prot = synth.protein_varlen(8, 3000)
     ctx.set_scheme(batch.Scheme(**synth.SCHEMES["cfg3"]).dense_for(sorted(synth.AMINO)))
     # proteins up to 1000 residues under BLOSUM62 fit the unsigned packed table kernels ...
-    assert ctx.plan_batch(prot.off1, prot.off2)["fill_kernel"].startswith("fill_p16t")
+    # (20 letters present: the lane-replicated table still leaves three blocks per SM)
+    assert ctx.plan_batch(prot.off1, prot.off2)["fill_kernel"] == "fill_p16b_r16_g32"
     assert ctx.plan_batch(prot.off1, prot.off2, flags=_native.GA_F_FORCE_GENERIC)["fill_kernel"].startswith("fill_i32t")
     # ... longer ones do not: 4 * 16 * 1100 > 65535
     off = np.array([0, 1100, 2200], dtype=np.int64)
@@ -276,6 +278,11 @@ def test_packed_table_kernel_at_the_edge_of_its_value_range():
             np.array(s2, dtype=np.uint8), np.array(o2, dtype=np.int64))
     ctx = _native.Context(0)
     ctx.set_scheme(dense)
+    out = ctx.align_batch(*data)
+    assert ctx.plan_info()["fill_kernel"] == "fill_p16b_r16_g32"
+    _compare_with_oracle(*data, dense, out)
+    # the same through the plain-table kernel (what alphabets above ~21 letters get)
+    os.environ["GA_FORCE_CFG"] = "fill_p16t_r16_g32"
     out = ctx.align_batch(*data)
     assert ctx.plan_info()["fill_kernel"] == "fill_p16t_r16_g32"
     _compare_with_oracle(*data, dense, out)

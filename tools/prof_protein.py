@@ -9,6 +9,11 @@ from globalign_b200.batch import Scheme
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 b = synth.workload("cfg3", n_pairs=n)
 dense = Scheme(**synth.SCHEMES["cfg3"]).dense_for(sorted(synth.AMINO))
+if os.environ.get("PROT_LETTERS") == "20":      # tables over the 20 letters that occur, not the matrix's 24
+    from globalign_b200 import lowering
+    sch = Scheme(**synth.SCHEMES["cfg3"])
+    dense = lowering.DenseScheme(sch.costing_mat, sch.gap_open_cost, letters=sorted(synth.AMINO))
+    dense.max_cost = int(max(max(row.values()) for row in sch.costing_mat.values()))
 remap = __import__("numpy").array([dense.index[ch] for ch in b.alphabet], dtype="uint8")
 s1, s2 = remap[b.s1], remap[b.s2]
 dev = torch.device("cuda", 0)
