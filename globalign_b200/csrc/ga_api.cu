@@ -29,7 +29,7 @@ struct KernelCfg {
     const char *name;
     LayInfo lay;
     bool simple;
-    bool banked;     // packed table kernel with the lane-replicated cost table
+    int banked;      // packed table kernel with the lane-replicated cost table: bytes per entry (0 = plain table)
     const void *fill_fn;
     void (*launch_fill)(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
                         const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const int *perm,
@@ -42,7 +42,7 @@ struct KernelCfg {
                         const long long *ops_off, int *out_len, int *out_status);
 };
 
-template <bool P, bool S, int R, int G, bool B>
+template <bool P, bool S, int R, int G, int B>
 static void launch_fill_t(int grid, size_t smem, cudaStream_t st, const SchemeDev &sc,
                           const TileDesc *tiles, const UniformTiles &ut, int n_tiles, int *counter, const int *perm,
                           const uint8_t *s1,
@@ -61,7 +61,7 @@ static void launch_walk_t(cudaStream_t st, const SchemeDev &sc, const TileDesc *
     walk_kernel<P, R, G><<<grid, 128, 0, st>>>(sc, tiles, ut, pair_lo, n_pairs, perm, s1, off1, s2, off2, codes,
                                                out_ops, ops_off, out_len, out_status);
 }
-template <bool P, bool S, int R, int G, bool B = false>
+template <bool P, bool S, int R, int G, int B = 0>
 static KernelCfg make_cfg(const char *name) {
     KernelCfg c;
     c.name = name;
@@ -98,7 +98,8 @@ static const std::vector<KernelCfg> &registry() {
         make_cfg<true, false, 12, 32>("fill_p16t_r12_g32"),
         make_cfg<true, false, 16, 32>("fill_p16t_r16_g32"),
         // ... with the cost table replicated per lane (no shared-memory bank conflicts)
-        make_cfg<true, false, 16, 32, true>("fill_p16b_r16_g32"),
+        make_cfg<true, false, 16, 32, 4>("fill_p16b_r16_g32"),
+        make_cfg<true, false, 16, 32, 2>("fill_p16h_r16_g32"),      // 16-bit entries
         // int32, simple schemes (compare instead of table)
         make_cfg<false, true, 8, 8>("fill_i32s_r8_g8"),
         make_cfg<false, true, 8, 16>("fill_i32s_r8_g16"),
@@ -440,9 +441,10 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
         if (maxM > 256) {
             // the lane-replicated table needs (A+1)^2 * 128 bytes per block; it pays (+4.5 % on
             // cfg3) only while three blocks still fit an SM, i.e. for alphabets of ~20 letters
-            const size_t tab = ((size_t)(sc.A + 1) * (sc.A + 1) * 32 + (sc.A + 1)) * 4;
-            const size_t stage = (size_t)4 * (((size_t)maxN + 32 + 2 + 1 + 16 + 15) & ~(size_t)15) * 4;
-            if (3 * (tab + stage + 1024) <= 224 * 1024) return find_cfg("fill_p16b_r16_g32");
+            const size_t ent = (size_t)(sc.A + 1) * (sc.A + 1) * 32;
+            const size_t stage = (size_t)4 * (((size_t)maxN + 32 + 2 + 1 + 16 + 15) & ~(size_t)15) * 4 + 1024;
+            if (3 * (ent * 4 + stage) <= 224 * 1024) return find_cfg("fill_p16b_r16_g32");
+            if (3 * (ent * 2 + stage) <= 224 * 1024) return find_cfg("fill_p16h_r16_g32");   // 16-bit entries
             return find_cfg("fill_p16t_r16_g32");
         }
         return find_cfg(maxM <= 64 ? "fill_p16t_r8_g8" : maxM <= 128 ? "fill_p16t_r8_g16" : "fill_p16t_r8_g32");
@@ -551,7 +553,7 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         const size_t A = (size_t)ctx->sc.A;
         table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
                          : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
-        if (cfg->banked) table = (((A + 1) * (A + 1) * 32 + (A + 1)) * 4 + 15) & ~(size_t)15;
+        if (cfg->banked) table = ((A + 1) * (A + 1) * 32 * (size_t)cfg->banked + (A + 1) * 4 + 15) & ~(size_t)15;
     }
     ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
     if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");

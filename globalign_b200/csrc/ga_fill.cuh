@@ -83,7 +83,10 @@ struct VOps<true, false> {
 // lives in word (b * AP + a) * 32 + L, i.e. always in shared-memory bank L -- so the two table
 // loads of a cell never conflict (the plain layout averages 3.1 wavefronts per load on random
 // protein letters and runs the shared-memory pipe at 78 %).  Costs AP^2 * 128 bytes per block.
-template <bool PACKED, bool SIMPLE, int R, int G, bool BANKED = false>
+// BANKED = 4: 32-bit entries, one wavefront per load.  BANKED = 2: 16-bit entries (half the memory,
+// alphabets up to ~28 letters at three blocks per SM); lanes 2k and 2k+1 then share a bank and
+// conflict when their entries differ in more than parity: ~1.5 wavefronts per load.
+template <bool PACKED, bool SIMPLE, int R, int G, int BANKED = 0>
 __global__ void __launch_bounds__(128)
 fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const UniformTiles ut, int n_tiles,
             int *tile_counter, const int *__restrict__ perm,
@@ -93,7 +96,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
             int *__restrict__ out_cost, int persistent) {
     using L = Lay<PACKED, R, G>;
     constexpr bool PT = PACKED && !SIMPLE;       // packed table kernel: two pairs per register, costs from tables
-    constexpr bool PB = PT && BANKED;            // ... with the lane-replicated (conflict-free) table
+    constexpr bool PB = PT && BANKED != 0;       // ... with the lane-replicated (conflict-free) table
+    constexpr int EB = BANKED == 2 ? 2 : 4;      // PB: bytes per table entry
     using V = VOps<PACKED, PT>;
     using BT = typename std::conditional<PACKED, uint32_t, uint8_t>::type;
     static_assert(G >= 1 && G <= 32 && R >= 1, "bad configuration");
@@ -105,16 +109,19 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const int AP = sc.A + 1;                     // PT: letters 0..A-1 plus the zero-cost padding letter A
     unsigned pt_lo = 0, pt_hi = 0;               // PT: shared-space byte addresses of the two tables
     if (PB) {
-        unsigned *tab = reinterpret_cast<unsigned *>(smem_raw);          // [b][a][lane]
-        const int n_words = AP * AP * 32;
+        unsigned *tab = reinterpret_cast<unsigned *>(smem_raw);          // [b][a][lane], EB bytes per entry
+        const int n_ent = AP * AP * 32;
+        const int n_words = n_ent * EB / 4;
         s_gh = reinterpret_cast<int *>(tab + n_words);
-        for (int k = threadIdx.x; k < n_words; k += blockDim.x) {
+        for (int k = threadIdx.x; k < n_ent; k += blockDim.x) {
             const int e = k >> 5, b = e / AP, a = e - b * AP;
-            tab[k] = (a < sc.A && b < sc.A) ? (unsigned)sc.sub4[a * sc.A + b] : 0u;
+            const unsigned v = (a < sc.A && b < sc.A) ? (unsigned)sc.sub4[a * sc.A + b] : 0u;
+            if (EB == 4) tab[k] = v;
+            else reinterpret_cast<unsigned short *>(tab)[k] = (unsigned short)v;
         }
         for (int k = threadIdx.x; k < AP; k += blockDim.x) s_gh[k] = k < sc.A ? sc.gh4t[k] : 1;
         table_bytes = ((size_t)(n_words + AP) * 4 + 15) & ~(size_t)15;
-        pt_lo = (unsigned)__cvta_generic_to_shared(tab) + 4u * (threadIdx.x & 31);   // my bank
+        pt_lo = (unsigned)__cvta_generic_to_shared(tab) + (unsigned)EB * (threadIdx.x & 31);   // my column
         pt_hi = pt_lo;
         __syncthreads();
     } else if (PT) {
@@ -247,8 +254,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                         const int row = ib + r;
                         const int la = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
                         const int lb = row < mB ? (int)ld_letter(s1, b1 + row, sc.seq_bits) : sc.A;
-                        aw[r] = (PB ? 128u : 4u) * (unsigned)la;      // byte offset of the letter in a table row
-                        awB[r] = (PB ? 128u : 4u) * (unsigned)lb;
+                        aw[r] = (PB ? 32u * EB : 4u) * (unsigned)la;  // byte offset of the letter in a table row
+                        awB[r] = (PB ? 32u * EB : 4u) * (unsigned)lb;
                         gvT[r] = (unsigned)sc.gv4t[la] | ((unsigned)sc.gv4t[lb] << 16);
                         gvrA[r] = sc.gv_raw[la];
                         gvrB[r] = sc.gv_raw[lb];
@@ -374,8 +381,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                             if (PT) {
                                 const unsigned la = bv & 0xFFFFu, lb = bv >> 16;
                                 ghT = (unsigned)s_gh[la] | ((unsigned)s_gh[lb] << 16);
-                                rowA = pt_lo + la * (unsigned)((PB ? 128 : 4) * AP);
-                                rowB = pt_hi + lb * (unsigned)((PB ? 128 : 4) * AP);
+                                rowA = pt_lo + la * (unsigned)((PB ? 32 * EB : 4) * AP);
+                                rowB = pt_hi + lb * (unsigned)((PB ? 32 * EB : 4) * AP);
                             } else {
                                 ghT = SIMPLE ? ghTc : (unsigned)s_gh[bv];
                             }
@@ -388,8 +395,16 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                                 if (PT) {
                                     // two table loads (address adds as IMADs) and one three-input add
                                     unsigned sa, sb2;
-                                    asm("ld.shared.u32 %0, [%1];" : "=r"(sa) : "r"(aw[r] * K1 + rowA));
-                                    asm("ld.shared.u32 %0, [%1];" : "=r"(sb2) : "r"(awB[r] * K1 + rowB));
+                                    if (PB && EB == 2) {
+                                        unsigned short ha, hb2;
+                                        asm("ld.shared.u16 %0, [%1];" : "=h"(ha) : "r"(aw[r] * K1 + rowA));
+                                        asm("ld.shared.u16 %0, [%1];" : "=h"(hb2) : "r"(awB[r] * K1 + rowB));
+                                        sa = ha;
+                                        sb2 = hb2;
+                                    } else {
+                                        asm("ld.shared.u32 %0, [%1];" : "=r"(sa) : "r"(aw[r] * K1 + rowA));
+                                        asm("ld.shared.u32 %0, [%1];" : "=r"(sb2) : "r"(awB[r] * K1 + rowB));
+                                    }
                                     d0 = PB ? diag + sa + (sb2 << 16) : diag + sa + sb2;
                                 } else if (PACKED) {
                                     d0 = __vminu2(aw[r] ^ bv, 0x00010001u) * mm4 + diag;

@@ -20,7 +20,7 @@ PACKED_CFGS = ["fill_p16_r7_g8", "fill_p16_r10_g8", "fill_p16_r13_g8", "fill_p16
 I32S_CFGS = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
 I32T_CFGS = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]
 P16T_CFGS = ["fill_p16t_r8_g8", "fill_p16t_r8_g16", "fill_p16t_r8_g32", "fill_p16t_r12_g32", "fill_p16t_r16_g32",
-             "fill_p16b_r16_g32"]
+             "fill_p16b_r16_g32", "fill_p16h_r16_g32"]
 
 
 @pytest.fixture(autouse=True)

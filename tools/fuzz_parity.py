@@ -23,7 +23,7 @@ PACKED = ["fill_p16_r7_g8", "fill_p16_r10_g8", "fill_p16_r13_g8", "fill_p16_r16_
 I32S = ["fill_i32s_r8_g8", "fill_i32s_r8_g16", "fill_i32s_r8_g32"]
 I32T = ["fill_i32t_r8_g8", "fill_i32t_r8_g16", "fill_i32t_r8_g32"]
 P16T = ["fill_p16t_r8_g8", "fill_p16t_r8_g16", "fill_p16t_r8_g32", "fill_p16t_r12_g32", "fill_p16t_r16_g32",
-             "fill_p16b_r16_g32"]
+             "fill_p16b_r16_g32", "fill_p16h_r16_g32"]
 
 
 def dense_simple(rng, A):
