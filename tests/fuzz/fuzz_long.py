@@ -9,9 +9,9 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tools"))
+sys.path.insert(0, str(ROOT / "tests" / "fuzz"))
 from globalign_b200 import _native  # noqa: E402
 from oracle import c_oracle  # noqa: E402
 from fuzz_parity import dense_simple, dense_table  # noqa: E402
