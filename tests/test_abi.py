@@ -61,3 +61,12 @@ def test_every_exported_symbol_is_mapped_in_integration_md():
     text = (Path(__file__).resolve().parents[1] / "INTEGRATION.md").read_text()
     missing = [e for e in _native.EXPORTS if e not in text and not (e.startswith("ga_ctx_") and "ga_ctx_*" in text)]
     assert not missing, missing
+
+
+def test_tools_do_not_use_the_oracle():
+    """tools/ holds tuning and profiling drivers of the PRODUCT; everything that needs the oracle
+    lives under tests/ (tests/fuzz/, tests/golden/)."""
+    from pathlib import Path
+    for p in (Path(__file__).resolve().parents[1] / "tools").glob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p
