@@ -31,7 +31,7 @@ EXPORTS = (
     "ga_ctx_set_stream", "ga_ctx_set_scratch_limit", "ga_set_scheme", "ga_align_batch",
     "ga_plan_batch", "ga_run_batch", "ga_sync", "ga_get_plan_info", "ga_get_timing",
     "ga_fill_values", "ga_alu_peak", "ga_align_long", "ga_align_replay", "ga_align_batch_uniform",
-    "ga_fill_values_f64", "ga_align_f64",
+    "ga_fill_values_f64", "ga_align_f64", "ga_walk_values", "ga_walk_values_f64",
 )
 
 
@@ -93,6 +93,10 @@ def lib():
                                C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     L.ga_align_replay.argtypes = [vp, vp, i64, vp, i64, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
                                   C.POINTER(i32), C.POINTER(i32)]
+    L.ga_walk_values.argtypes = [vp, vp, i64, vp, i64, vp, vp, i64, C.POINTER(i32), vp, C.POINTER(i64),
+                                 C.POINTER(i32), C.POINTER(i32)]
+    L.ga_walk_values_f64.argtypes = [vp, i32, vp, vp, vp, f64, f64, vp, i64, vp, i64, vp, vp, i64,
+                                     C.POINTER(f64), vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     for name in EXPORTS:
         if name not in ("ga_last_error",):
             getattr(L, name).restype = C.c_int
@@ -274,6 +278,40 @@ class Context:
                                          None if draws is None else _ptr(draws), 0 if draws is None else len(draws),
                                          C.byref(cost), _ptr(packed), C.byref(nops), C.byref(neval),
                                          C.byref(status)))
+        return cost.value, unpack_ops(packed, 0, nops.value), neval.value, status.value
+
+    def walk_values(self, s1, s2, table, draws=None):
+        """The traceback alone on the caller's int32 (m+1, n+1, 3) value table
+        -> (cost, ops walk order, n_eval, status)."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        m, n = len(s1), len(s2)
+        assert table.dtype == np.int32 and table.flags.c_contiguous and table.shape == (m + 1, n + 1, 3)
+        if draws is not None:
+            draws = np.ascontiguousarray(draws, dtype=np.uint16)
+        packed = np.zeros(4 * ((m + n + 15) // 16) + 16, dtype=np.uint8)
+        cost, nops, neval, status = C.c_int32(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self._L.ga_walk_values(self._h, _ptr(s1), m, _ptr(s2), n, _ptr(table),
+                                           None if draws is None else _ptr(draws),
+                                           0 if draws is None else len(draws), C.byref(cost), _ptr(packed),
+                                           C.byref(nops), C.byref(neval), C.byref(status)))
+        return cost.value, unpack_ops(packed, 0, nops.value), neval.value, status.value
+
+    def walk_values_f64(self, dense, s1, s2, table, draws=None):
+        """The same for a float64 table and float-valued penalties (dense: DenseSchemeF64)."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        m, n = len(s1), len(s2)
+        assert table.dtype == np.float64 and table.flags.c_contiguous and table.shape == (m + 1, n + 1, 3)
+        if draws is not None:
+            draws = np.ascontiguousarray(draws, dtype=np.uint16)
+        packed = np.zeros(4 * ((m + n + 15) // 16) + 16, dtype=np.uint8)
+        cost, nops, neval, status = C.c_double(0.0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self._L.ga_walk_values_f64(self._h, dense.A, _ptr(dense.sub), _ptr(dense.gap_h),
+                                               _ptr(dense.gap_v), dense.gap_open, dense.max_cost, _ptr(s1), m,
+                                               _ptr(s2), n, _ptr(table), None if draws is None else _ptr(draws),
+                                               0 if draws is None else len(draws), C.byref(cost), _ptr(packed),
+                                               C.byref(nops), C.byref(neval), C.byref(status)))
         return cost.value, unpack_ops(packed, 0, nops.value), neval.value, status.value
 
     def alu_peak(self, mode: int) -> float:

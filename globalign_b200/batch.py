@@ -270,7 +270,40 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
     else:
         from .parallel import align_on_devices
         cost, ops, ops_off, ops_len, status = align_on_devices(on_device, cat1, off1, cat2, off2, list(devices))
+    _realign_single_letter_pairs(up1, up2, dense, cat1, off1, cat2, off2, scheme, device if not devices else devices[0],
+                                 cost, ops, ops_off, ops_len, status)
     return BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme)
+
+
+def _realign_single_letter_pairs(up1, up2, dense, cat1, off1, cat2, off2, scheme, device,
+                                 cost, ops, ops_off, ops_len, status):
+    """Simple schemes build their matrices over the letters of the PAIR (start.py:319-343), so a
+    pair made of one repeated letter has no mismatch entry and a smaller max_cost -- hence a
+    smaller boundary sentinel (globaligner.py:777) -- than the batch-wide tables give it.  The
+    sentinel only matters when max(m, n) <= gap_open_cost, where the
+    reference's result is sentinel-dependent (or undefined): those few pairs are re-aligned one
+    by one with their own matrices so that the batch call agrees with find_global_alignment."""
+    if scheme.scoring_mat is not None or dense.A < 2:
+        return
+    m_len, n_len = np.diff(off1), np.diff(off2)
+    short = np.flatnonzero(np.maximum(m_len, n_len) <= scheme.gap_open_cost)
+    if short.size == 0:
+        return
+    ctx = _native.default_context(device)
+    for k in short:
+        a = cat1[off1[k]:off1[k + 1]]
+        b = cat2[off2[k]:off2[k + 1]]
+        if not (a.min() == a.max() == b.min() == b.max()):
+            continue
+        s1, s2 = up1[int(k)], up2[int(k)]
+        _, cm = scheme.matrices_for(s1, s2)
+        own = DenseScheme(cm, scheme.gap_open_cost)
+        ctx.set_scheme(own)
+        c1, o1, _, l1, st1 = ctx.align_batch(own.encode(s1), np.array([0, len(s1)], dtype=np.int64),
+                                             own.encode(s2), np.array([0, len(s2)], dtype=np.int64))
+        cost[k], ops_len[k], status[k] = c1[0], l1[0], st1[0]
+        ops[ops_off[k]:ops_off[k] + len(o1)] = o1
+    ctx.set_scheme(dense)
 
 
 def read_pairs_from_fasta(fasta_path, fasta_path_2=None):

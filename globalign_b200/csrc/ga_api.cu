@@ -177,6 +177,8 @@ struct ga_ctx {
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
     // long-pair path
     DevBuf l_colsum, l_rowsum, l_brow, l_vchk, l_prog, l_misc, l_xrow, l_meta, l_seg;
+    // single-pair value-table paths (ga_fill_values, ga_align_replay): kept between calls
+    DevBuf v_s1, v_s2, v_tab, v_draws, v_ops, v_misc;
     // timing
     cudaEvent_t ev[8] = {};
     std::vector<ChunkEvents> cev;
@@ -285,7 +287,7 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
                       &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
                       &ctx->d_opsoff, &ctx->d_len, &ctx->d_status, &ctx->l_colsum, &ctx->l_rowsum,
                       &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc, &ctx->l_xrow, &ctx->l_meta,
-                      &ctx->l_seg})
+                      &ctx->l_seg, &ctx->v_s1, &ctx->v_s2, &ctx->v_tab, &ctx->v_draws, &ctx->v_ops, &ctx->v_misc})
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->in_piece) if (e) cudaEventDestroy(e);
@@ -391,27 +393,32 @@ extern "C" int ga_set_scheme(ga_ctx *ctx, int A, const int32_t *sub, const int32
     ctx->h_gv.assign(gap_v, gap_v + A);
     ctx->have_scheme = true;
     ctx->have_plan = false;
+    ctx->timing_valid = false;
     return GA_OK;
 }
 
 // ------------------------------------------------------------------ planner
-static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32_t flags) {
+// Does the value range of a packed kernel hold these lengths?
+static bool cfg_fits16(const ga_ctx *ctx, const KernelCfg *c, int maxM, int maxN) {
     const SchemeDev &sc = ctx->sc;
-    // largest value any cell (padding included) can take, times 4 plus tag, must fit int16
-    auto fits16 = [&](const KernelCfg *c) {
+    const long long big = (long long)(sc.max_cost + 1) * std::max(maxM, maxN);
+    if (c->simple) {
+        // largest value any cell (padding included) can take, times 4 plus tag, must fit int16
         const int band = c->lay.BAND, G = c->lay.G;
         const long long Mp = ((maxM + band - 1) / band) * (long long)band, Np = maxN + G;
-        const long long big = (long long)(sc.max_cost + 1) * std::max(maxM, maxN);
         const long long vmax = big + (std::min(Mp, Np) + 2) * sc.max_cost + 3LL * sc.o;
         return 4 * vmax + 3 < 32767 && 4LL * sc.mm < 65536;
-    };
+    }
     // The packed table kernels compare UNSIGNED halves and give padded rows and columns a zero-cost
     // letter, so padded cells only copy values: h <= big + o (a path of max(i,j) steps plus one
     // gap open), L / U <= h + o + max_cost, their inputs d1 / d2 one more step cost.
-    auto fits16u = [&]() {
-        const long long big = (long long)(sc.max_cost + 1) * std::max(maxM, maxN);
-        return 4 * (big + 2LL * sc.o + 2LL * sc.max_cost) + 3 <= 65535 && sc.A <= 64;
-    };
+    return 4 * (big + 2LL * sc.o + 2LL * sc.max_cost) + 3 <= 65535 && sc.A <= 64;
+}
+
+static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32_t flags) {
+    const SchemeDev &sc = ctx->sc;
+    auto fits16 = [&](const KernelCfg *c) { return cfg_fits16(ctx, c, maxM, maxN); };
+    auto fits16u = [&]() { return cfg_fits16(ctx, find_cfg("fill_p16t_r8_g8"), maxM, maxN); };
     if (const char *force = getenv("GA_FORCE_CFG")) {      // tests and tuning
         const KernelCfg *c = find_cfg(force);
         if (!c || (c->simple && !sc.simple)) return nullptr;
@@ -450,6 +457,23 @@ static const KernelCfg *choose_cfg(const ga_ctx *ctx, int maxM, int maxN, uint32
         return find_cfg(maxM <= 64 ? "fill_p16t_r8_g8" : maxM <= 128 ? "fill_p16t_r8_g16" : "fill_p16t_r8_g32");
     }
     return find_cfg(maxM <= 64 ? "fill_i32t_r8_g8" : maxM <= 128 ? "fill_i32t_r8_g16" : "fill_i32t_r8_g32");
+}
+
+// dynamic shared memory of a fill kernel: cost table (table-driven schemes) + the staged seq_2
+// letters of every item of the block's four warps
+constexpr size_t SMEM_LIMIT = 200 * 1024;
+static size_t fill_smem_bytes(const ga_ctx *ctx, const KernelCfg *cfg, int maxN) {
+    const LayInfo &L = cfg->lay;
+    const size_t sb_stride = (size_t)(((maxN + L.G - 1 + L.S + 1 + 16) + 15) & ~15);
+    const size_t elt = L.packed ? 4 : 1;
+    size_t table = 0;
+    if (!cfg->simple) {
+        const size_t A = (size_t)ctx->sc.A;
+        table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
+                         : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
+        if (cfg->banked) table = ((A + 1) * (A + 1) * 32 * (size_t)cfg->banked + (A + 1) * 4 + 15) & ~(size_t)15;
+    }
+    return table + (size_t)4 * L.IPW * sb_stride * elt;
 }
 
 static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
@@ -521,6 +545,7 @@ static int plan_uniform(ga_ctx *ctx, int64_t m, int64_t n, int64_t n_pairs, uint
 static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
                        uint32_t flags, int maxM, int maxN, int minM, int minN, int64_t cells, HostTimer &ht) {
     for (float &v : ctx->ms) v = 0.f;
+    ctx->timing_valid = false;          // the chunk events now belong to a plan that has not run
     {
         const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
         if ((flags & GA_F_SEQ_2BIT) && (flags & GA_F_SEQ_4BIT)) return fail(ctx, GA_E_ARG, "choose one sequence packing");
@@ -532,6 +557,22 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     ht.lap("plan: scan pairs");
     const KernelCfg *cfg = choose_cfg(ctx, maxM, maxN, flags);
     if (!cfg) return fail(ctx, GA_E_ARG, "no usable kernel configuration (GA_FORCE_CFG names an unknown kernel or one whose value range / scheme kind does not fit)");
+    // choose_cfg looks at seq_1 only (rows); the seq_2 letters of every item of a warp are staged
+    // in shared memory, so a short seq_1 against a long seq_2 may not fit the few-lanes-per-group
+    // kernels (4 items per warp).  Fall back to wider groups of the same family, then from the
+    // packed to the int32 family (one byte per staged letter): n <= 32768 always fits the latter.
+    if (fill_smem_bytes(ctx, cfg, maxN) > SMEM_LIMIT && !getenv("GA_FORCE_CFG")) {
+        const KernelCfg *alt = nullptr;
+        for (int pass = 0; pass < 2 && !alt; ++pass)
+            for (const auto &c : registry()) {
+                if (c.simple != cfg->simple || c.banked) continue;
+                if (pass == 0 ? (c.lay.packed != cfg->lay.packed || c.lay.G <= cfg->lay.G) : (c.lay.packed != 0)) continue;
+                if (c.lay.packed && !cfg_fits16(ctx, &c, maxM, maxN)) continue;
+                if (fill_smem_bytes(ctx, &c, maxN) > SMEM_LIMIT) continue;
+                if (!alt || c.lay.G < alt->lay.G || (c.lay.G == alt->lay.G && c.lay.R > alt->lay.R)) alt = &c;
+            }
+        if (alt) cfg = alt;
+    }
     const LayInfo &L = cfg->lay;
     {   // int32 range
         const long long Mp = ((maxM + L.BAND - 1) / L.BAND) * (long long)L.BAND;
@@ -547,16 +588,8 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     const int warps = 4;
     ctx->sb_stride = ((maxN + L.G - 1 + L.S + 1 + 16) + 15) & ~15;
     ctx->bnd_stride = maxN + 8;
-    const size_t elt = L.packed ? 4 : 1;
-    size_t table = 0;
-    if (!cfg->simple) {
-        const size_t A = (size_t)ctx->sc.A;
-        table = L.packed ? ((2 * (A + 1) * (A + 1) + (A + 1)) * 4 + 15) & ~(size_t)15
-                         : (((A + 1) * A + A) * 4 + 15) & ~(size_t)15;
-        if (cfg->banked) table = ((A + 1) * (A + 1) * 32 * (size_t)cfg->banked + (A + 1) * 4 + 15) & ~(size_t)15;
-    }
-    ctx->smem = table + (size_t)warps * L.IPW * ctx->sb_stride * elt;
-    if (ctx->smem > 200 * 1024) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
+    ctx->smem = fill_smem_bytes(ctx, cfg, maxN);
+    if (ctx->smem > SMEM_LIMIT) return fail(ctx, GA_E_ARG, "sequences too long for the batched kernels' shared-memory staging");
     CK(cudaFuncSetAttribute(cfg->fill_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg->fill_fn, 128, ctx->smem));
@@ -1105,8 +1138,8 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     if (!s1 || !s2 || !out_cost || m < 1 || n < 1 || m > (1 << 28) || n > (1 << 28) ||
         (!cost_only && (!out_ops || !out_n_ops || !out_status)))
         return fail(ctx, GA_E_ARG, "bad arguments to ga_align_long");
-    ctx->sc.seq_bits = 8;               // this entry point takes one letter per byte
-    const SchemeDev &sc = ctx->sc;
+    SchemeDev sc = ctx->sc;             // a copy: this entry point takes one letter per byte, whatever
+    sc.seq_bits = 8;                    // packing the current batch plan (kept valid) was made for
     if (!sc.simple && sc.A > 64) return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
     {
         const long long big = (long long)(sc.max_cost + 1) * std::max(m, n);
@@ -1256,34 +1289,89 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
 }
 
 // ------------------------------------------------------------------ full value table (kernels: ga_values.cuh)
+// letters of a single pair must index the scheme's tables
+static int check_letters(ga_ctx *ctx, const uint8_t *s, int64_t len, const char *which) {
+    const int A = ctx->sc.A;
+    for (int64_t k = 0; k < len; ++k)
+        if (s[k] >= A) return fail(ctx, GA_E_ARG, "letter index out of range in %s", which);
+    return GA_OK;
+}
+
 extern "C" int ga_fill_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                               int keep_boundary, int32_t *table) {
     if (!ctx) return GA_E_ARG;
     if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
     if (!s1 || !s2 || !table || m < 1 || n < 1 || (m + 1) * (n + 1) > (int64_t)50'000'000)
         return fail(ctx, GA_E_ARG, "ga_fill_values is for small pairs");
+    int rc;
+    if ((rc = check_letters(ctx, s1, m, "seq_1")) || (rc = check_letters(ctx, s2, n, "seq_2"))) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t tb = (size_t)(m + 1) * (n + 1) * 3 * 4;
-    uint8_t *d1 = nullptr, *d2 = nullptr;
-    int *dt = nullptr;
-    CK(cudaMalloc(&d1, m));
-    CK(cudaMalloc(&d2, n));
-    CK(cudaMalloc(&dt, tb));
+    if ((rc = ensure(ctx, ctx->v_s1, (size_t)m)) || (rc = ensure(ctx, ctx->v_s2, (size_t)n)) ||
+        (rc = ensure(ctx, ctx->v_tab, tb)))
+        return rc;
+    uint8_t *d1 = (uint8_t *)ctx->v_s1.p, *d2 = (uint8_t *)ctx->v_s2.p;
+    int *dt = (int *)ctx->v_tab.p;
     cudaStream_t st = ctx->stream;
+    SchemeDev sc = ctx->sc;
+    sc.seq_bits = 8;
     CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dt, table, tb, cudaMemcpyHostToDevice, st));
-    values_kernel<IntCosts><<<1, 256, 0, st>>>(IntCosts{ctx->sc}, d1, (int)m, d2, (int)n, keep_boundary, dt);
+    values_kernel<IntCosts><<<1, 256, 0, st>>>(IntCosts{sc}, d1, (int)m, d2, (int)n, keep_boundary, dt);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(table, dt, tb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(d1);
-    cudaFree(d2);
-    cudaFree(dt);
     return GA_OK;
 }
 
 // ------------------------------------------------------------------ seeded replay of random ties (kernel: ga_values.cuh)
+// Shared by ga_align_replay (table filled here from the sequences) and ga_walk_values (table given
+// by the caller: the reference's dp_array_backward walks whatever dp_array it is handed).
+static int replay_impl(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                       const int32_t *given_table, const uint16_t *draws, int64_t n_draws, int32_t *out_cost,
+                       uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
+    int rc;
+    if ((rc = check_letters(ctx, s1, m, "seq_1")) || (rc = check_letters(ctx, s2, n, "seq_2"))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t tb = (size_t)(m + 1) * (n + 1) * 3 * 4;
+    const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
+    if ((rc = ensure(ctx, ctx->v_s1, (size_t)m)) || (rc = ensure(ctx, ctx->v_s2, (size_t)n)) ||
+        (rc = ensure(ctx, ctx->v_tab, tb)) || (rc = ensure(ctx, ctx->v_draws, (size_t)std::max<int64_t>(n_draws, 1) * 2)) ||
+        (rc = ensure(ctx, ctx->v_ops, ops_words * 4)) || (rc = ensure(ctx, ctx->v_misc, 64)))
+        return rc;
+    uint8_t *d1 = (uint8_t *)ctx->v_s1.p, *d2 = (uint8_t *)ctx->v_s2.p;
+    int *dt = (int *)ctx->v_tab.p, *dmisc = (int *)ctx->v_misc.p;
+    uint16_t *dd = draws ? (uint16_t *)ctx->v_draws.p : nullptr;
+    uint32_t *dops = (uint32_t *)ctx->v_ops.p;
+    SchemeDev sc = ctx->sc;
+    sc.seq_bits = 8;
+    CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
+    if (draws) CK(cudaMemcpyAsync(dd, draws, (size_t)n_draws * 2, cudaMemcpyHostToDevice, st));
+    if (given_table) {
+        CK(cudaMemcpyAsync(dt, given_table, tb, cudaMemcpyHostToDevice, st));
+    } else {
+        values_kernel<IntCosts><<<1, 1024, 0, st>>>(IntCosts{sc}, d1, (int)m, d2, (int)n, 0, dt);
+        CK(cudaGetLastError());
+    }
+    replay_walk_kernel<IntCosts><<<1, 32, 0, st>>>(IntCosts{sc}, d1, (int)m, d2, (int)n, dt, dd, dops,
+                                         (long long *)(dmisc + 2), dmisc, dmisc + 1, dmisc + 4);
+    CK(cudaGetLastError());
+    int hm[8] = {};
+    CK(cudaMemcpyAsync(hm, dmisc, sizeof hm, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long nops = 0;
+    memcpy(&nops, hm + 2, 8);
+    *out_n_eval = hm[0];
+    *out_status = hm[1];
+    *out_cost = hm[4];
+    *out_n_ops = nops;
+    CK(cudaMemcpy(out_ops, dops, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
+    return GA_OK;
+}
+
 extern "C" int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                                const uint16_t *draws, int64_t n_draws, int32_t *out_cost, uint8_t *out_ops,
                                int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
@@ -1297,40 +1385,20 @@ extern "C" int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const 
         if (big + (m + n + 2) * (long long)ctx->sc.max_cost + 3LL * ctx->sc.o >= 0x7fffffffLL)
             return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
     }
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const size_t tb = (size_t)(m + 1) * (n + 1) * 3 * 4;
-    const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
-    uint8_t *d1 = nullptr, *d2 = nullptr;
-    int *dt = nullptr, *dmisc = nullptr;
-    uint16_t *dd = nullptr;
-    uint32_t *dops = nullptr;
-    CK(cudaMalloc(&d1, m));
-    CK(cudaMalloc(&d2, n));
-    CK(cudaMalloc(&dt, tb));
-    CK(cudaMalloc(&dd, (size_t)n_draws * 2));
-    CK(cudaMalloc(&dops, ops_words * 4));
-    CK(cudaMalloc(&dmisc, 64));
-    CK(cudaMemcpyAsync(d1, s1, m, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d2, s2, n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dd, draws, (size_t)n_draws * 2, cudaMemcpyHostToDevice, st));
-    values_kernel<IntCosts><<<1, 1024, 0, st>>>(IntCosts{ctx->sc}, d1, (int)m, d2, (int)n, 0, dt);
-    CK(cudaGetLastError());
-    replay_walk_kernel<IntCosts><<<1, 32, 0, st>>>(IntCosts{ctx->sc}, d1, (int)m, d2, (int)n, dt, dd, dops,
-                                         (long long *)(dmisc + 2), dmisc, dmisc + 1, dmisc + 4);
-    CK(cudaGetLastError());
-    int hm[8] = {};
-    CK(cudaMemcpyAsync(hm, dmisc, sizeof hm, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    long long nops = 0;
-    memcpy(&nops, hm + 2, 8);
-    *out_n_eval = hm[0];
-    *out_status = hm[1];
-    *out_cost = hm[4];
-    *out_n_ops = nops;
-    CK(cudaMemcpy(out_ops, dops, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d1); cudaFree(d2); cudaFree(dt); cudaFree(dd); cudaFree(dops); cudaFree(dmisc);
-    return GA_OK;
+    return replay_impl(ctx, s1, m, s2, n, nullptr, draws, n_draws, out_cost, out_ops, out_n_ops, out_n_eval,
+                       out_status);
+}
+
+extern "C" int ga_walk_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                              const int32_t *table, const uint16_t *draws, int64_t n_draws, int32_t *out_cost,
+                              uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
+    if (!ctx) return GA_E_ARG;
+    if (!ctx->have_scheme) return fail(ctx, GA_E_STATE, "ga_set_scheme has not been called");
+    if (!s1 || !s2 || !table || !out_cost || !out_ops || !out_n_ops || !out_n_eval || !out_status || m < 1 ||
+        n < 1 || (draws && n_draws < m + n) || (m + 1) * (n + 1) > (int64_t)60'000'000)
+        return fail(ctx, GA_E_ARG, "ga_walk_values: single pairs up to 6e7 table cells, m+n draws or none");
+    return replay_impl(ctx, s1, m, s2, n, table, draws, n_draws, out_cost, out_ops, out_n_ops, out_n_eval,
+                       out_status);
 }
 
 // ------------------------------------------------------------------ float-valued penalties (f64)
@@ -1392,15 +1460,11 @@ extern "C" int ga_fill_values_f64(ga_ctx *ctx, int32_t A, const double *sub, con
     return GA_OK;
 }
 
-extern "C" int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
-                            double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2,
-                            int64_t n, const uint16_t *draws, int64_t n_draws, double *out_cost,
-                            uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
-    if (!ctx) return GA_E_ARG;
-    if (!sub || !gap_h || !gap_v || !s1 || !s2 || !out_cost || !out_ops || !out_n_ops || !out_n_eval ||
-        !out_status || A < 1 || A > 250 || m < 1 || n < 1 || (draws && n_draws < m + n) ||
-        (m + 1) * (n + 1) > (int64_t)50'000'000)
-        return fail(ctx, GA_E_ARG, "ga_align_f64: single pairs up to 5e7 table cells, m+n draws or none");
+static int align_f64_impl(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
+                          double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2,
+                          int64_t n, const double *given_table, const uint16_t *draws, int64_t n_draws,
+                          double *out_cost, uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval,
+                          int32_t *out_status) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     F64Pair w;
@@ -1414,8 +1478,12 @@ extern "C" int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const dou
         CK(cudaMalloc(&w.dd, (size_t)n_draws * 2));
         CK(cudaMemcpyAsync(w.dd, draws, (size_t)n_draws * 2, cudaMemcpyHostToDevice, st));
     }
-    values_kernel<F64Costs><<<1, 1024, 0, st>>>(c, w.d1, (int)m, w.d2, (int)n, 0, w.dt);
-    CK(cudaGetLastError());
+    if (given_table) {
+        CK(cudaMemcpyAsync(w.dt, given_table, (size_t)(m + 1) * (n + 1) * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        values_kernel<F64Costs><<<1, 1024, 0, st>>>(c, w.d1, (int)m, w.d2, (int)n, 0, w.dt);
+        CK(cudaGetLastError());
+    }
     // dmisc: [0] n_eval, [1] status, [2..3] n_ops (int64), [4..5] cost (f64)
     replay_walk_kernel<F64Costs><<<1, 32, 0, st>>>(c, w.d1, (int)m, w.d2, (int)n, w.dt, w.dd, w.dops,
                                                          (long long *)(w.dmisc + 2), w.dmisc, w.dmisc + 1,
@@ -1432,6 +1500,33 @@ extern "C" int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const dou
     *out_n_ops = nops;
     CK(cudaMemcpy(out_ops, w.dops, (size_t)((nops + 15) / 16) * 4, cudaMemcpyDeviceToHost));
     return GA_OK;
+}
+
+extern "C" int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
+                            double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2,
+                            int64_t n, const uint16_t *draws, int64_t n_draws, double *out_cost,
+                            uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
+    if (!ctx) return GA_E_ARG;
+    if (!sub || !gap_h || !gap_v || !s1 || !s2 || !out_cost || !out_ops || !out_n_ops || !out_n_eval ||
+        !out_status || A < 1 || A > 250 || m < 1 || n < 1 || (draws && n_draws < m + n) ||
+        (m + 1) * (n + 1) > (int64_t)50'000'000)
+        return fail(ctx, GA_E_ARG, "ga_align_f64: single pairs up to 5e7 table cells, m+n draws or none");
+    return align_f64_impl(ctx, A, sub, gap_h, gap_v, gap_open, max_cost, s1, m, s2, n, nullptr, draws, n_draws,
+                          out_cost, out_ops, out_n_ops, out_n_eval, out_status);
+}
+
+extern "C" int ga_walk_values_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h,
+                                  const double *gap_v, double gap_open, double max_cost, const uint8_t *s1,
+                                  int64_t m, const uint8_t *s2, int64_t n, const double *table,
+                                  const uint16_t *draws, int64_t n_draws, double *out_cost, uint8_t *out_ops,
+                                  int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status) {
+    if (!ctx) return GA_E_ARG;
+    if (!sub || !gap_h || !gap_v || !s1 || !s2 || !table || !out_cost || !out_ops || !out_n_ops || !out_n_eval ||
+        !out_status || A < 1 || A > 250 || m < 1 || n < 1 || (draws && n_draws < m + n) ||
+        (m + 1) * (n + 1) > (int64_t)50'000'000)
+        return fail(ctx, GA_E_ARG, "ga_walk_values_f64: single pairs up to 5e7 table cells, m+n draws or none");
+    return align_f64_impl(ctx, A, sub, gap_h, gap_v, gap_open, max_cost, s1, m, s2, n, table, draws, n_draws,
+                          out_cost, out_ops, out_n_ops, out_n_eval, out_status);
 }
 
 // ------------------------------------------------------------------ integer-ALU roofline probe (kernels: ga_probe.cuh)

@@ -165,6 +165,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     const unsigned ghTc = V::pk(4u * sc.gh + 1u, 4u * sc.gh + 1u);
     const unsigned gvTc = V::pk(4u * sc.gv + 2u, 4u * sc.gv + 2u);
     const unsigned padb = SIMPLE ? (unsigned)PAD_B : (PT ? (unsigned)sc.A : 0u);
+    const unsigned blim = SIMPLE ? 0xFFu : (PT ? (unsigned)sc.A : (unsigned)(sc.A - 1));   // largest usable seq_2 letter
     // a*k+b forms that must stay IMADs (FMA pipe); see SchemeDev::k_one
     const unsigned K1 = sc.k_one, K4 = sc.k_four, KM1 = sc.k_minus_one;
 
@@ -214,9 +215,11 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
             const int na = (int)(pair_off(off2, qa + 1, ut.N) - oa), nb = (int)(pair_off(off2, qb + 1, ut.N) - ob);
             BT *row = sb + (size_t)q * sb_stride;
             for (int c = lane; c < sb_len; c += 32) {
-                const unsigned va = c < na ? ld_letter(s2, oa + c, sc.seq_bits) : padb;
+                // table kernels index with the letters: an out-of-range letter (caller error) is
+                // clamped so that it cannot address outside the tables
+                const unsigned va = c < na ? min(ld_letter(s2, oa + c, sc.seq_bits), blim) : padb;
                 if (PACKED) {
-                    const unsigned vb = c < nb ? ld_letter(s2, ob + c, sc.seq_bits) : padb;
+                    const unsigned vb = c < nb ? min(ld_letter(s2, ob + c, sc.seq_bits), blim) : padb;
                     row[c] = (BT)(va | (vb << 16));
                 } else {
                     row[c] = (BT)va;
@@ -252,8 +255,8 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     #pragma unroll
                     for (int r = 0; r < RT; ++r) {
                         const int row = ib + r;
-                        const int la = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
-                        const int lb = row < mB ? (int)ld_letter(s1, b1 + row, sc.seq_bits) : sc.A;
+                        const int la = row < mA ? min((int)ld_letter(s1, a1 + row, sc.seq_bits), sc.A) : sc.A;
+                        const int lb = row < mB ? min((int)ld_letter(s1, b1 + row, sc.seq_bits), sc.A) : sc.A;
                         aw[r] = (PB ? 32u * EB : 4u) * (unsigned)la;  // byte offset of the letter in a table row
                         awB[r] = (PB ? 32u * EB : 4u) * (unsigned)lb;
                         gvT[r] = (unsigned)sc.gv4t[la] | ((unsigned)sc.gv4t[lb] << 16);
@@ -299,7 +302,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
     #pragma unroll
                     for (int r = 0; r < RT; ++r) {
                         const int row = ib + r;
-                        const int a = row < mA ? (int)ld_letter(s1, a1 + row, sc.seq_bits) : sc.A;
+                        const int a = row < mA ? min((int)ld_letter(s1, a1 + row, sc.seq_bits), sc.A) : sc.A;
                         aw[r] = (unsigned)(a * sc.A);
                         gvT[r] = (unsigned)sc.gv4t[a];
                         gvr[r] = sc.gv_raw[a];

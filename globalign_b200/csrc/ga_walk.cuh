@@ -123,12 +123,12 @@ walk_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
             int want;
             if (i == 0) {
                 long long row = sc.o;
-                for (int c = 0; c < j; ++c) row += sc.simple ? sc.gh : sc.gh_raw[ld_letter(s2, a2 + c, sc.seq_bits)];
+                for (int c = 0; c < j; ++c) row += sc.simple ? sc.gh : sc.gh_raw[min(ld_letter(s2, a2 + c, sc.seq_bits), (unsigned)(sc.A - 1))];
                 v1 = row;
                 want = 1;
             } else {
                 long long col = sc.o;
-                for (int c = 0; c < i; ++c) col += sc.simple ? sc.gv : sc.gv_raw[ld_letter(s1, a1 + c, sc.seq_bits)];
+                for (int c = 0; c < i; ++c) col += sc.simple ? sc.gv : sc.gv_raw[min(ld_letter(s1, a1 + c, sc.seq_bits), (unsigned)sc.A)];
                 v2 = col;
                 want = 2;
             }

@@ -224,16 +224,58 @@ def dp_array_forward(dp_array, seq_1: str, seq_2: str, costing_mat: dict, gap_op
 
 
 def dp_array_backward(dp_array, seq_1: str, seq_2: str, costing_mat: dict, gap_open_cost: int):
-    """-> (seq_1_aligned, middle_part, seq_2_aligned, cost).  The walk runs on the
-    GPU over direction codes recomputed from the sequences; ``dp_array`` is only
-    consulted for its corner value (the cost), exactly what a table filled by
-    ``dp_array_forward`` from ``make_dp_array`` holds."""
-    ops, cost = _align_one(seq_1, seq_2, costing_mat, gap_open_cost)
-    if dp_array is not None and dp_array[len(seq_1)][len(seq_2)] is not None:
-        if min(dp_array[len(seq_1)][len(seq_2)]) != cost:
-            raise RuntimeError("dp_array was not produced by make_dp_array + dp_array_forward "
-                               "for these sequences and costs")
+    """-> (seq_1_aligned, middle_part, seq_2_aligned, cost).  Like the reference's
+    (globaligner.py:395-593) this walks the ``dp_array`` it is handed -- whatever boundary values
+    it was built with (the reference's own test writes them by hand,
+    tests/globaligner_test.py:6-37): the table is uploaded and one GPU thread ranks the three
+    values of every cell on the path (``ga_walk_values``).  ``dp_array=None`` recomputes the
+    table from the sequences (the whole hot path)."""
+    if dp_array is None:
+        ops, cost = _align_one(seq_1, seq_2, costing_mat, gap_open_cost)
+        top, mid, bot = render(ops, seq_1, seq_2)
+        return top, mid, bot, cost
+    m, n = len(seq_1), len(seq_2)
+    if m < 1 or n < 1:
+        raise RuntimeError("dp_array_backward needs two non-empty sequences")
+    try:
+        values = np.array([[dp_array[i][j] for j in range(n + 1)] for i in range(m + 1)], dtype=np.float64)
+    except (TypeError, ValueError) as exc:
+        raise TypeError("dp_array must hold a 3-tuple of numbers in every cell "
+                        "(fill it with dp_array_forward first)") from exc
+    if values.shape != (m + 1, n + 1, 3):
+        raise TypeError("dp_array must be (len(seq_1)+1) x (len(seq_2)+1) cells of 3 values")
+    ctx = _native.default_context(0)
+    integral = is_integral(costing_mat, gap_open_cost) and bool(np.all(values == np.rint(values))) \
+        and float(np.abs(values).max()) < 2.0 ** 30
+    if TIE_BREAKING == "reference_random":
+        import random
+        state = random.getstate()
+        draws, words = _reference_draws(m + n)
+    elif TIE_BREAKING == "canonical":
+        draws = words = None
+    else:
+        raise ValueError("TIE_BREAKING must be 'canonical' or 'reference_random'")
+    if integral:
+        dense = DenseScheme(costing_mat, gap_open_cost)
+        ctx.set_scheme(dense)
+        cost, ops, n_eval, status = ctx.walk_values(dense.encode(seq_1), dense.encode(seq_2),
+                                                    np.ascontiguousarray(values, dtype=np.int32), draws)
+    else:
+        dense = DenseSchemeF64(costing_mat, gap_open_cost)
+        cost, ops, n_eval, status = ctx.walk_values_f64(dense, dense.encode(seq_1), dense.encode(seq_2),
+                                                        np.ascontiguousarray(values), draws)
+    if draws is not None:        # leave the global generator where the reference would have left it
+        random.setstate(state)
+        if words[n_eval]:
+            random.getrandbits(32 * int(words[n_eval]))
+    if status != 0:
+        raise ReferenceUndefinedError(
+            "the reference's traceback leaves the DP table on this dp_array: it raises IndexError "
+            "or wraps to negative indices there")
     top, mid, bot = render(ops, seq_1, seq_2)
+    if integral:
+        # hand back the caller's own number type for the corner minimum (:425)
+        cost = min(dp_array[m][n])
     return top, mid, bot, cost
 
 

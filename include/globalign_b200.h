@@ -188,6 +188,17 @@ int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2
                     const uint16_t *draws, int64_t n_draws, int32_t *out_cost, uint8_t *out_ops,
                     int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status);
 
+/* The traceback alone, on a value table the CALLER provides: the reference's dp_array_backward
+ * (globaligner.py:395-593) walks whatever dp_array it is handed -- its own test builds one with
+ * hand-written boundary values (tests/globaligner_test.py:6-37) -- ranking the three values of
+ * each cell (:425-581).  `table` is (m+1) x (n+1) x 3 int32, row-major, as ga_fill_values leaves
+ * it.  draws == NULL: canonical tie order; otherwise as ga_align_replay.  out_cost = min of the
+ * corner cell (:425).  status 1: the walk leaves the table (the reference raises IndexError or
+ * wraps to negative indices).  Not a throughput path: (m+1)*(n+1) <= 6e7. */
+int ga_walk_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
+                   const int32_t *table, const uint16_t *draws, int64_t n_draws, int32_t *out_cost,
+                   uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status);
+
 /* Float-valued penalties.  The reference's entry point coerces every score
  * and cost with int() (start.py:51-69,121-133,423), but its inner functions take floats when
  * called directly (type hints globaligner.py:371,761).  These two calls serve that case for
@@ -207,6 +218,12 @@ int ga_align_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h,
                  double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
                  const uint16_t *draws, int64_t n_draws, double *out_cost, uint8_t *out_ops,
                  int64_t *out_n_ops, int32_t *out_n_eval, int32_t *out_status);
+/* ga_walk_values for an f64 table (the walk of ga_align_f64 on the caller's values). */
+int ga_walk_values_f64(ga_ctx *ctx, int32_t A, const double *sub, const double *gap_h, const double *gap_v,
+                       double gap_open, double max_cost, const uint8_t *s1, int64_t m, const uint8_t *s2,
+                       int64_t n, const double *table, const uint16_t *draws, int64_t n_draws,
+                       double *out_cost, uint8_t *out_ops, int64_t *out_n_ops, int32_t *out_n_eval,
+                       int32_t *out_status);
 
 /* Integer-ALU roofline microbenchmark (no memory traffic): giga-instructions/s the
  * device retires of one instruction kind.  Throughput modes (8 independent chains per

@@ -508,6 +508,166 @@ def test_long_seq2_in_batched_kernels_and_auto_routing():
     assert rc == 0 and r.cost == cost and (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) == batch.render(ops, a, b)
 
 
+def test_short_seq1_against_long_seq2_picks_a_kernel_that_fits():
+    """A short seq_1 selects a few-lanes-per-group kernel by its rows; its shared-memory staging of
+    seq_2 grows with n, so for long seq_2 the planner must move to wider groups / the int32 family
+    instead of failing (header: n <= 32768).  12 x 20000 and 50 x 3500 with unit costs, through
+    the batch call and through find_global_alignment (m * n below the long-pair threshold)."""
+    rng = random.Random(21)
+    ctx = _native.Context(0)
+    for dense, A in ((_simple_dense(4, 1, 1, 1, 1), 4), (_simple_dense(4, 5, 2, 2, 10), 4), (_table_dense(rng, 20, 7), 20)):
+        ctx.set_scheme(dense)
+        for m, n in ((12, 20000), (50, 3500), (15, 16000), (3, 32768), (40, 13000)):
+            s1 = np.array([rng.randrange(A) for _ in range(m + 7)], dtype=np.uint8)
+            s2 = np.array([rng.randrange(A) for _ in range(n + 900)], dtype=np.uint8)
+            off1 = np.array([0, m, m + 7], dtype=np.int64)
+            off2 = np.array([0, n, n + 900], dtype=np.int64)
+            out = ctx.align_batch(s1, off1, s2, off2)
+            _compare_with_oracle(s1, off1, s2, off2, dense, out)
+    ctx.close()
+    a = "ACGTTGCAACGT"
+    b = "".join(rng.choice("ACGT") for _ in range(20000))
+    r = find_global_alignment(seq_1=a, seq_2=b, mismatch_cost=1, gap_open_cost=1, gap_extension_cost=1)
+    ops, cost, rc = c_oracle.align(a, b, r.costing_mat, r.gap_open_cost)
+    assert rc == 0 and r.cost == cost and (r.seq_1_aligned, r.middle_part, r.seq_2_aligned) == batch.render(ops, a, b)
+
+
+def test_long_pair_call_leaves_a_packed_plan_intact():
+    """ga_align_long takes one letter per byte; it must not change how a batch plan made for
+    2-bit / 4-bit packed streams reads its input (the plan stays valid across the call)."""
+    rng = random.Random(22)
+    dense = _simple_dense(4, 5, 2, 2, 10)
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    import torch
+    n = 300
+    s1 = np.array([rng.randrange(4) for _ in range(n * 100)], dtype=np.uint8)
+    s2 = np.array([rng.randrange(4) for _ in range(n * 100)], dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.int64) * 100
+    ref = ctx.align_batch(s1, off, s2, off)
+    for bits in (2, 4):
+        ops_off = _native.ops_offsets(off, off)
+        ctx.plan_batch(off, off, ops_off, flags=_native.seq_flag(bits))
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        d1, d2, do, doo = dev(_native.pack_letters(s1, bits)), dev(_native.pack_letters(s2, bits)), dev(off), dev(ops_off)
+        dc = torch.empty(n, dtype=torch.int32, device="cuda")
+        dl, dst = torch.empty_like(dc), torch.empty_like(dc)
+        dops = torch.empty(int(ops_off[-1]) + 16, dtype=torch.uint8, device="cuda")
+        run = lambda: ctx.run_batch(d1.data_ptr(), do.data_ptr(), d2.data_ptr(), do.data_ptr(), dc.data_ptr(),
+                                    dops.data_ptr(), doo.data_ptr(), dl.data_ptr(), dst.data_ptr())
+        run()
+        ctx.sync()
+        assert np.array_equal(dc.cpu().numpy(), ref[0])
+        lp = synth.dna_single(700, 5, 6)
+        ctx.align_long(lp.s1, lp.s2)                       # same context, between two runs of the plan
+        dc.zero_()
+        run()
+        ctx.sync()
+        assert np.array_equal(dc.cpu().numpy(), ref[0]) and np.array_equal(dl.cpu().numpy(), ref[3])
+        assert np.array_equal(dops.cpu().numpy()[: int(ops_off[-1])], ref[1][: int(ops_off[-1])])
+    ctx.close()
+
+
+def test_out_of_range_letters_are_refused_or_harmless():
+    """Letters >= A are a caller error.  Single-pair entry points refuse them; the batch kernels
+    clamp them (results for that pair are meaningless, but nothing is read out of bounds and the
+    context stays usable)."""
+    rng = random.Random(23)
+    dense = _table_dense(rng, 5, 3)
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    good = np.array([0, 1, 2, 3, 4, 1], dtype=np.uint8)
+    bad = np.array([0, 1, 200, 3, 255, 1], dtype=np.uint8)
+    table = np.zeros((7, 7, 3), dtype=np.int32)
+    with pytest.raises(RuntimeError):
+        ctx.fill_values(bad, good, table, keep_boundary=False)
+    with pytest.raises(RuntimeError):
+        ctx.align_replay(good, bad, np.zeros(12, dtype=np.uint16))
+    with pytest.raises(RuntimeError):
+        ctx.align_long(bad, good)
+    off = np.array([0, 6, 12], dtype=np.int64)
+    s1 = np.concatenate([good, bad])
+    s2 = np.concatenate([bad, good])
+    for cfg in (None, "fill_i32t_r8_g8", "fill_p16t_r8_g8", "fill_p16b_r16_g32"):
+        if cfg:
+            os.environ["GA_FORCE_CFG"] = cfg
+        ctx.align_batch(s1, off, s2, off)                  # must not fault
+        os.environ.pop("GA_FORCE_CFG", None)
+    gs1 = np.concatenate([good, good[::-1]])
+    out = ctx.align_batch(gs1, off, gs1[::-1].copy(), off)   # the context still works
+    _compare_with_oracle(gs1, off, gs1[::-1].copy(), off, dense, out)
+    ctx.close()
+
+
+def test_timing_is_invalid_after_a_new_plan():
+    dense = _simple_dense(4, 5, 2, 2, 10)
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    off = np.arange(65, dtype=np.int64) * 50
+    s = np.zeros(64 * 50, dtype=np.uint8)
+    ctx.align_batch(s, off, s, off)
+    assert ctx.timing()["total"] > 0
+    ctx.plan_batch(off[:9], off[:9], _native.ops_offsets(off[:9], off[:9]))
+    with pytest.raises(RuntimeError):
+        ctx.timing()                                       # the new plan has not run
+    ctx.close()
+
+
+def test_dp_array_backward_walks_the_table_it_is_given():
+    """tests/golden/seam_cases.json (frozen from the reference by make_seam_golden.py): tables
+    with hand-written or edited boundary values -- the first one is the reference's own
+    (tests/globaligner_test.py:6-37).  dp_array_forward fills them on the GPU, dp_array_backward
+    walks THOSE values (ga_walk_values), and both equal the reference."""
+    from globalign_b200 import globaligner as GA
+    cases = golden("seam_cases.json")
+    assert cases[0]["seq_1"] == "AG" and cases[0]["row0"][0] == [0, 7, 7]
+    differs_from_recomputed = 0
+    for r in cases:
+        s1, s2, cm, o = r["seq_1"], r["seq_2"], r["cm"], r["o"]
+        m, n = len(s1), len(s2)
+        dp = [[None] * (n + 1) for _ in range(m + 1)]
+        for j in range(n + 1):
+            dp[0][j] = tuple(r["row0"][j])
+        for i in range(m + 1):
+            dp[i][0] = tuple(r["col0"][i])
+        GA.dp_array_forward(dp, s1, s2, cm, o)
+        assert [[list(c) for c in row] for row in dp] == r["table"]
+        if "error" in r:
+            with pytest.raises(batch.ReferenceUndefinedError):
+                GA.dp_array_backward(dp, s1, s2, cm, o)
+            continue
+        got = GA.dp_array_backward(dp, s1, s2, cm, o)
+        assert list(got) == r["out"]
+        if max(m, n) > o:
+            try:
+                differs_from_recomputed += list(GA.dp_array_backward(None, s1, s2, cm, o)) != r["out"]
+            except batch.ReferenceUndefinedError:
+                differs_from_recomputed += 1
+    assert differs_from_recomputed > 0       # the fixture does exercise tables the sequences alone do not give
+
+
+def test_batch_agrees_with_single_pair_call_on_one_letter_pairs():
+    """Simple schemes build the costing matrix over the letters of the PAIR (start.py:319-343): a
+    pair of one repeated letter has no mismatch entry, hence a smaller sentinel.  It only matters
+    for max(m, n) <= gap_open_cost; there the batch call must still agree with the single-pair
+    call ('AA' vs 'AAA', mismatch 3 / extension 1 / open 8 -> cost 6, not 9)."""
+    kw = dict(mismatch_cost=3, gap_extension_cost=1, gap_open_cost=8)
+    s1 = ["AA", "AAA", "ACGTACGTACGT", "CCCC", "A", "GGGGGGGGG", "TT", "AC"]
+    s2 = ["AAA", "AA", "ACGAACGTACT", "CC", "AAAA", "GGGGGGGGGGG", "TTTTTTT", "AAA"]
+    res = batch.find_global_alignments(s1, s2, **kw)
+    for k, (a, b) in enumerate(zip(s1, s2)):
+        try:
+            one = find_global_alignment(seq_1=a, seq_2=b, **kw)
+        except batch.ReferenceUndefinedError:
+            assert res.status[k] != 0, k
+            continue
+        assert res.status[k] == 0, k
+        r = res[k]
+        assert (r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score) == \
+            (one.seq_1_aligned, one.middle_part, one.seq_2_aligned, one.cost, one.score), k
+    assert find_global_alignment(seq_1="AA", seq_2="AAA", **kw).cost == 6
+
+
 def test_one_letter_and_large_alphabets():
     r = find_global_alignment(seq_1="AAAAAAA", seq_2="AAAA")
     ops, cost, rc = c_oracle.align("AAAAAAA", "AAAA", r.costing_mat, r.gap_open_cost)

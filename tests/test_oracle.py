@@ -150,3 +150,33 @@ def test_float_penalty_golden_vectors():
             assert [float(v) for v in tab[i][j]] == vals          # tolerance: none (bit-exact)
         ops, cost = py_oracle.walk(tab, r["seq_1"], r["seq_2"], r["o"], cm=r["cm"])
         assert list(py_oracle.render(ops, r["seq_1"], r["seq_2"])) + [float(cost)] == r["out"]
+
+
+def test_walk_on_caller_provided_tables():
+    """tests/golden/seam_cases.json: tables with hand-written / edited boundary values, filled and
+    walked by the reference itself (make_seam_golden.py), incl. the table of the reference's own
+    test (tests/globaligner_test.py:6-37).  The oracle's fill + value-comparing walk reproduce
+    them; where the reference raises, the oracle refuses."""
+    cases = golden("seam_cases.json")
+    assert cases[0]["seq_1"] == "AG" and cases[0]["row0"][0] == [0, 7, 7]
+    n_nonstandard = 0
+    for r in cases:
+        s1, s2, cm, o = r["seq_1"], r["seq_2"], r["cm"], r["o"]
+        m, n = len(s1), len(s2)
+        tb = [[None] * (n + 1) for _ in range(m + 1)]
+        for j in range(n + 1):
+            tb[0][j] = tuple(r["row0"][j])
+        for i in range(m + 1):
+            tb[i][0] = tuple(r["col0"][i])
+        std = py_oracle.boundary_table(s1, s2, cm, o)
+        n_nonstandard += any(std[0][j] != tb[0][j] for j in range(n + 1)) or \
+            any(std[i][0] != tb[i][0] for i in range(m + 1))
+        py_oracle.fill_in_place(tb, s1, s2, cm, o)
+        assert [[list(c) for c in row] for row in tb] == r["table"]
+        if "error" in r:
+            with pytest.raises(ValueError):
+                py_oracle.walk(tb, s1, s2, o)
+            continue
+        ops, cost = py_oracle.walk(tb, s1, s2, o)
+        assert [*py_oracle.render(ops, s1, s2), cost] == r["out"]
+    assert n_nonstandard > 200
