@@ -14,7 +14,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libglobalign_b200.so"
+import os
+
+#: GA_B200_LIB: another build of the library (tuning variants of tools/tune_long.py); default: in-tree
+LIB_PATH = Path(os.environ.get("GA_B200_LIB") or Path(__file__).resolve().parent / "libglobalign_b200.so")
 
 GA_F_DEFAULT = 0
 GA_F_FORCE_GENERIC = 1
@@ -31,7 +34,7 @@ EXPORTS = (
     "ga_ctx_set_stream", "ga_ctx_set_scratch_limit", "ga_set_scheme", "ga_align_batch",
     "ga_plan_batch", "ga_run_batch", "ga_sync", "ga_get_plan_info", "ga_get_timing",
     "ga_fill_values", "ga_alu_peak", "ga_align_long", "ga_align_replay", "ga_align_batch_uniform",
-    "ga_fill_values_f64", "ga_align_f64", "ga_walk_values", "ga_walk_values_f64",
+    "ga_fill_values_f64", "ga_align_f64", "ga_walk_values", "ga_walk_values_f64", "ga_align_batch_rle",
 )
 
 
@@ -78,6 +81,7 @@ def lib():
     L.ga_set_scheme.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32]
     L.ga_align_batch.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, u32]
     L.ga_align_batch_uniform.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, u32]
+    L.ga_align_batch_rle.argtypes = [vp, vp, vp, i64, vp, vp, i64, i64, vp, vp, i64, vp, u32]
     L.ga_plan_batch.argtypes = [vp, vp, vp, i64, vp, u32]
     L.ga_run_batch.argtypes = [vp] + [vp] * 9
     L.ga_sync.argtypes = [vp]
@@ -216,6 +220,31 @@ class Context:
         self._check(self._L.ga_align_batch_uniform(self._h, _ptr(s1), m, _ptr(s2), n, n_pairs, _ptr(cost),
                                                    _ptr(ops), _ptr(ops_len), _ptr(status), flags))
         return cost, ops, stride, ops_len, status
+
+    def align_batch_rle(self, s1, off1, s2, off2, m: int = 0, n: int = 0, n_pairs: int | None = None,
+                        flags: int = 0, out=None, capacity: int | None = None):
+        """Compact result stream (ga_align_batch_rle): -> (res, rle, rle_off) with
+        res = structured array (cost int32, nops_status uint32: bit 31 = status), rle = run-length
+        encoded ops of all pairs back to back, rle_off = int64[n_pairs + 1].
+        off1 = off2 = None: fixed-length batch, every pair m x n (n_pairs given).
+        `out`: optional preallocated (res, rle, rle_off), e.g. views of pinned memory."""
+        s1 = np.ascontiguousarray(s1, dtype=np.uint8)
+        s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+        if off1 is not None:
+            off1 = np.ascontiguousarray(off1, dtype=np.int64)
+            off2 = np.ascontiguousarray(off2, dtype=np.int64)
+            n_pairs = len(off1) - 1
+            worst = int(off1[-1] + off2[-1])
+        else:
+            worst = (m + n) * n_pairs
+        if out is None:
+            cap = worst if capacity is None else int(capacity)         # untouched pages cost nothing
+            out = (np.empty(n_pairs, dtype=PAIR_RESULT), np.empty(max(cap, 1), dtype=np.uint8),
+                   np.empty(n_pairs + 1, dtype=np.int64))
+        res, rle, rle_off = out
+        self._check(self._L.ga_align_batch_rle(self._h, _ptr(s1), _ptr(off1), m, _ptr(s2), _ptr(off2), n, n_pairs,
+                                               _ptr(res), _ptr(rle), len(rle), _ptr(rle_off), flags))
+        return res, rle, rle_off
 
     # -- device-buffer entry points (pointers are ints, e.g. torch.Tensor.data_ptr())
     def plan_batch(self, off1, off2, ops_off=None, flags: int = 0):
@@ -378,6 +407,17 @@ def ops_offsets(off1, off2) -> np.ndarray:
     out = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(nbytes, out=out[1:])
     return out
+
+
+#: one record of ga_align_batch_rle (ga_pair_result)
+PAIR_RESULT = np.dtype([("cost", "<i4"), ("nops_status", "<u4")])
+
+
+def unpack_rle(rle: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """Run-length encoded ops of one pair (bytes [lo, hi) of the compact stream) as a uint8 array
+    of 0/1/2 in walk order -- the same array unpack_ops gives for the fixed-slice form."""
+    b = rle[lo:hi]
+    return np.repeat(b & 3, (b >> 2).astype(np.int64) + 1)
 
 
 def unpack_ops(ops: np.ndarray, start: int, count: int) -> np.ndarray:

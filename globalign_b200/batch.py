@@ -46,9 +46,13 @@ def render(ops: np.ndarray, seq_1: str, seq_2: str):
 class BatchAlignment:
     """Packed results of a batch; ``batch[k]`` builds the k-th AlignmentResults."""
 
-    def __init__(self, seqs_1, seqs_2, cost, ops, ops_off, ops_len, status, scheme):
+    def __init__(self, seqs_1, seqs_2, cost, ops, ops_off, ops_len, status, scheme, rle: bool = False):
+        """`rle`: ops / ops_off hold the compact run-length stream of ga_align_batch_rle instead of
+        fixed 2-bit slices (what find_global_alignments asks the library for)."""
         self.seqs_1, self.seqs_2 = seqs_1, seqs_2
         self.cost, self.ops, self.ops_off, self.ops_len, self.status = cost, ops, ops_off, ops_len, status
+        self.rle = rle
+        self._patched_ops = {}       # pairs re-aligned one by one (_realign_single_letter_pairs)
         self._scheme = scheme
         # (ASCII upper-casing keeps lengths: measure the caller's strings, not the lazy view)
         m = np.fromiter(map(len, getattr(seqs_1, "_seqs", seqs_1)), dtype=np.int64, count=len(seqs_1))
@@ -59,6 +63,10 @@ class BatchAlignment:
         return len(self.cost)
 
     def ops_of(self, k: int) -> np.ndarray:
+        if k in self._patched_ops:
+            return self._patched_ops[k]
+        if self.rle:
+            return _native.unpack_rle(self.ops, int(self.ops_off[k]), int(self.ops_off[k + 1]))
         return _native.unpack_ops(self.ops, int(self.ops_off[k]), int(self.ops_len[k]))
 
     def __getitem__(self, k: int) -> AlignmentResults:
@@ -254,6 +262,7 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
         lowered = _lower_batch(seqs_1, seqs_2, limit, scheme)
     up1, up2, dense, cat1, off1, cat2, off2 = lowered
     def on_device(dev, c1, o1, c2, o2):
+        """-> (cost, rle, rle_off, ops_len, status): the compact result stream of one GPU."""
         ctx = _native.default_context(dev)
         ctx.set_scheme(dense)
         n_pairs = len(o1) - 1
@@ -261,22 +270,24 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
         if n_pairs > 1 and o1[-1] == m0 * n_pairs and o2[-1] == n0 * n_pairs and \
                 np.array_equal(o1, np.arange(n_pairs + 1) * m0) and np.array_equal(o2, np.arange(n_pairs + 1) * n0):
             # fixed-length batch (reads of one length): the entry point without offset arrays
-            cost, ops, stride, ops_len, status = ctx.align_batch_uniform(c1, m0, c2, n0, n_pairs)
-            return cost, ops, np.arange(n_pairs + 1, dtype=np.int64) * stride, ops_len, status
-        return ctx.align_batch(c1, o1, c2, o2)
+            res, rle, rle_off = ctx.align_batch_rle(c1, None, c2, None, m0, n0, n_pairs)
+        else:
+            res, rle, rle_off = ctx.align_batch_rle(c1, o1, c2, o2)
+        nops = res["nops_status"]
+        return (res["cost"].copy(), rle[: int(rle_off[-1])], rle_off, (nops & 0x7FFFFFFF).astype(np.int32),
+                (nops >> 31).astype(np.int32))
 
     if devices is None or len(devices) <= 1:
         cost, ops, ops_off, ops_len, status = on_device(device if not devices else devices[0], cat1, off1, cat2, off2)
     else:
         from .parallel import align_on_devices
         cost, ops, ops_off, ops_len, status = align_on_devices(on_device, cat1, off1, cat2, off2, list(devices))
-    _realign_single_letter_pairs(up1, up2, dense, cat1, off1, cat2, off2, scheme, device if not devices else devices[0],
-                                 cost, ops, ops_off, ops_len, status)
-    return BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme)
+    res = BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme, rle=True)
+    _realign_single_letter_pairs(res, dense, cat1, off1, cat2, off2, scheme, device if not devices else devices[0])
+    return res
 
 
-def _realign_single_letter_pairs(up1, up2, dense, cat1, off1, cat2, off2, scheme, device,
-                                 cost, ops, ops_off, ops_len, status):
+def _realign_single_letter_pairs(res: "BatchAlignment", dense, cat1, off1, cat2, off2, scheme, device):
     """Simple schemes build their matrices over the letters of the PAIR (start.py:319-343), so a
     pair made of one repeated letter has no mismatch entry and a smaller max_cost -- hence a
     smaller boundary sentinel (globaligner.py:777) -- than the batch-wide tables give it.  The
@@ -290,20 +301,24 @@ def _realign_single_letter_pairs(up1, up2, dense, cat1, off1, cat2, off2, scheme
     if short.size == 0:
         return
     ctx = _native.default_context(device)
+    patched = {}
     for k in short:
         a = cat1[off1[k]:off1[k + 1]]
         b = cat2[off2[k]:off2[k + 1]]
         if not (a.min() == a.max() == b.min() == b.max()):
             continue
-        s1, s2 = up1[int(k)], up2[int(k)]
+        s1, s2 = res.seqs_1[int(k)], res.seqs_2[int(k)]
         _, cm = scheme.matrices_for(s1, s2)
         own = DenseScheme(cm, scheme.gap_open_cost)
         ctx.set_scheme(own)
         c1, o1, _, l1, st1 = ctx.align_batch(own.encode(s1), np.array([0, len(s1)], dtype=np.int64),
                                              own.encode(s2), np.array([0, len(s2)], dtype=np.int64))
-        cost[k], ops_len[k], status[k] = c1[0], l1[0], st1[0]
-        ops[ops_off[k]:ops_off[k] + len(o1)] = o1
+        res.cost[k], res.ops_len[k], res.status[k] = c1[0], l1[0], st1[0]
+        patched[int(k)] = _native.unpack_ops(o1, 0, int(l1[0]))
     ctx.set_scheme(dense)
+    if patched:
+        res.score = final_cost_to_score(res.cost.astype(np.int64), m_len, n_len, scheme.max_score)
+        res._patched_ops = patched
 
 
 def read_pairs_from_fasta(fasta_path, fasta_path_2=None):

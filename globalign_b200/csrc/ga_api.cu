@@ -21,6 +21,8 @@
 #include "ga_long.cuh"
 #include "ga_values.cuh"
 #include "ga_probe.cuh"
+#include "ga_rle.cuh"
+#include <cub/device/device_scan.cuh>
 
 using namespace ga;
 
@@ -128,6 +130,7 @@ struct Chunk {
 // events of one chunk of the pipeline
 struct ChunkEvents {
     cudaEvent_t in0, in1, f0, f1, w0, w1, out0, out1;
+    cudaEvent_t base, r0, r1;      // compact (RLE) output: chunk size known on the host / its copy
 };
 
 struct DevBuf {
@@ -179,11 +182,16 @@ struct ga_ctx {
     DevBuf l_colsum, l_rowsum, l_brow, l_vchk, l_prog, l_misc, l_xrow, l_meta, l_seg;
     // single-pair value-table paths (ga_fill_values, ga_align_replay): kept between calls
     DevBuf v_s1, v_s2, v_tab, v_draws, v_ops, v_misc;
+    // compact (RLE) output of ga_align_batch_rle
+    DevBuf r_rle, r_len, r_rel, r_off, r_res, r_base, r_tmp, r_flag;
+    long long *h_base = nullptr;        // pinned: running end of the compact stream after each chunk
+    size_t h_base_cap = 0;
+    int64_t plan_ops_bytes = 0;         // bytes of the internal fixed-slice 2-bit ops of the current plan
     // timing
     cudaEvent_t ev[8] = {};
     std::vector<ChunkEvents> cev;
     float ms[GA_T_COUNT] = {};
-    bool timing_valid = false, timing_io = false;
+    bool timing_valid = false, timing_io = false, timing_rle = false;
 };
 
 // GA_DEBUG_TIMING=1: host-side phase times on stderr (diagnostics)
@@ -287,13 +295,15 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
                       &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
                       &ctx->d_opsoff, &ctx->d_len, &ctx->d_status, &ctx->l_colsum, &ctx->l_rowsum,
                       &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc, &ctx->l_xrow, &ctx->l_meta,
-                      &ctx->l_seg, &ctx->v_s1, &ctx->v_s2, &ctx->v_tab, &ctx->v_draws, &ctx->v_ops, &ctx->v_misc})
+                      &ctx->l_seg, &ctx->v_s1, &ctx->v_s2, &ctx->v_tab, &ctx->v_draws, &ctx->v_ops, &ctx->v_misc,
+                      &ctx->r_rle, &ctx->r_len, &ctx->r_rel, &ctx->r_off, &ctx->r_res, &ctx->r_base, &ctx->r_tmp, &ctx->r_flag})
         if (b->p) cudaFree(b->p);
+    if (ctx->h_base) cudaFreeHost(ctx->h_base);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->in_piece) if (e) cudaEventDestroy(e);
     if (ctx->in_begin) cudaEventDestroy(ctx->in_begin);
     for (auto &c : ctx->cev)
-        for (cudaEvent_t e : {c.in0, c.in1, c.f0, c.f1, c.w0, c.w1, c.out0, c.out1}) cudaEventDestroy(e);
+        for (cudaEvent_t e : {c.in0, c.in1, c.f0, c.f1, c.w0, c.w1, c.out0, c.out1, c.base, c.r0, c.r1}) cudaEventDestroy(e);
     for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -489,9 +499,9 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
     HostTimer ht;
     ctx->have_plan = false;
     int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30;
-    int64_t cells = 0;
+    int64_t cells = 0, ops_bytes = 0;
     {
-        struct Part { int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30; int64_t cells = 0, bad = -1; int why = 0; };
+        struct Part { int maxM = 0, maxN = 0, minM = 1 << 30, minN = 1 << 30; int64_t cells = 0, bad = -1, ops_bytes = 0; int why = 0; };
         Part parts[8];
         const bool check_ops = out_ops_off && !(flags & GA_F_COST_ONLY);
         parallel_for(n_pairs, [&](int t, int64_t lo, int64_t hi) {
@@ -511,6 +521,7 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
                 a.minM = std::min<int>(a.minM, (int)m);
                 a.minN = std::min<int>(a.minN, (int)n);
                 a.cells += m * n;
+                a.ops_bytes += (((m + n + 3) / 4) + 3) & ~(int64_t)3;
             }
             parts[t] = a;
         });
@@ -526,9 +537,12 @@ extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *
             minM = std::min(minM, a.minM);
             minN = std::min(minN, a.minN);
             cells += a.cells;
+            ops_bytes += a.ops_bytes;
         }
     }
-    return plan_common(ctx, s1_off, s2_off, n_pairs, flags, maxM, maxN, minM, minN, cells, ht);
+    int rc = plan_common(ctx, s1_off, s2_off, n_pairs, flags, maxM, maxN, minM, minN, cells, ht);
+    ctx->plan_ops_bytes = ops_bytes;
+    return rc;
 }
 
 // Planning for a fixed-length batch without offset arrays (every pair m x n).
@@ -539,7 +553,9 @@ static int plan_uniform(ga_ctx *ctx, int64_t m, int64_t n, int64_t n_pairs, uint
     CK(cudaSetDevice(ctx->device));
     HostTimer ht;
     ctx->have_plan = false;
-    return plan_common(ctx, nullptr, nullptr, n_pairs, flags, (int)m, (int)n, (int)m, (int)n, m * n * n_pairs, ht);
+    int rc = plan_common(ctx, nullptr, nullptr, n_pairs, flags, (int)m, (int)n, (int)m, (int)n, m * n * n_pairs, ht);
+    ctx->plan_ops_bytes = ((((m + n) + 3) / 4 + 3) & ~(int64_t)3) * n_pairs;
+    return rc;
 }
 
 static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
@@ -822,7 +838,7 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     ht.lap("plan: scratch + tile upload");
     while (ctx->cev.size() < ctx->chunks.size()) {
         ChunkEvents c;
-        for (cudaEvent_t *e : {&c.in0, &c.in1, &c.f0, &c.f1, &c.w0, &c.w1, &c.out0, &c.out1}) CK(cudaEventCreate(e));
+        for (cudaEvent_t *e : {&c.in0, &c.in1, &c.f0, &c.f1, &c.w0, &c.w1, &c.out0, &c.out1, &c.base, &c.r0, &c.r1}) CK(cudaEventCreate(e));
         ctx->cev.push_back(c);
     }
     ctx->cfg = cfg;
@@ -868,6 +884,11 @@ struct HostIO {
     const int64_t *off1 = nullptr, *off2 = nullptr, *ops_off = nullptr;
     int32_t *cost = nullptr, *len = nullptr, *status = nullptr;
     uint8_t *ops = nullptr;
+    // compact (RLE) output instead of cost / ops / len / status
+    PairResult *res = nullptr;
+    uint8_t *rle = nullptr;
+    int64_t *rle_off = nullptr;
+    int64_t rle_cap = 0;
 };
 
 // The chunk pipeline.  For chunk c (buffers / streams chosen by c & 1):
@@ -932,8 +953,39 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
                              d_len, d_status);
             CK(cudaGetLastError());
         }
+        if (io && io->rle) {
+            // compact result stream (ga_rle.cuh): runs per pair, scan, chunk base, write.  The chunk
+            // base chains through the chunks, which finish in order but on alternating streams.
+            if (c > 0 && !serial) CK(cudaStreamWaitEvent(sW, ctx->cev[c - 1].w1, 0));
+            const int g1 = (np + 255) / 256;
+            rle_count_kernel<<<g1, 256, 0, sW>>>(ch.pair_lo, np, d_ops, (const long long *)d_ops_off, ctx->uni_ops_stride,
+                                                 d_len, d_status, (int *)ctx->r_len.p);
+            size_t tmp_bytes = ctx->r_tmp.cap;
+            CK(cub::DeviceScan::ExclusiveScan(ctx->r_tmp.p, tmp_bytes, (const int *)ctx->r_len.p + ch.pair_lo,
+                                              (long long *)ctx->r_rel.p + ch.pair_lo, cuda::std::plus<>{}, 0LL, np, sW));
+            rle_base_kernel<<<1, 32, 0, sW>>>((long long *)ctx->r_base.p, (int)c, ch.pair_lo, np,
+                                              (const long long *)ctx->r_rel.p, (const int *)ctx->r_len.p);
+            rle_write_kernel<<<g1, 256, 0, sW>>>(ch.pair_lo, np, d_ops, (const long long *)d_ops_off, ctx->uni_ops_stride,
+                                                 d_len, d_status, d_cost, (const long long *)ctx->r_rel.p,
+                                                 (const long long *)ctx->r_base.p, (int)c, (long long)io->rle_cap,
+                                                 (uint8_t *)ctx->r_rle.p, (long long *)ctx->r_off.p,
+                                                 (PairResult *)ctx->r_res.p, (int *)ctx->r_flag.p,
+                                                 c + 1 == nc ? 1 : 0, (long long)ctx->n_pairs);
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(E.w1, sW));
-        if (io) {
+        if (io && io->rle) {
+            CK(cudaStreamWaitEvent(sOut, E.w1, 0));
+            CK(cudaEventRecord(E.out0, sOut));
+            CK(cudaMemcpyAsync(ctx->h_base + c + 1, (long long *)ctx->r_base.p + c + 1, 8, cudaMemcpyDeviceToHost, sOut));
+            CK(cudaEventRecord(E.base, sOut));
+            CK(cudaMemcpyAsync(io->res + ch.pair_lo, (PairResult *)ctx->r_res.p + ch.pair_lo, (size_t)np * sizeof(PairResult),
+                               cudaMemcpyDeviceToHost, sOut));
+            const size_t extra = c + 1 == nc ? 1 : 0;          // the closing offset travels with the last chunk
+            CK(cudaMemcpyAsync(io->rle_off + ch.pair_lo, (long long *)ctx->r_off.p + ch.pair_lo, ((size_t)np + extra) * 8,
+                               cudaMemcpyDeviceToHost, sOut));
+            CK(cudaEventRecord(E.out1, sOut));
+        } else if (io) {
             CK(cudaStreamWaitEvent(sOut, E.w1, 0));
             CK(cudaEventRecord(E.out0, sOut));
             CK(cudaMemcpyAsync(io->cost + ch.pair_lo, d_cost + ch.pair_lo, (size_t)np * 4, cudaMemcpyDeviceToHost, sOut));
@@ -947,6 +999,23 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
             CK(cudaEventRecord(E.out1, sOut));
         }
     }
+    if (io && io->rle) {
+        // The compact stream's size is known only on the device: as each chunk's running end
+        // arrives (8 bytes), its part of the stream is copied out.  The host waits per chunk
+        // while later chunks are still being filled and walked.
+        cudaStream_t sOut = ctx->aux[5];
+        ctx->h_base[0] = 0;
+        for (size_t c = 0; c < nc; ++c) {
+            ChunkEvents &E = ctx->cev[c];
+            CK(cudaEventSynchronize(E.base));
+            const long long lo = ctx->h_base[c], hi = std::min<long long>(ctx->h_base[c + 1], io->rle_cap);
+            CK(cudaEventRecord(E.r0, sOut));
+            if (hi > lo)
+                CK(cudaMemcpyAsync(io->rle + lo, (const uint8_t *)ctx->r_rle.p + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, sOut));
+            CK(cudaEventRecord(E.r1, sOut));
+        }
+        CK(cudaStreamWaitEvent(main, ctx->cev[nc - 1].r1, 0));
+    }
     // join: the caller-visible stream waits for the tails of every auxiliary stream
     if (!serial || io) {
         for (size_t c = (nc >= 2 ? nc - 2 : 0); c < nc; ++c) {
@@ -957,6 +1026,7 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
     CK(cudaEventRecord(ctx->ev[1], main));
     ctx->timing_valid = true;
     ctx->timing_io = io != nullptr;
+    ctx->timing_rle = io && io->rle;
     return GA_OK;
 }
 
@@ -990,6 +1060,10 @@ extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
         if (ctx->timing_io) {
             CK(cudaEventElapsedTime(&t, ctx->cev[c].out0, ctx->cev[c].out1));
             d2h += t;
+            if (ctx->timing_rle) {
+                CK(cudaEventElapsedTime(&t, ctx->cev[c].r0, ctx->cev[c].r1));
+                d2h += t;
+            }
         }
     }
     if (ctx->timing_io) CK(cudaEventElapsedTime(&h2d, ctx->in_begin, ctx->in_piece[ctx->in_pieces - 1]));
@@ -1021,12 +1095,21 @@ extern "C" int ga_get_timing(ga_ctx *ctx, float *ms) {
 // ------------------------------------------------------------------ host-buffer entry points
 // Shared by ga_align_batch (offset arrays) and ga_align_batch_uniform (every pair um x un, offset
 // arrays implicit: s1_off == s2_off == out_ops_off == nullptr).
+// compact output of ga_align_batch_rle (instead of cost / ops / ops_len / status)
+struct RleOut {
+    PairResult *res;
+    uint8_t *rle;
+    int64_t cap;
+    int64_t *off;
+};
+
 static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off, const uint8_t *s2,
                             const int64_t *s2_off, int64_t um, int64_t un, int64_t n_pairs, int32_t *out_cost,
                             uint8_t *out_ops, const int64_t *out_ops_off, int32_t *out_ops_len,
-                            int32_t *out_status, uint32_t flags) {
+                            int32_t *out_status, uint32_t flags, const RleOut *ro = nullptr) {
     const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
     const bool implicit = s1_off == nullptr;
+    if (ro && cost_only) return fail(ctx, GA_E_ARG, "the compact output has no cost-only form");
     if (n_pairs < 1 || n_pairs > 0x7fffff00LL) return fail(ctx, GA_E_ARG, "bad batch (1 <= n_pairs < 2^31)");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream, sIn = ctx->aux[4];
@@ -1037,7 +1120,8 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     const size_t b1 = (size_t)((t1 * bits + 7) / 8), b2 = (size_t)((t2 * bits + 7) / 8);
     const size_t offb = (size_t)(n_pairs + 1) * 8;
     const int64_t ops_stride = ((((um + un) + 3) / 4) + 3) & ~(int64_t)3;
-    const size_t opsb = cost_only ? 0 : (size_t)(implicit ? ops_stride * n_pairs : out_ops_off[n_pairs]);
+    // (compact output of a ragged batch: the internal slices are sized after planning)
+    const size_t opsb = cost_only ? 0 : (size_t)(implicit ? ops_stride * n_pairs : (ro ? 0 : out_ops_off[n_pairs]));
     int rc;
     if ((rc = ensure(ctx, ctx->d_s1, b1 + 16)) || (rc = ensure(ctx, ctx->d_s2, b2 + 16)) ||
         (rc = ensure(ctx, ctx->d_cost, (size_t)n_pairs * 4)))
@@ -1058,7 +1142,19 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     if (!implicit) {
         CK(cudaMemcpyAsync(ctx->d_off1.p, s1_off, offb, cudaMemcpyHostToDevice, sIn));
         CK(cudaMemcpyAsync(ctx->d_off2.p, s2_off, offb, cudaMemcpyHostToDevice, sIn));
-        if (!cost_only) CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
+        if (ro) {
+            // the internal 2-bit slices of a compact-output call: offsets made on the device
+            size_t t_a = 0;
+            CK(cub::DeviceScan::ExclusiveScan(nullptr, t_a, (long long *)nullptr, (long long *)nullptr, cuda::std::plus<>{}, 0LL, (int)n_pairs, sIn));
+            if ((rc = ensure(ctx, ctx->r_tmp, t_a + 256))) return rc;
+            ops_need_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, sIn>>>((const long long *)ctx->d_off1.p, (const long long *)ctx->d_off2.p,
+                                                                          (int)n_pairs, (long long *)ctx->d_opsoff.p);
+            size_t tb = ctx->r_tmp.cap;
+            CK(cub::DeviceScan::ExclusiveScan(ctx->r_tmp.p, tb, (long long *)ctx->d_opsoff.p, (long long *)ctx->d_opsoff.p,
+                                              cuda::std::plus<>{}, 0LL, (int)n_pairs, sIn));
+        } else if (!cost_only) {
+            CK(cudaMemcpyAsync(ctx->d_opsoff.p, out_ops_off, offb, cudaMemcpyHostToDevice, sIn));
+        }
     }
     // about 1 MB per piece: fine enough that the first chunk waits for little more than its own
     // letters, coarse enough that small batches are one copy per sequence set
@@ -1082,7 +1178,7 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     HostTimer ht;
     ctx->plan_for_io = true;
     rc = implicit ? plan_uniform(ctx, um, un, n_pairs, flags)
-                  : ga_plan_batch(ctx, s1_off, s2_off, n_pairs, cost_only ? nullptr : out_ops_off, flags);
+                  : ga_plan_batch(ctx, s1_off, s2_off, n_pairs, (cost_only || ro) ? nullptr : out_ops_off, flags);
     ctx->plan_for_io = false;
     if (rc) { cudaStreamSynchronize(sIn); return rc; }
     for (int k = EARLY; k < IN_PIECES; ++k)
@@ -1092,6 +1188,29 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     io.total1 = t1; io.total2 = t2; io.pieces = IN_PIECES;
     io.s1 = s1; io.s2 = s2; io.off1 = s1_off; io.off2 = s2_off; io.ops_off = out_ops_off;
     io.cost = out_cost; io.len = out_ops_len; io.status = out_status; io.ops = out_ops;
+    if (ro) {
+        const size_t nc = ctx->chunks.size();
+        size_t t_b = 0;
+        int max_np = 0;
+        for (const Chunk &ch : ctx->chunks) max_np = std::max(max_np, ch.pair_hi - ch.pair_lo);
+        CK(cub::DeviceScan::ExclusiveScan(nullptr, t_b, (const int *)nullptr, (long long *)nullptr, cuda::std::plus<>{}, 0LL, max_np, st));
+        if ((rc = ensure(ctx, ctx->d_ops, (size_t)ctx->plan_ops_bytes + 16)) || (rc = ensure(ctx, ctx->r_tmp, t_b + 256)) ||
+            (rc = ensure(ctx, ctx->r_len, (size_t)n_pairs * 4)) || (rc = ensure(ctx, ctx->r_rel, (size_t)n_pairs * 8)) ||
+            (rc = ensure(ctx, ctx->r_off, (size_t)(n_pairs + 1) * 8)) || (rc = ensure(ctx, ctx->r_res, (size_t)n_pairs * sizeof(PairResult))) ||
+            (rc = ensure(ctx, ctx->r_base, (nc + 1) * 8)) || (rc = ensure(ctx, ctx->r_flag, 16)) ||
+            (rc = ensure(ctx, ctx->r_rle, (size_t)ro->cap + 16)))
+            return rc;
+        if (ctx->h_base_cap < nc + 1) {
+            if (ctx->h_base) CK(cudaFreeHost(ctx->h_base));
+            ctx->h_base = nullptr;
+            ctx->h_base_cap = 0;
+            CK(cudaMallocHost(&ctx->h_base, (nc + 1 + 64) * 8));
+            ctx->h_base_cap = nc + 1 + 64;
+        }
+        CK(cudaMemsetAsync(ctx->r_base.p, 0, 8, st));
+        CK(cudaMemsetAsync(ctx->r_flag.p, 0, 16, st));
+        io.res = ro->res; io.rle = ro->rle; io.rle_cap = ro->cap; io.rle_off = ro->off;
+    }
     rc = run_pipeline(ctx, (const uint8_t *)ctx->d_s1.p, implicit ? nullptr : (const int64_t *)ctx->d_off1.p,
                       (const uint8_t *)ctx->d_s2.p, implicit ? nullptr : (const int64_t *)ctx->d_off2.p,
                       (int32_t *)ctx->d_cost.p, (uint8_t *)ctx->d_ops.p,
@@ -1101,7 +1220,23 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     ht.lap("align: enqueue pipeline");
     CK(cudaStreamSynchronize(st));
     ht.lap("align: wait for the device");
+    if (ro && ctx->h_base[ctx->chunks.size()] > ro->cap)
+        return fail(ctx, GA_E_NOMEM, "the compact operation stream needs %lld bytes, the buffer holds %lld",
+                    ctx->h_base[ctx->chunks.size()], (long long)ro->cap);
     return GA_OK;
+}
+
+extern "C" int ga_align_batch_rle(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off, int64_t m, const uint8_t *s2,
+                                  const int64_t *s2_off, int64_t n, int64_t n_pairs, ga_pair_result *out_res,
+                                  uint8_t *out_rle, int64_t rle_capacity, int64_t *out_rle_off, uint32_t flags) {
+    if (!ctx) return GA_E_ARG;
+    static_assert(sizeof(ga_pair_result) == sizeof(PairResult), "record layout");
+    if (!s1 || !s2 || !out_res || !out_rle || !out_rle_off || rle_capacity < 1 || (s1_off == nullptr) != (s2_off == nullptr))
+        return fail(ctx, GA_E_ARG, "null host buffer");
+    if (!s1_off && (m < 1 || n < 1)) return fail(ctx, GA_E_ARG, "fixed-length form needs m >= 1 and n >= 1");
+    const RleOut ro{reinterpret_cast<PairResult *>(out_res), out_rle, rle_capacity, out_rle_off};
+    return align_batch_impl(ctx, s1, s1_off, s2, s2_off, s1_off ? 0 : m, s1_off ? 0 : n, n_pairs, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, flags, &ro);
 }
 
 extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off,
@@ -1143,8 +1278,10 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     if (!sc.simple && sc.A > 64) return fail(ctx, GA_E_ARG, "table-driven schemes support at most 64 letters");
     {
         const long long big = (long long)(sc.max_cost + 1) * std::max(m, n);
-        const long long vmax = big + (std::min<long long>(m + LBAND, n + 32) + 2) * sc.max_cost + 3LL * sc.o;
-        if (4 * vmax + 3 >= 0x7fffffffLL) return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
+        // plain values (traceback kernels) and the fill's gap-shifted values, which go down to
+        // -4 * (sum of all gap-extension costs) and must stay clear of L_INVALID
+        const long long vmax = big + (m + n + LBAND + 2) * (long long)sc.max_cost + 3LL * sc.o;
+        if (4 * vmax + 3 >= 0x7f000000LL) return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -1178,7 +1315,7 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     CK(cudaMemcpyAsync(ctx->d_s2.p, s2, (size_t)n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->l_colsum.p, colsum.data(), colsum.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->l_rowsum.p, rowsum.data(), rowsum.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(ctx->l_brow.p, 0xFF, brow_b, st));      // -1 = boundary entry not yet written
+    CK(cudaMemsetAsync(ctx->l_brow.p, 0x80, brow_b, st));      // L_INVALID = boundary entry not yet written
     CK(cudaMemsetAsync(ctx->l_misc.p, 0, 256, st));
     // l_misc: [0] band counter, [1] cost, [2] status, [3] tiles, [4..5] n_ops
     int *misc = (int *)ctx->l_misc.p;
@@ -1196,11 +1333,17 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     a.nck = nck;
     a.big = (unsigned)((long long)(sc.max_cost + 1) * std::max(m, n));
     a.out_cost = misc + 1;
+    a.o4 = a.o4b = 4 * sc.o;
     const size_t table = sc.simple ? 0 : ((((size_t)(sc.A + 1) * sc.A + sc.A) * 4 + 15) & ~(size_t)15);
-    const int grid = std::min((nbands + LWARPS - 1) / LWARPS, ctx->sm_count * 4);
+    // one band-sweeping warp per scheduler: the chains of a lane give a lone warp enough
+    // independent work to keep issuing; more bands than warps queue on the atomic band counter
+    int blocks_per_sm = 1;
+    if (const char *e = getenv("GA_LONG_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, std::min(8, atoi(e)));
+    const int grid = std::min((nbands + LWARPS - 1) / LWARPS, ctx->sm_count * blocks_per_sm);
+    const bool fill_table = sc.A <= 64;          // shifted substitution table in shared memory
     CK(cudaEventRecord(ctx->ev[2], st));
-    if (sc.simple) long_fill_kernel<true><<<grid, 32 * LWARPS, 0, st>>>(sc, a);
-    else long_fill_kernel<false><<<grid, 32 * LWARPS, table, st>>>(sc, a);
+    if (fill_table) long_fill_kernel<1><<<grid, 32 * LWARPS, (size_t)(sc.A + 1) * sc.A * 4, st>>>(sc, a);
+    else long_fill_kernel<0><<<grid, 32 * LWARPS, 0, st>>>(sc, a);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[3], st));
     int launches = 1;

@@ -1,19 +1,35 @@
 // K2 + K5: one long pair on the whole chip (sm_100a).
 //
-// K2, long_fill_kernel -- fill without storing direction codes.  The DP matrix is cut
-// into bands of LBAND = 32 lanes x LR rows; one warp sweeps one band with the same
-// anti-diagonal wavefront as the batched kernel (ga_fill.cuh: lane g owns LR rows and
-// works on column t-g at step t; h/U of its bottom row go to lane g+1 by shuffle).
-// (LR = 4 rows per lane: 128-row bands.)  Band k reads the bottom row of band k-1 (h, U per column) from global memory, 32
-// columns at a time, behind a progress counter that band k-1 publishes with a
-// release fence -- a systolic pipeline of bands across all SMs.  Bands are claimed in
-// increasing order from an atomic counter, so a band's predecessor is always running
-// or finished: no deadlock, no co-residency requirement.  Kept for the traceback:
-//   * brow[k][j]      (h, U) of the last row of band k, every column  (8 B / column / band)
-//   * vchk[k][c][...] (h, L) of every row of band k at column c*LCC   (8 B / row / checkpoint)
-// i.e. 8/LBAND + 8/LCC = 0.09 bytes per cell instead of the 0.5 bytes per cell of stored
-// direction codes (0.94 GB instead of 5 GB for 100 kb x 100 kb); taller bands and sparser
-// checkpoints shrink it further at the price of more recomputation in K5.
+// K2, long_fill_kernel -- fill without storing direction codes.  The DP matrix is cut into
+// bands of LBAND = 32 lanes x LR rows; one warp sweeps one band as an anti-diagonal wavefront,
+// bands pipelined across all SMs (band k reads the bottom row of band k-1 from global memory).
+//
+//   * ILP inside a lane.  The LR rows of a lane form LNC chains of LELL rows.  Chain q = g*LNC + k
+//     (lane g, chain k) works at step t on column t - q + 1: the chains of a lane sit on different
+//     columns, so their cell updates are independent and interleave in the instruction stream; only
+//     the LELL rows of one chain depend on each other within a step.  (Round 1 ran all rows of a
+//     lane on one column: one serial chain of 4 cells, a lone warp issuing every ~3.75 cycles.)
+//     The chains of a step run bottom-up (chain LNC-1 first), so the shuffled inputs of chain 0
+//     are needed last and the shuffle latency hides behind the other chains.
+//   * Gap-shifted values.  X^(i,j) = 4 * (X(i,j) - GH(j) - GV(i)) with GH / GV the running sums of
+//     the per-letter horizontal / vertical gap-extension costs.  In this domain
+//         d0 = h^(i-1,j-1) + 4*(sub(a,b) - gap_h[b] - gap_v[a])          (one table load + add)
+//         h  = min3(d0, L^(i,j-1), U^(i-1,j))                            VIMNMX3
+//         L^ = min(h + 4o, L^(i,j-1)),  U^ = min(h + 4o, U^(i-1,j))      2 x VIADDMNMX
+//     -- the two gap-extension additions per cell are gone, and per-letter gap costs cost nothing.
+//     L(i,j) = min(D0+o, D1, D2+o) is the level-1 candidate handed to column j+1, U(i,j) =
+//     min(D0+o, D1+o, D2) the level-2 candidate handed to row i+1 (reference cell update,
+//     globaligner.py:331-363).  The shift is the same for the three candidates of a cell, so every
+//     comparison -- and every tie -- is unchanged.  Exact integers throughout.
+//   * Boundary hand-off.  (h^, U^) of a band's last row go to global memory with one 64-bit store
+//     per column; the consumer fetches them LSYNC columns at a time, one block AHEAD of its
+//     wavefront (the load latency hides behind a block of steps), synchronised by the data itself:
+//     entries are pre-set to L_INVALID and re-polled only if they have not arrived.  Bands are claimed in
+//     increasing order from an atomic counter, so a band's predecessor is always running or
+//     finished: no deadlock, no co-residency requirement.
+// Kept for the traceback (shifted values; K5 adds the shift back):
+//   * brow[k][j]      (h^, U^) of the last row of band k, every column  (8 B / column / band)
+//   * vchk[k][c][...] (h^, L^) of every row of band k at column c*LCC   (8 B / row / checkpoint)
 //
 // K5, long_trace_kernel -- linear-space traceback by checkpoint + recompute (the
 // reference has no such mode; SURVEY.md 7.3 option (a)).  One warp repeats: re-fill,
@@ -32,23 +48,42 @@
 
 namespace ga {
 
-constexpr int LR = 4;               // rows per lane (more, shorter bands: the pipeline is latency-bound)
+#ifndef GA_LONG_ELL
+#define GA_LONG_ELL 3
+#endif
+#ifndef GA_LONG_NC
+#define GA_LONG_NC 2
+#endif
+constexpr int LELL = GA_LONG_ELL;   // rows per chain (updated one after the other within a step)
+constexpr int LNC = GA_LONG_NC;     // chains per lane (independent within a step)
+constexpr int LR = LELL * LNC;      // rows per lane
 constexpr int LBAND = 32 * LR;      // rows per band
 constexpr int LCC = 128;            // columns between vertical checkpoints
-constexpr int LSYNC = 16;           // columns per boundary-row fetch (sets the lag between bands)
+#ifndef GA_LONG_LSYNC
+#define GA_LONG_LSYNC 16
+#endif
+constexpr int LSYNC = GA_LONG_LSYNC; // columns per boundary-row fetch = steps per unrolled block
+constexpr int L_INVALID = (int)0x80808080;   // boundary entry not yet written (memset 0x80)
+static_assert(LNC <= 16 && LR <= 16 && (LSYNC == 8 || LSYNC == 16 || LSYNC == 32), "chains per lane / rows per lane / block length");
 
 struct LongArgs {
     const uint8_t *s1, *s2;         // device letters
     int m, n;
     const int *colsum;              // m+1: o + sum_{t<=i} gap_v[s1[t-1]]  (column-0 level-2 values), [0] = o
     const int *rowsum;              // n+1: o + sum_{t<=j} gap_h[s2[t-1]]  (row-0 level-1 values)
-    int2 *brow;                     // nbands x (n+1)
-    int2 *vchk;                     // nbands x nck x 32 x LR
+    int2 *brow;                     // nbands x (n+1), shifted values
+    int2 *vchk;                     // nbands x nck x 32 x LR, shifted values
     int *band_counter;
     int nbands, nck;
     unsigned big;                   // reference sentinel (max_cost+1)*max(m,n)
     int *out_cost;
+    int o4, o4b;                    // both 4 * gap_open, as two parameters (see FillConsts)
 };
+
+// 4 * (GH(j) + GV(i)): what the fill subtracted from the values of cell (i, j)
+__device__ __forceinline__ int long_shift(const LongArgs &a, int o, int i, int j) {
+    return 4 * ((a.rowsum[j] - o) + (a.colsum[min(i, a.m)] - o));
+}
 
 template <bool SIMPLE>
 struct LongLane {
@@ -79,7 +114,8 @@ __device__ __forceinline__ void long_load_rows(const SchemeDev &sc, const LongAr
     }
 }
 
-// one column of LR cells for this lane; returns (hb, ub) through references
+// one column of LR cells for this lane (traceback kernels: plain x4 domain with level tags);
+// returns (hb, ub) through references
 template <bool SIMPLE, bool CODES>
 __device__ __forceinline__ void long_cells(const SchemeDev &sc, const int *s_sub, LongLane<SIMPLE> &ln,
                                            unsigned &diag_io, unsigned up, unsigned bv, unsigned ghT,
@@ -114,134 +150,288 @@ __device__ __forceinline__ void long_cells(const SchemeDev &sc, const int *s_sub
 // ---------------------------------------------------------------------------- K2
 constexpr int LWARPS = 4;           // independent band-sweeping warps per block (one per scheduler)
 
-// One block of LSYNC steps of a band sweep, fully unrolled (compile-time shuffle lanes and store
-// offsets).  The fill keeps no direction codes, so it needs no argmin tags: values stay
-// multiples of 4 (the traceback kernels' domain) and the per-cell tag clears disappear --
-// min over tagged values, cleared, equals min over the untagged ones.  CHECK = false is the
-// steady state (every lane inside the matrix for the whole block).
-template <bool SIMPLE, bool CHECK>
-__device__ __forceinline__ void long_fill_block(LongLane<SIMPLE> &ln, const int *s_sub, const int *s_gh,
-                                                unsigned &rh_prev, unsigned &hb, unsigned &ub, unsigned &bv,
-                                                unsigned bblk, int2 tblk, int g, int j0, int N, int2 *brow_j0,
-                                                int2 *my_vchk, unsigned gh4c, unsigned o4, unsigned mm4) {
+// MODE 1: substitution costs (already shifted by the gap costs) from a table in shared memory --
+// any scheme with A <= 64 letters.  MODE 0: compare-and-select for simple schemes over larger
+// alphabets (the table would not fit).
+//
+// The column letters run ONE STEP AHEAD of the cells: at step t every chain already holds the
+// letter of the column it works on (bv) and the substitution costs of its rows against it (sv),
+// fetched during step t-1; during step t it fetches those of step t+1.  Letters simply shift
+// along the chains (chain q's letter at step t+1 is chain q-1's at step t), so neither the
+// shuffle that moves them between lanes nor the table load sits on the path of the cell update.
+template <int MODE>
+struct FillLane {
+    unsigned aw[LR];        // MODE 1: shared-space byte address of the row letter's table row; MODE 0: the letter
+    int hl[LR], Lp[LR];     // h^ and L^ of my rows at the last column their chain computed
+    int sv[LR];             // shifted substitution cost of my rows at their chain's current column
+    int ub[LNC];            // U^ out of the last row of chain k (input of the row below)
+    int hd[LNC];            // h^ of the last row of chain k one column earlier (diagonal input of the row below)
+    unsigned bv[LNC];       // letter of chain k's current column (MODE 1: its byte offset in a table row)
+    int rh_prev;            // h^ of the row above my first row, one column earlier
+    int rh_in, ru_in;       // h^ / U^ of the row above my first row at my chain 0's next column (shuffled a step ahead)
+};
+
+// (o4 and o4b hold the same number but arrive as two kernel parameters: computed in the kernel
+// as 4 * o the assembler folds the multiply into an IMAD and emits h + 4o once plus two plain
+// minima -- three instructions -- instead of two fused VIADDMNMX.)
+struct FillConsts {
+    int o4, o4b;            // 4 * gap_open
+    int cm4, cx4;           // MODE 0: shifted match / mismatch cost
+    unsigned k1;            // runtime 1 (IMAD forms, see SchemeDev::k_one)
+};
+
+// shifted substitution cost of row r against column letter b
+template <int MODE>
+__device__ __forceinline__ int long_sub(const FillLane<MODE> &ln, int r, unsigned b, const FillConsts &c) {
+    if (MODE == 1) {
+        int v;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(ln.aw[r] * c.k1 + b));        // address add as IMAD (FMA pipe)
+        return v;
+    }
+    return ln.aw[r] != b ? c.cx4 : c.cm4;
+}
+
+// The LELL cells of chain K at its current column.  diag / up: h^(i-1, j-1) and U^(i-1, j) of the
+// row above the chain's first row.
+template <int MODE, int K>
+__device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up, const FillConsts &c) {
+#pragma unroll
+    for (int r = K * LELL; r < (K + 1) * LELL; ++r) {
+        const int d0 = (int)((unsigned)diag * c.k1 + (unsigned)ln.sv[r]);           // IMAD
+        const int h = __vimin3_s32(d0, ln.Lp[r], up);
+        diag = ln.hl[r];
+        ln.hl[r] = h;
+        ln.Lp[r] = __viaddmin_s32(h, c.o4, ln.Lp[r]);
+        up = __viaddmin_s32(h, c.o4b, up);
+    }
+    ln.hd[K] = diag;
+    ln.ub[K] = up;
+}
+
+// chain K of one step: my column is j (chain K lags chain 0 by K columns)
+template <int MODE, bool CHECK, int K>
+__device__ __forceinline__ void long_one_chain(FillLane<MODE> &ln, int j, int N, int diag, int up,
+                                               bool last_lane, int2 *brow_j, const FillConsts &c) {
+    if (!CHECK || (j >= 1 && j <= N)) {
+        long_chain<MODE, K>(ln, diag, up, c);
+        if (K == LNC - 1 && last_lane) __stcg(brow_j, make_int2(ln.hl[LR - 1], ln.ub[LNC - 1]));
+    }
+}
+
+// chains K, K-1, ..., 1 of one step (each reads the state its upper neighbour chain had one step ago)
+template <int MODE, bool CHECK, int K>
+__device__ __forceinline__ void long_mid_chains(FillLane<MODE> &ln, int j0, int N, bool last_lane, int2 *brow_j,
+                                                const FillConsts &c) {
+    if constexpr (K >= 1) {
+        long_one_chain<MODE, CHECK, K>(ln, j0 - K, N, ln.hd[K - 1], ln.ub[K - 1], last_lane, brow_j, c);
+        long_mid_chains<MODE, CHECK, K - 1>(ln, j0, N, last_lane, brow_j, c);
+    }
+}
+
+// (h^, L^) of the rows of chain K to the column checkpoint
+template <int MODE, int K>
+__device__ __forceinline__ void long_store_chain(const FillLane<MODE> &ln, int2 *dst) {
+#pragma unroll
+    for (int r = K * LELL; r < (K + 1) * LELL; ++r) __stcg(dst + r, make_int2(ln.hl[r], ln.Lp[r]));
+}
+
+// One block of LSYNC steps of a band sweep, fully unrolled (compile-time store offsets).  CHECK =
+// false is the steady state (every chain inside the matrix for the whole block).  `slot`: shared-
+// space address of this block's LSYNC staged inputs of lane 0: entry u = (h^, U^ of the row above the
+// band at column t0 + 1 + u, letter of the NEXT column), 16 bytes; every lane loads entry u + 1
+// during step u (a broadcast), lane 0 keeps it.
+//
+// A lone warp issues in order, so every value that crosses lanes is requested long before it is
+// used: the bottom row of my last chain is shuffled to the lane below right after that chain's
+// update (first thing in a step) and consumed by the lane below's chain 0 at the END of its next
+// step (ln.rh_in / ln.ru_in carry it across); the letter shuffle is issued first in a step and consumed
+// after all cell updates.
+//
+// Column checkpoints (CK blocks only): at step t the only chain of the band that can sit on a
+// multiple of LCC is chain (t + 1) mod LCC (if the band has that many chains) -- a warp-uniform
+// fact, so the test is a uniform branch and the store a predicated one in the owning lane.  Blocks
+// in which no step can hit (most of them) are instantiated without that code.
+template <int MODE, bool CHECK, bool CK>
+__device__ __forceinline__ void long_fill_block(FillLane<MODE> &ln, unsigned slot, int g, int t0,
+                                                int N, int2 *my_brow, int2 *band_vchk, const FillConsts &c) {
+    static_assert(32 * LNC <= LCC, "at most one chain of a band on a checkpoint column per step");
+    const int q0 = g * LNC;
+    const bool last_lane = g == 31;
+    int2 *brow_j0 = my_brow + (t0 - (q0 + LNC - 1) + 1);   // column of my last chain at the block's first step
+    int4 e;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(slot));
 #pragma unroll
     for (int u = 0; u < LSYNC; ++u) {
-        const int j = j0 + u;
-        unsigned rh = __shfl_up_sync(FULL, hb, 1);
-        unsigned ru = __shfl_up_sync(FULL, ub, 1);
-        unsigned bin = __shfl_up_sync(FULL, bv, 1);
-        const unsigned b0 = __shfl_sync(FULL, bblk, u);
-        const unsigned th = (unsigned)__shfl_sync(FULL, tblk.x, u);
-        const unsigned tu = (unsigned)__shfl_sync(FULL, tblk.y, u);
-        if (g == 0) { bin = b0; rh = th; ru = tu; }
-        bv = bin;
-        if (!CHECK || (j >= 1 && j <= N)) {
-            unsigned diag = rh_prev, up = ru;
-            rh_prev = rh;
-            const unsigned gh4 = SIMPLE ? gh4c : (unsigned)(s_gh[bv] - 1);
-#pragma unroll
-            for (int r = 0; r < LR; ++r) {
-                unsigned d0;
-                if (SIMPLE) d0 = diag + (ln.aw[r] != bv ? mm4 : 0u);
-                else d0 = diag + (unsigned)s_sub[ln.aw[r] + bv];
-                const unsigned d1 = ln.Lp[r] + gh4;
-                const unsigned d2 = up + ln.gvT[r];
-                const unsigned h = (unsigned)__vimin3_s32((int)d0, (int)d1, (int)d2);
-                diag = ln.hl[r];
-                ln.hl[r] = h;
-                ln.Lp[r] = (unsigned)__viaddmin_s32((int)h, (int)o4, (int)d1);
-                up = (unsigned)__viaddmin_s32((int)h, (int)o4, (int)d2);
+        const unsigned nbs = __shfl_up_sync(FULL, ln.bv[LNC - 1], 1);      // my chain 0's letter of the NEXT step
+        const int j0 = t0 + u - q0 + 1;                    // column of my chain 0 at this step
+        int rh_next = 0, ru_next = 0;
+        if constexpr (LNC > 1) {
+            long_one_chain<MODE, CHECK, LNC - 1>(ln, j0 - (LNC - 1), N, ln.hd[LNC - 2], ln.ub[LNC - 2], last_lane,
+                                                 brow_j0 + u, c);
+            rh_next = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
+            ru_next = __shfl_up_sync(FULL, ln.ub[LNC - 1], 1);
+            long_mid_chains<MODE, CHECK, LNC - 2>(ln, j0, N, last_lane, brow_j0 + u, c);
+        }
+        {   // chain 0: the row above is the last row of the lane above (lane 0: of the band above)
+            int rh = ln.rh_in, ru = ln.ru_in;
+            if (g == 0) { rh = e.x; ru = e.y; }
+            if (!CHECK || (j0 >= 1 && j0 <= N)) {
+                const int diag = ln.rh_prev;
+                ln.rh_prev = rh;
+                long_chain<MODE, 0>(ln, diag, ru, c);
+                if (LNC == 1 && last_lane) __stcg(brow_j0 + u, make_int2(ln.hl[LR - 1], ln.ub[0]));
             }
-            hb = ln.hl[LR - 1];
-            ub = up;
-            if (g == 31) __stcg(brow_j0 + u, make_int2((int)hb, (int)ub));   // one 64-bit store
-            if ((j & (LCC - 1)) == 0) {
-                int2 *dst = my_vchk + (size_t)(j / LCC) * (32 * LR);
+        }
+        if constexpr (LNC == 1) {
+            rh_next = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
+            ru_next = __shfl_up_sync(FULL, ln.ub[0], 1);
+        }
+        ln.rh_in = rh_next;
+        ln.ru_in = ru_next;
+        // letters and substitution costs of the next step (loads issued now, used a step later)
+        const unsigned nb0 = g == 0 ? (unsigned)e.z : nbs;
 #pragma unroll
-                for (int r = 0; r < LR; ++r) __stcg(dst + r, make_int2((int)ln.hl[r], (int)ln.Lp[r]));
+        for (int k = LNC - 1; k >= 0; --k) ln.bv[k] = k == 0 ? nb0 : ln.bv[k - 1];
+#pragma unroll
+        for (int r = 0; r < LR; ++r) ln.sv[r] = long_sub<MODE>(ln, r, ln.bv[r / LELL], c);
+        if (u + 1 < LSYNC)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                         : "r"(slot + 16u * (u + 1)));
+        if constexpr (CK || CHECK) {
+            const int qs = (t0 + u + 1) & (LCC - 1);       // warp-uniform
+            if (qs < 32 * LNC) {
+                const int gs = qs / LNC, ks = qs - gs * LNC;
+                const int j = t0 + u - qs + 1;             // a multiple of LCC
+                if (!CHECK || (j >= 1 && j <= N)) {
+                    int2 *dst = band_vchk + ((size_t)(j / LCC) * 32 + gs) * LR;
+                    if (g == gs) {
+                        if (LNC > 0 && ks == 0) long_store_chain<MODE, 0>(ln, dst);
+                        if (LNC > 1 && ks == 1) long_store_chain<MODE, (LNC > 1 ? 1 : 0)>(ln, dst);
+                        if (LNC > 2 && ks == 2) long_store_chain<MODE, (LNC > 2 ? 2 : 0)>(ln, dst);
+                        if (LNC > 3 && ks == 3) long_store_chain<MODE, (LNC > 3 ? 3 : 0)>(ln, dst);
+                    }
+                }
             }
         }
     }
 }
 
-template <bool SIMPLE>
+template <int MODE>
 __global__ void __launch_bounds__(32 * LWARPS)
 long_fill_kernel(const SchemeDev sc, const LongArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *s_sub = reinterpret_cast<int *>(smem_raw);
-    int *s_gh = s_sub;
-    if (!SIMPLE) {
+    __shared__ int4 s_stage[LWARPS][2][LSYNC];          // lane 0's inputs, two blocks per warp
+    int *s_tab = reinterpret_cast<int *>(smem_raw);
+    if (MODE == 1) {
+        // shifted substitution costs 4*(sub(a,b) - gap_h[b] - gap_v[a]); row A = padding letter
+        // (rows past the end of seq_1: sub4 row A and gv_raw[A] are zero)
         const int n_sub = (sc.A + 1) * sc.A;
-        s_gh = s_sub + n_sub;
-        for (int k = threadIdx.x; k < n_sub; k += blockDim.x) s_sub[k] = sc.sub4[k];
-        for (int k = threadIdx.x; k < sc.A; k += blockDim.x) s_gh[k] = sc.gh4t[k];
+        for (int k = threadIdx.x; k < n_sub; k += blockDim.x) {
+            const int ai = k / sc.A, b = k - ai * sc.A;
+            s_tab[k] = sc.sub4[k] - 4 * sc.gh_raw[b] - 4 * sc.gv_raw[ai];
+        }
         __syncthreads();
     }
+    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(s_tab);
     const int g = threadIdx.x & 31;     // the warps of a block never synchronise with each other again
-    const unsigned o4 = 4u * sc.o, mm4 = 4u * sc.mm;
-    const unsigned gh4c = 4u * sc.gh;
+    int4 *my_stage = &s_stage[threadIdx.x >> 5][0][0];
+    const unsigned stage_base = (unsigned)__cvta_generic_to_shared(my_stage);
+    FillConsts c;
+    c.o4 = a.o4;
+    c.o4b = a.o4b;
+    c.cm4 = -4 * (sc.gh + sc.gv);
+    c.cx4 = 4 * (sc.mm - sc.gh - sc.gv);
+    c.k1 = sc.k_one;
     const unsigned big = a.big;
     // hot fields in registers (kernel parameters live in constant memory; an LDC inside
     // the step loop sits on the critical path of a lone warp)
     const int N = a.n, M = a.m;
     const uint8_t *const S2 = a.s2;
     const int *const ROWSUM = a.rowsum;
-    const unsigned O = (unsigned)sc.o;
+    const int O = sc.o;
     for (;;) {
         int band = 0;
         if (g == 0) band = atomicAdd(a.band_counter, 1);
         band = __shfl_sync(FULL, band, 0);
         if (band >= a.nbands) break;
         const int ib = band * LBAND + g * LR;
-        LongLane<SIMPLE> ln;
-        long_load_rows<SIMPLE>(sc, a, ib, ln);
+        FillLane<MODE> ln;
+#pragma unroll
+        for (int k = 0; k < LNC; ++k) { ln.ub[k] = 0; ln.hd[k] = 0; ln.bv[k] = 0u; }
+        if (g == 0) ln.bv[0] = MODE == 1 ? 4u * (unsigned)S2[0] : (unsigned)S2[0];     // chain 0 of lane 0 starts on column 1
 #pragma unroll
         for (int r = 0; r < LR; ++r) {
-            const unsigned c = (unsigned)a.colsum[min(ib + r + 1, a.m)];
-            ln.hl[r] = min(big, c) << 2;
-            ln.Lp[r] = min(big, c + sc.o) << 2;
-            ln.gvT[r] -= 2u;                         // untagged vertical gap cost (4 * gap_v)
+            const int row = ib + r;
+            if (MODE == 1) ln.aw[r] = tab_base + 4u * (unsigned)sc.A * (row < M ? (unsigned)a.s1[row] : (unsigned)sc.A);
+            else ln.aw[r] = row < M ? (unsigned)a.s1[row] : (unsigned)PAD_A;
+            const int cs = a.colsum[min(ib + r + 1, M)];
+            const int gvs = cs - O;
+            ln.hl[r] = 4 * ((int)min(big, (unsigned)cs) - gvs);
+            ln.Lp[r] = 4 * ((int)min(big, (unsigned)(cs + O)) - gvs);
+            ln.sv[r] = long_sub<MODE>(ln, r, ln.bv[r / LELL], c);
         }
-        unsigned rh_prev = 0;
-        if (ib != 0) rh_prev = min(big, (unsigned)a.colsum[min(ib, a.m)]) << 2;
+        ln.rh_prev = 0;
+        if (ib != 0) {
+            const int cs = a.colsum[min(ib, M)];
+            ln.rh_prev = 4 * ((int)min(big, (unsigned)cs) - (cs - O));
+        }
         int2 *my_brow = a.brow + (size_t)band * (N + 1);
         const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (N + 1);
-        int2 *my_vchk = a.vchk + ((size_t)band * a.nck) * (32 * LR) + (size_t)g * LR;
+        int2 *band_vchk = a.vchk + ((size_t)band * a.nck) * (32 * LR);
 
-        unsigned hb = 0, ub = 0, bv = 0;
-        const int nsteps = N + 31;
-        for (int t0 = 0; t0 < nsteps; t0 += LSYNC) {
-            // next LSYNC columns: letters of seq_2 and the boundary row above this band
-            const int c0 = t0 + 1;                          // first column of the block (1-based)
-            const int cj = c0 + (g & (LSYNC - 1));          // lanes >= LSYNC duplicate a valid column
-            const unsigned bblk = cj <= N ? (unsigned)S2[cj - 1] : (SIMPLE ? (unsigned)PAD_B : 0u);
-            int2 tblk = make_int2(0, 0);
-            if (band > 0) {
-                if (cj <= N) {
-                    do { tblk = ld_volatile_int2(up_brow + cj); } while (tblk.x < 0);   // -1 = not yet written
-                }
-                __syncwarp();
-            } else {
-                const unsigned rj = (unsigned)ROWSUM[min(cj, N)];
-                tblk = make_int2((int)(min(big, rj) << 2), (int)(min(big, rj + O) << 2));
+        // Raw loads for the LSYNC columns from t0 + 1 on (lanes >= LSYNC duplicate a valid column): the
+        // letter of the column AFTER mine and the boundary-row entry above this band (which may still
+        // be L_INVALID; band 0: the row-0 running sum instead).  Nothing here USES a loaded value --
+        // a lone warp would stall on it -- that happens one block later, in `stage`.
+        auto fetch = [&](int t0, unsigned &braw, int2 &traw) {
+            const int cj = t0 + 1 + (g & (LSYNC - 1));
+            braw = 0u;
+            traw = make_int2(0, 0);
+            if (cj + 1 <= N) braw = (unsigned)S2[cj];
+            if (cj <= N) {
+                if (band > 0) traw = ld_volatile_int2(up_brow + cj);
+                else traw.x = ROWSUM[cj];
             }
-            const int j0 = t0 - g + 1;                      // my column at the first step of the block
-            int2 *brow_j0 = my_brow + j0;
-            if (t0 >= 31 && t0 + LSYNC <= N)
-                long_fill_block<SIMPLE, false>(ln, s_sub, s_gh, rh_prev, hb, ub, bv, bblk, tblk, g, j0, N,
-                                               brow_j0, my_vchk, gh4c, o4, mm4);
-            else
-                long_fill_block<SIMPLE, true>(ln, s_sub, s_gh, rh_prev, hb, ub, bv, bblk, tblk, g, j0, N,
-                                              brow_j0, my_vchk, gh4c, o4, mm4);
+        };
+        const int nsteps = N + 32 * LNC - 1;
+        unsigned bnext;
+        int2 tnext;
+        fetch(0, bnext, tnext);
+        ln.rh_in = 0;
+        ln.ru_in = 0;
+        __syncwarp();                       // the previous band's last reads of the staging area are done
+        for (int t0 = 0, blk = 0; t0 < nsteps; t0 += LSYNC, ++blk) {
+            int2 tblk = tnext;
+            const int cj = t0 + 1 + (g & (LSYNC - 1));
+            if (band > 0) {                 // entries requested one block ago: poll only what has not arrived
+                if (cj <= N)
+                    while (tblk.x == L_INVALID) tblk = ld_volatile_int2(up_brow + cj);
+            } else if (cj <= N) {
+                const int rj = tblk.x;
+                const int ghs = rj - O;
+                tblk = make_int2(4 * ((int)min(big, (unsigned)rj) - ghs), 4 * ((int)min(big, (unsigned)(rj + O)) - ghs));
+            }
+            if (g < LSYNC) my_stage[(blk & 1) * LSYNC + g] = make_int4(tblk.x, tblk.y, (int)(MODE == 1 ? 4u * bnext : bnext), 0);
+            __syncwarp();
+            if (t0 + LSYNC < nsteps) fetch(t0 + LSYNC, bnext, tnext);
+            const unsigned slot = stage_base + (unsigned)((blk & 1) * LSYNC * 16);
+            const int tq = t0 & (LCC - 1);
+            const bool ck = tq < 32 * LNC || tq + LSYNC >= LCC;        // can a step of this block hit a checkpoint column?
+            if (t0 >= 32 * LNC && t0 + LSYNC <= N) {
+                if (ck) long_fill_block<MODE, false, true>(ln, slot, g, t0, N, my_brow, band_vchk, c);
+                else long_fill_block<MODE, false, false>(ln, slot, g, t0, N, my_brow, band_vchk, c);
+            } else {
+                long_fill_block<MODE, true, true>(ln, slot, g, t0, N, my_brow, band_vchk, c);
+            }
         }
-        // the last active step of every lane was column N: hl[] now holds h(row, N)
+        // the last active step of every chain was column N: hl[] now holds h^(row, N)
         if (band == (M - 1) / LBAND && g == ((M - 1) % LBAND) / LR) {
             const int rm = (M - 1) % LR;
-            unsigned v = 0;
+            int v = 0;
 #pragma unroll
             for (int r = 0; r < LR; ++r)
                 if (r == rm) v = ln.hl[r];
-            *a.out_cost = (int)(v >> 2);
+            *a.out_cost = (v >> 2) + (ROWSUM[N] - O) + (a.colsum[M] - O);
         }
     }
 }
@@ -279,16 +469,18 @@ __device__ __forceinline__ unsigned long_restore(const SchemeDev &sc, const Long
         }
         return ib == 0 ? 0u : (min(big, (unsigned)a.colsum[min(ib, a.m)]) << 2);
     }
+    // (the fill keeps gap-shifted values, see long_shift)
     const int2 *src = a.vchk + (((size_t)band * a.nck + jc / LCC) * 32 + g) * LR;
 #pragma unroll
     for (int r = 0; r < LR; ++r) {
         const int2 v = __ldcg(src + r);
-        ln.hl[r] = (unsigned)v.x;
-        ln.Lp[r] = (unsigned)v.y;
+        const int sh = long_shift(a, sc.o, ib + r + 1, jc);
+        ln.hl[r] = (unsigned)(v.x + sh);
+        ln.Lp[r] = (unsigned)(v.y + sh);
     }
     unsigned above = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);   // bottom-row h of the lane above
     if (g == 0) {
-        if (band > 0) above = (unsigned)__ldcg(a.brow + (size_t)(band - 1) * (a.n + 1) + jc).x;
+        if (band > 0) above = (unsigned)(__ldcg(a.brow + (size_t)(band - 1) * (a.n + 1) + jc).x + long_shift(a, sc.o, band * LBAND, jc));
         else above = min(big, (unsigned)a.rowsum[jc]) << 2;
     }
     return above;
@@ -312,6 +504,9 @@ __device__ __forceinline__ void long_refill_codes(const SchemeDev &sc, const Lon
             bblk = (unsigned)a.s2[cj - 1];
             if (band > 0) {
                 tblk = __ldcg(up_brow + cj);
+                const int sh = long_shift(a, sc.o, band * LBAND, cj);
+                tblk.x += sh;
+                tblk.y += sh;
             } else {
                 const unsigned rj = (unsigned)a.rowsum[cj];
                 tblk = make_int2((int)(min(k.big, rj) << 2), (int)(min(k.big, rj + sc.o) << 2));
@@ -521,6 +716,9 @@ long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
             bblk = (unsigned)a.s2[cj - 1];
             if (band > 0) {
                 tblk = __ldcg(up_brow + cj);
+                const int sh = long_shift(a, sc.o, band * LBAND, cj);
+                tblk.x += sh;
+                tblk.y += sh;
             } else {
                 const unsigned rj = (unsigned)a.rowsum[cj];
                 tblk = make_int2((int)(min(k.big, rj) << 2), (int)(min(k.big, rj + sc.o) << 2));

@@ -86,6 +86,18 @@ def _mutate_fixed(rng, s1: np.ndarray, n_letters: int, p_sub: float, p_ins: floa
 _BLOCK = 4096      # pairs per independently seeded block (keeps prefixes stable)
 
 
+def _for_blocks(fn, jobs):
+    """Blocks are independent (own seed, own output rows): large workloads are drawn on a few
+    host threads (numpy releases the GIL inside its generators and ufuncs)."""
+    import os
+    threads = min(len(jobs), max(1, min(16, (os.cpu_count() or 1))))
+    if threads <= 1 or len(jobs) < 8:
+        return [fn(j) for j in jobs]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        return list(pool.map(fn, jobs))
+
+
 def dna_fixed(n_pairs: int, length: int, seed: int, p_sub=0.08, p_ins=0.01, p_del=0.01,
               first_block: int = 0) -> PairBatch:
     """Configs 2 and 5: `n_pairs` DNA pairs, both of exactly `length` letters.
@@ -95,13 +107,17 @@ def dna_fixed(n_pairs: int, length: int, seed: int, p_sub=0.08, p_ins=0.01, p_de
     skips that many blocks: rank r of a sharded run generates only its own shard."""
     s1 = np.empty((n_pairs, length), dtype=np.uint8)
     s2 = np.empty((n_pairs, length), dtype=np.uint8)
-    for blk, lo in enumerate(range(0, n_pairs, _BLOCK)):
+
+    def one(job):
+        blk, lo = job
         hi = min(n_pairs, lo + _BLOCK)
         rng = np.random.default_rng([seed, first_block + blk])
         a = rng.integers(0, 4, size=(_BLOCK, length), dtype=np.uint8)
         b = _mutate_fixed(rng, a, 4, p_sub, p_ins, p_del)
         s1[lo:hi] = a[: hi - lo]
         s2[lo:hi] = b[: hi - lo]
+
+    _for_blocks(one, list(enumerate(range(0, n_pairs, _BLOCK))))
     off = np.arange(n_pairs + 1, dtype=np.int64) * length
     return PairBatch(DNA, s1.reshape(-1), off, s2.reshape(-1), off.copy())
 
@@ -153,12 +169,13 @@ def protein_varlen(n_pairs: int, seed: int, lo: int = 300, hi: int = 1000, p_sub
     """Config 3: protein pairs, len(seq_1) ~ U{lo..hi}; seq_2 = seq_1 with 15 %
     substitutions and 5 % indel events of geometric length (mean 3), clamped to
     [lo, hi] letters.  Drawn in blocks of 4096 pairs (prefix-stable)."""
-    parts = []
-    for blk, start in enumerate(range(0, n_pairs, _BLOCK)):
+    def one(job):
+        blk, start = job
         rng = np.random.default_rng([seed, blk])
         full = _protein_block(rng, _BLOCK, lo, hi, p_sub, p_indel, mean_indel)
-        parts.append(full.head(min(_BLOCK, n_pairs - start)))
-    return concat(parts)
+        return full.head(min(_BLOCK, n_pairs - start))
+
+    return concat(_for_blocks(one, list(enumerate(range(0, n_pairs, _BLOCK)))))
 
 
 def concat(parts: list[PairBatch]) -> PairBatch:

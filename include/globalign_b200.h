@@ -113,6 +113,27 @@ int ga_align_batch_uniform(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint
                            int64_t n_pairs, int32_t *out_cost, uint8_t *out_ops, int32_t *out_ops_len,
                            int32_t *out_status, uint32_t flags);
 
+/* The same hot path with a COMPACT result stream: one 8-byte record per pair and the alignments as
+ * run-length encoded operations packed back to back -- what dp_array_backward's three strings
+ * (globaligner.py:584-593) are made of, in ~10 bytes per read pair instead of a fixed slice of
+ * ceil((m+n)/4) bytes.  With several GPUs behind one host the device-to-host copy of the result is
+ * what limits the end-to-end rate; this form cuts it ~4x.
+ *   out_res[p]      cost and number of alignment columns (bit 31 of nops_status = status[p])
+ *   out_rle         RLE bytes, pair p at [out_rle_off[p], out_rle_off[p+1]): bits 0-1 operation
+ *                   (0 / 1 / 2 as above), bits 2-7 run length - 1 (longer runs continue in the next
+ *                   byte), walk order.  Capacity rle_capacity bytes; m+n bytes per pair always
+ *                   suffice; GA_E_NOMEM (nothing written past the end) if it is too small.
+ *   out_rle_off     n_pairs + 1 entries, written by the call.
+ * s1_off == s2_off == NULL: fixed-length batch (every pair m x n, as ga_align_batch_uniform);
+ * otherwise m and n are ignored.  flags: the GA_F_SEQ_* packings, GA_F_KEEP_ORDER, GA_F_FORCE_GENERIC. */
+typedef struct {
+    int32_t cost;
+    uint32_t nops_status;
+} ga_pair_result;
+int ga_align_batch_rle(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off, int64_t m, const uint8_t *s2,
+                       const int64_t *s2_off, int64_t n, int64_t n_pairs, ga_pair_result *out_res,
+                       uint8_t *out_rle, int64_t rle_capacity, int64_t *out_rle_off, uint32_t flags);
+
 /* Same work on DEVICE-resident buffers, split into planning (host side: reads
  * the two offset arrays, sizes scratch, uploads tile metadata) and running
  * (only kernels; asynchronous on the ctx stream).  d_* are device pointers the

@@ -29,7 +29,7 @@ def main():
         simple = rng.random() < 0.6
         A = rng.choice([2, 4, 4, 5] if simple else [3, 4, 20])
         dense = dense_simple(rng, A) if simple else dense_table(rng, A)
-        m = rng.choice([1, 2, 127, 128, 129, 255, 256, 257, rng.randint(1, 700), rng.randint(1, 3000), rng.randint(1, 3000)])
+        m = rng.choice([1, 2, 127, 128, 129, 191, 192, 193, 255, 256, 257, 383, 384, 385, rng.randint(1, 700), rng.randint(1, 3000), rng.randint(1, 3000)])
         n = rng.choice([1, 2, 15, 16, 17, 127, 128, 129, rng.randint(1, 700), rng.randint(1, 3000), rng.randint(1, 3000)])
         a = np.array([rng.randrange(A) for _ in range(m)], dtype=np.uint8)
         kind = rng.random()

@@ -1,0 +1,154 @@
+"""Pure-Python model of the long-pair fill kernel's schedule and arithmetic (ga_long.cuh,
+long_fill_kernel): chains of rows skewed inside a lane, values in the gap-shifted domain,
+band-boundary rows and column checkpoints as the traceback kernels read them.  It mirrors the
+CUDA code statement by statement (same state variables, same update order) so that the
+algorithm -- who reads which value from which step -- is checked against the oracle's full
+table on the CPU, where there is no GPU.  Test infrastructure only.
+
+Layout: a band = LANES lanes x LR rows, LR = NC chains x ELL rows.  Chain q = g*NC + k (lane g,
+chain k) works at step t on column j = t - q + 1; its ELL rows are updated top to bottom within
+the step (dependent), different chains of a lane are independent within a step.
+
+Shifted domain: X^(i,j) = 4 * (X(i,j) - GH(j) - GV(i)), GH(j) = sum_{t<=j} gap_h[s2[t-1]],
+GV(i) = sum_{t<=i} gap_v[s1[t-1]].  Then
+    d0 = h^(i-1,j-1) + 4*(sub(a,b) - gap_h[b] - gap_v[a])
+    h  = min(d0, L^(i,j-1), U^(i-1,j))
+    L^(i,j) = min(h + 4o, L^(i,j-1)),   U^(i,j) = min(h + 4o, U^(i-1,j))
+where L(i,j) = min(D0+o, D1, D2+o)(i,j) is the level-1 candidate handed to column j+1 and
+U(i,j) = min(D0+o, D1+o, D2)(i,j) the level-2 candidate handed to row i+1: the gap-extension
+additions disappear from the cell update.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+INVALID = -(2 ** 31) + 0x00808080      # 0x80808080 as int32: "boundary entry not yet written"
+
+
+class Scheme:
+    def __init__(self, A, sub, gap_h, gap_v, o, max_cost):
+        self.A, self.sub, self.gap_h, self.gap_v, self.o, self.max_cost = A, sub, gap_h, gap_v, o, max_cost
+
+
+def fill_long(s1, s2, sc: Scheme, ELL=2, NC=2, LANES=4, LSYNC=4, LCC=8):
+    """-> (cost, brow, vchk) with brow[band][j] = (h^, U^) of the band's last row and
+    vchk[band][c][g][r] = (h^, L^) of row g*LR+r of the band at column c*LCC (shifted, x4)."""
+    m, n = len(s1), len(s2)
+    LR = ELL * NC
+    LBAND = LANES * LR
+    nbands = (m + LBAND - 1) // LBAND
+    nck = n // LCC + 2
+    o = sc.o
+    o4 = 4 * o
+    big = (sc.max_cost + 1) * max(m, n)
+    colsum = [o]
+    for i in range(1, m + 1):
+        colsum.append(colsum[-1] + sc.gap_v[s1[i - 1]])
+    rowsum = [o]
+    for j in range(1, n + 1):
+        rowsum.append(rowsum[-1] + sc.gap_h[s2[j - 1]])
+    gv_pad = list(sc.gap_v) + [0]
+    # table of shifted substitution costs, row A = padding letter (rows past the end of seq_1)
+    tab = [[4 * ((sc.sub[a * sc.A + b] if a < sc.A else 0) - sc.gap_h[b] - gv_pad[a]) for b in range(sc.A)]
+           for a in range(sc.A + 1)]
+    brow = [[None] * (n + 1) for _ in range(nbands)]
+    vchk = [[[[None] * LR for _ in range(LANES)] for _ in range(nck)] for _ in range(nbands)]
+    cost = None
+
+    def col0(i):                       # shifted column-0 values of DP row i: (h^, L^)
+        c = colsum[min(i, m)]
+        gvs = c - o
+        return 4 * (min(big, c) - gvs), 4 * (min(big, c + o) - gvs)
+
+    assert LANES * NC <= LCC, "at most one chain of a band is on a checkpoint column per step"
+    for band in range(nbands):
+        # ---- per-lane state
+        aw = [[0] * LR for _ in range(LANES)]
+        hl = [[0] * LR for _ in range(LANES)]
+        Lp = [[0] * LR for _ in range(LANES)]
+        ub = [[0] * NC for _ in range(LANES)]
+        hd = [[0] * NC for _ in range(LANES)]
+        bv = [[0] * NC for _ in range(LANES)]      # letter of chain k at the CURRENT step (runs one step ahead of the cells)
+        sv = [[0] * LR for _ in range(LANES)]      # shifted substitution cost of row r at the current step
+        rh_prev = [0] * LANES
+        for g in range(LANES):
+            ib = band * LBAND + g * LR
+            for r in range(LR):
+                row = ib + r
+                aw[g][r] = s1[row] if row < m else sc.A
+                hl[g][r], Lp[g][r] = col0(ib + r + 1)
+            rh_prev[g] = 0 if ib == 0 else col0(ib)[0]
+        bv[0][0] = s2[0]                           # lane 0, chain 0 starts on column 1
+        for g in range(LANES):
+            for r in range(LR):
+                sv[g][r] = tab[aw[g][r]][bv[g][r // ELL]]
+        nsteps = n + LANES * NC - 1
+        for t0 in range(0, nsteps, LSYNC):
+            # staged inputs of lane 0, chain 0: entry u = (h^, U^ of the row above at column c, letter of
+            # column c + 1) for c = t0 + 1 + u
+            stage = []
+            for u in range(LSYNC):
+                cj = t0 + 1 + u
+                nxt = s2[cj] if cj + 1 <= n else 0
+                if cj <= n:
+                    if band > 0:
+                        v = brow[band - 1][cj]
+                        assert v is not None and v[0] != INVALID
+                    else:
+                        rj = rowsum[cj]
+                        ghs = rj - o
+                        v = (4 * (min(big, rj) - ghs), 4 * (min(big, rj + o) - ghs))
+                    stage.append((v[0], v[1], nxt))
+                else:
+                    stage.append((0, 0, 0))
+            for u in range(LSYNC):
+                t = t0 + u
+                # shuffles first: every lane reads its upper neighbour's state of step t-1
+                rh = [hl[g - 1][LR - 1] if g > 0 else stage[u][0] for g in range(LANES)]
+                ru = [ub[g - 1][NC - 1] if g > 0 else stage[u][1] for g in range(LANES)]
+                nb = [bv[g - 1][NC - 1] if g > 0 else stage[u][2] for g in range(LANES)]
+                for g in range(LANES):
+                    # letters and substitution costs of the NEXT step
+                    nbv = [nb[g]] + [bv[g][k - 1] for k in range(1, NC)]
+                    svn = [tab[aw[g][r]][nbv[r // ELL]] for r in range(LR)]
+                    for k in range(NC - 1, -1, -1):
+                        q = g * NC + k
+                        j = t - q + 1
+                        if not (1 <= j <= n):
+                            continue
+                        assert bv[g][k] == s2[j - 1]
+                        if k > 0:
+                            diag, up = hd[g][k - 1], ub[g][k - 1]
+                        else:
+                            diag, up = rh_prev[g], ru[g]
+                            rh_prev[g] = rh[g]
+                        for r in range(k * ELL, (k + 1) * ELL):
+                            d0 = diag + sv[g][r]
+                            h = min(d0, Lp[g][r], up)
+                            diag = hl[g][r]
+                            hl[g][r] = h
+                            Lp[g][r] = min(h + o4, Lp[g][r])
+                            up = min(h + o4, up)
+                        hd[g][k] = diag
+                        ub[g][k] = up
+                        if k == NC - 1 and g == LANES - 1:
+                            brow[band][j] = (hl[g][LR - 1], up)
+                    bv[g] = nbv
+                    sv[g] = svn
+                # at most one chain of the band is on a checkpoint column, and which one follows from t alone
+                qs = (t + 1) % LCC
+                if qs < LANES * NC:
+                    gs, ks = qs // NC, qs % NC
+                    j = t - qs + 1
+                    if 1 <= j <= n:
+                        for r in range(ks * ELL, (ks + 1) * ELL):
+                            vchk[band][j // LCC][gs][r] = (hl[gs][r], Lp[gs][r])
+        if band == (m - 1) // LBAND:
+            g, r = ((m - 1) % LBAND) // LR, (m - 1) % LR
+            cost = hl[g][r] // 4 + (rowsum[n] - o) + (colsum[m] - o)
+    return cost, brow, vchk, (rowsum, colsum, LBAND, LR)
+
+
+def unshift(v, i, j, rowsum, colsum, o, m):
+    """Stored (shifted, x4) value of cell (i, j) -> plain cost x4."""
+    return v + 4 * ((rowsum[j] - o) + (colsum[min(i, m)] - o))

@@ -51,7 +51,8 @@ def test_product_never_imports_oracle():
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
     for p in (ROOT / "globalign_b200" / "csrc").glob("*"):
-        assert "oracle" not in p.read_text().lower() or p.name == "Makefile", p
+        if p.is_file():
+            assert "oracle" not in p.read_text().lower() or p.name == "Makefile", p
 
 
 def test_every_exported_symbol_is_mapped_in_integration_md():

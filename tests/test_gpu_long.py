@@ -39,7 +39,7 @@ def _check(ctx, dense, s1, s2, full_oracle=True):
 def test_long_path_random_sizes_simple_and_table():
     rng = random.Random(77)
     ctx = _native.Context(0)
-    for trial in range(60):
+    for trial in range(90):
         table = trial % 3 == 2
         if table:
             A = rng.choice([4, 20, 24])
@@ -48,7 +48,8 @@ def test_long_path_random_sizes_simple_and_table():
             A = rng.choice([2, 4, 5])
             dense = _simple_dense(A, rng.randint(1, 6), rng.randint(1, 3), rng.randint(1, 3), rng.randint(0, 12))
         ctx.set_scheme(dense)
-        m = rng.choice([1, 2, 7, 255, 256, 257, 300, 511, 513, 1000, 1300])
+        # around the band edges of every tuning build (128-, 192-, 256-, 288-row bands)
+        m = rng.choice([1, 2, 7, 127, 128, 129, 191, 192, 193, 255, 256, 257, 300, 383, 384, 385, 511, 513, 577, 1000, 1300])
         n = rng.choice([1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 700, 1100])
         s1 = np.array([rng.randrange(A) for _ in range(m)], dtype=np.uint8)
         if rng.random() < 0.6 and m > 8:
@@ -61,6 +62,22 @@ def test_long_path_random_sizes_simple_and_table():
         else:
             s2 = np.array([rng.randrange(A) for _ in range(n)], dtype=np.uint8)
         _check(ctx, dense, s1, s2)
+    ctx.close()
+
+
+def test_long_path_large_alphabet_simple_scheme_and_per_letter_gaps():
+    """The fill's two forms: shifted substitution table in shared memory (A <= 64, any scheme,
+    per-letter gap costs absorbed by the shift) and compare-and-select (simple schemes over more
+    letters than the table holds)."""
+    rng = random.Random(78)
+    ctx = _native.Context(0)
+    for A, dense in ((100, _simple_dense(100, 4, 1, 2, 3)), (64, _simple_dense(64, 2, 3, 1, 0)),
+                     (24, _table_dense(rng, 24, 9)), (3, _table_dense(rng, 3, 0))):
+        ctx.set_scheme(dense)
+        for m, n in ((700, 650), (193, 4000), (1500, 129)):
+            s1 = np.array([rng.randrange(A) for _ in range(m)], dtype=np.uint8)
+            s2 = np.array([(int(s1[k % m]) if rng.random() < 0.85 else rng.randrange(A)) for k in range(n)], dtype=np.uint8)
+            _check(ctx, dense, s1, s2)
     ctx.close()
 
 

@@ -564,7 +564,10 @@ def test_long_pair_call_leaves_a_packed_plan_intact():
         run()
         ctx.sync()
         assert np.array_equal(dc.cpu().numpy(), ref[0]) and np.array_equal(dl.cpu().numpy(), ref[3])
-        assert np.array_equal(dops.cpu().numpy()[: int(ops_off[-1])], ref[1][: int(ops_off[-1])])
+        got = dops.cpu().numpy()
+        for k in range(n):
+            assert np.array_equal(_native.unpack_ops(got, int(ops_off[k]), int(ref[3][k])),
+                                  _native.unpack_ops(ref[1], int(ref[2][k]), int(ref[3][k]))), k
     ctx.close()
 
 
@@ -666,6 +669,67 @@ def test_batch_agrees_with_single_pair_call_on_one_letter_pairs():
         assert (r.seq_1_aligned, r.middle_part, r.seq_2_aligned, r.cost, r.score) == \
             (one.seq_1_aligned, one.middle_part, one.seq_2_aligned, one.cost, one.score), k
     assert find_global_alignment(seq_1="AA", seq_2="AAA", **kw).cost == 6
+
+
+def test_compact_rle_output_equals_fixed_slice_output():
+    """ga_align_batch_rle: the same alignments as ga_align_batch, as one record per pair plus
+    run-length encoded ops packed back to back.  Ragged and fixed-length batches, several chunk
+    counts, simple and table schemes, out-of-domain pairs (status 1), and a buffer that is too small."""
+    rng = random.Random(31)
+    ctx = _native.Context(0)
+    cases = []
+    for A, dense in ((4, _simple_dense(4, 5, 2, 2, 10)), (4, _simple_dense(4, 3, 1, 1, 40)), (20, _table_dense(rng, 20, 6))):
+        s1, o1, s2, o2 = _random_batch(rng, 3000, A, 180, 170)
+        cases.append((dense, s1, o1, s2, o2, None))
+        n = 2500
+        u1 = np.array([rng.randrange(A) for _ in range(n * 100)], dtype=np.uint8)
+        u2 = u1.copy()
+        flip = np.array([rng.random() < 0.12 for _ in range(len(u2))])
+        u2[flip] = [rng.randrange(A) for _ in range(int(flip.sum()))]
+        off = np.arange(n + 1, dtype=np.int64) * 100
+        cases.append((dense, u1, off, u2, off.copy(), (100, 100, n)))
+    for dense, s1, o1, s2, o2, uni in cases:
+        ctx.set_scheme(dense)
+        for chunks in (None, "1", "3"):
+            if chunks:
+                os.environ["GA_CHUNKS"] = chunks
+            else:
+                os.environ.pop("GA_CHUNKS", None)
+            cost, ops, ops_off, ops_len, status = ctx.align_batch(s1, o1, s2, o2)
+            if uni:
+                res, rle, roff = ctx.align_batch_rle(s1, None, s2, None, uni[0], uni[1], uni[2])
+            else:
+                res, rle, roff = ctx.align_batch_rle(s1, o1, s2, o2)
+            assert np.array_equal(res["cost"], cost)
+            assert np.array_equal(res["nops_status"] >> 31, (status != 0).astype(np.uint32))
+            ok = status == 0
+            assert np.array_equal((res["nops_status"] & 0x7FFFFFFF)[ok], ops_len[ok].astype(np.uint32))
+            assert roff[0] == 0 and np.all(np.diff(roff) >= 0)
+            for k in range(len(cost)):
+                got = _native.unpack_rle(rle, int(roff[k]), int(roff[k + 1]))
+                if ok[k]:
+                    assert np.array_equal(got, _native.unpack_ops(ops, int(ops_off[k]), int(ops_len[k]))), k
+                else:
+                    assert len(got) == 0
+            # runs are maximal: no two neighbouring bytes of a pair with the same op unless the first is a full run of 64
+            k = int(np.argmax(np.diff(roff)))
+            b = rle[int(roff[k]): int(roff[k + 1])]
+            same = (b[1:] & 3) == (b[:-1] & 3)
+            assert np.all((b[:-1][same] >> 2) == 63)
+        os.environ.pop("GA_CHUNKS", None)
+        total = int(roff[-1])
+        small = (np.empty(len(cost), dtype=_native.PAIR_RESULT), np.empty(max(1, total // 2), dtype=np.uint8),
+                 np.empty(len(cost) + 1, dtype=np.int64))
+        with pytest.raises(MemoryError):
+            if uni:
+                ctx.align_batch_rle(s1, None, s2, None, uni[0], uni[1], uni[2], out=small)
+            else:
+                ctx.align_batch_rle(s1, o1, s2, o2, out=small)
+        exact = (small[0], np.empty(total, dtype=np.uint8), small[2])
+        r2 = ctx.align_batch_rle(s1, o1, s2, o2, out=exact) if not uni else \
+            ctx.align_batch_rle(s1, None, s2, None, uni[0], uni[1], uni[2], out=exact)
+        assert np.array_equal(r2[1][:total], rle[:total])
+    ctx.close()
 
 
 def test_one_letter_and_large_alphabets():
