@@ -46,7 +46,7 @@ def render(ops: np.ndarray, seq_1: str, seq_2: str):
 class BatchAlignment:
     """Packed results of a batch; ``batch[k]`` builds the k-th AlignmentResults."""
 
-    def __init__(self, seqs_1, seqs_2, cost, ops, ops_off, ops_len, status, scheme, rle: bool = False):
+    def __init__(self, seqs_1, seqs_2, cost, ops, ops_off, ops_len, status, scheme, rle: bool = False, lens=None):
         """`rle`: ops / ops_off hold the compact run-length stream of ga_align_batch_rle instead of
         fixed 2-bit slices (what find_global_alignments asks the library for)."""
         self.seqs_1, self.seqs_2 = seqs_1, seqs_2
@@ -55,8 +55,11 @@ class BatchAlignment:
         self._patched_ops = {}       # pairs re-aligned one by one (_realign_single_letter_pairs)
         self._scheme = scheme
         # (ASCII upper-casing keeps lengths: measure the caller's strings, not the lazy view)
-        m = np.fromiter(map(len, getattr(seqs_1, "_seqs", seqs_1)), dtype=np.int64, count=len(seqs_1))
-        n = np.fromiter(map(len, getattr(seqs_2, "_seqs", seqs_2)), dtype=np.int64, count=len(seqs_2))
+        if lens is not None:
+            m, n = lens
+        else:
+            m = np.fromiter(map(len, getattr(seqs_1, "_seqs", seqs_1)), dtype=np.int64, count=len(seqs_1))
+            n = np.fromiter(map(len, getattr(seqs_2, "_seqs", seqs_2)), dtype=np.int64, count=len(seqs_2))
         self.score = final_cost_to_score(cost.astype(np.int64), m, n, scheme.max_score)
 
     def __len__(self):
@@ -170,6 +173,48 @@ def _lower_batch(seqs_1, seqs_2, limit, scheme):
     return up1, up2, dense, np.concatenate(enc1), off1, np.concatenate(enc2), off2
 
 
+def _lower_native(seqs_1, seqs_2, limit, scheme):
+    """The all-ASCII case through the `_strings` extension (csrc/ga_strings.c): two parallel passes
+    over the strings' own buffers -- which byte values occur, then every letter mapped through one
+    256-entry table (case folding + letter -> index) -- instead of join / encode / translate in
+    Python (~5x faster on a million read pairs).  -> None when the extension is not built, the
+    inputs are not lists of ASCII str, or anything needs the per-pair path's exact error."""
+    try:
+        from . import _strings
+    except ImportError:
+        return None
+    if not (isinstance(seqs_1, list) and isinstance(seqs_2, list)):
+        return None
+    sc1 = _strings.scan(seqs_1)
+    sc2 = _strings.scan(seqs_2) if sc1 is not None else None
+    if sc1 is None or sc2 is None:
+        return None
+    (h1, _t1, l1, seen1), (h2, _t2, l2, seen2) = sc1, sc2
+    m_len = np.frombuffer(l1, dtype=np.int64)
+    n_len = np.frombuffer(l2, dtype=np.int64)
+    seen = np.frombuffer(seen1, dtype=np.uint8) | np.frombuffer(seen2, dtype=np.uint8)
+    if seen[ord(GAP)] or bool((~(m_len * n_len < limit) | (m_len * n_len == 0)).any()):
+        return None                      # the general path raises the reference's error for the first offending pair
+    known = {chr(c).upper() for c in np.flatnonzero(seen)}
+    if any(len(ch) != 1 or ord(ch) > 127 for ch in known):
+        return None
+    dense = scheme.dense_for(sorted(known))
+    table = bytearray(256)
+    for ch, k in dense.index.items():
+        if ord(ch) < 128:
+            table[ord(ch)] = k
+            table[ord(ch.lower())] = k
+    table = bytes(table)
+    cat1 = np.frombuffer(_strings.translate(h1, table), dtype=np.uint8)
+    cat2 = np.frombuffer(_strings.translate(h2, table), dtype=np.uint8)
+    n = len(seqs_1)
+    off1 = np.zeros(n + 1, dtype=np.int64)
+    off2 = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(m_len, out=off1[1:])
+    np.cumsum(n_len, out=off2[1:])
+    return _LazyUpper(seqs_1), _LazyUpper(seqs_2), dense, cat1, off1, cat2, off2
+
+
 def _lower_ascii_batch(seqs_1, seqs_2, limit, scheme):
     """The same for all-ASCII input without a Python-level loop over the pairs: the sequences are
     joined, upper-cased and mapped through one 256-entry table (large read sets spend their time
@@ -257,7 +302,9 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
     limit = start.MAX_SEQ_LEN_PRODUCT if max_seq_len_prod is None else max_seq_len_prod
     scheme = Scheme(scoring_mat_name, scoring_mat_path, match_score, mismatch_score, mismatch_cost,
                     gap_open_score, gap_open_cost, gap_extension_score, gap_extension_cost)
-    lowered = _lower_ascii_batch(seqs_1, seqs_2, limit, scheme)
+    lowered = _lower_native(seqs_1, seqs_2, limit, scheme)
+    if lowered is None:
+        lowered = _lower_ascii_batch(seqs_1, seqs_2, limit, scheme)
     if lowered is None:
         lowered = _lower_batch(seqs_1, seqs_2, limit, scheme)
     up1, up2, dense, cat1, off1, cat2, off2 = lowered
@@ -282,7 +329,8 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
     else:
         from .parallel import align_on_devices
         cost, ops, ops_off, ops_len, status = align_on_devices(on_device, cat1, off1, cat2, off2, list(devices))
-    res = BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme, rle=True)
+    res = BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme, rle=True,
+                         lens=(np.diff(off1), np.diff(off2)))
     _realign_single_letter_pairs(res, dense, cat1, off1, cat2, off2, scheme, device if not devices else devices[0])
     return res
 

@@ -130,7 +130,7 @@ struct Chunk {
 // events of one chunk of the pipeline
 struct ChunkEvents {
     cudaEvent_t in0, in1, f0, f1, w0, w1, out0, out1;
-    cudaEvent_t base, r0, r1;      // compact (RLE) output: chunk size known on the host / its copy
+    cudaEvent_t base, r0, r1, x1;  // compact (RLE) output: chunk size known on the host / its copy / its kernels done
 };
 
 struct DevBuf {
@@ -303,7 +303,7 @@ extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
     for (auto &e : ctx->in_piece) if (e) cudaEventDestroy(e);
     if (ctx->in_begin) cudaEventDestroy(ctx->in_begin);
     for (auto &c : ctx->cev)
-        for (cudaEvent_t e : {c.in0, c.in1, c.f0, c.f1, c.w0, c.w1, c.out0, c.out1, c.base, c.r0, c.r1}) cudaEventDestroy(e);
+        for (cudaEvent_t e : {c.in0, c.in1, c.f0, c.f1, c.w0, c.w1, c.out0, c.out1, c.base, c.r0, c.r1, c.x1}) cudaEventDestroy(e);
     for (auto &a : ctx->aux) if (a) cudaStreamDestroy(a);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -838,7 +838,7 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     ht.lap("plan: scratch + tile upload");
     while (ctx->cev.size() < ctx->chunks.size()) {
         ChunkEvents c;
-        for (cudaEvent_t *e : {&c.in0, &c.in1, &c.f0, &c.f1, &c.w0, &c.w1, &c.out0, &c.out1, &c.base, &c.r0, &c.r1}) CK(cudaEventCreate(e));
+        for (cudaEvent_t *e : {&c.in0, &c.in1, &c.f0, &c.f1, &c.w0, &c.w1, &c.out0, &c.out1, &c.base, &c.r0, &c.r1, &c.x1}) CK(cudaEventCreate(e));
         ctx->cev.push_back(c);
     }
     ctx->cfg = cfg;
@@ -953,10 +953,11 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
                              d_len, d_status);
             CK(cudaGetLastError());
         }
+        CK(cudaEventRecord(E.w1, sW));          // the chunk's direction codes are free again from here
         if (io && io->rle) {
             // compact result stream (ga_rle.cuh): runs per pair, scan, chunk base, write.  The chunk
             // base chains through the chunks, which finish in order but on alternating streams.
-            if (c > 0 && !serial) CK(cudaStreamWaitEvent(sW, ctx->cev[c - 1].w1, 0));
+            if (c > 0 && !serial) CK(cudaStreamWaitEvent(sW, ctx->cev[c - 1].x1, 0));
             const int g1 = (np + 255) / 256;
             rle_count_kernel<<<g1, 256, 0, sW>>>(ch.pair_lo, np, d_ops, (const long long *)d_ops_off, ctx->uni_ops_stride,
                                                  d_len, d_status, (int *)ctx->r_len.p);
@@ -972,10 +973,10 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
                                                  (PairResult *)ctx->r_res.p, (int *)ctx->r_flag.p,
                                                  c + 1 == nc ? 1 : 0, (long long)ctx->n_pairs);
             CK(cudaGetLastError());
+            CK(cudaEventRecord(E.x1, sW));
         }
-        CK(cudaEventRecord(E.w1, sW));
         if (io && io->rle) {
-            CK(cudaStreamWaitEvent(sOut, E.w1, 0));
+            CK(cudaStreamWaitEvent(sOut, E.x1, 0));
             CK(cudaEventRecord(E.out0, sOut));
             CK(cudaMemcpyAsync(ctx->h_base + c + 1, (long long *)ctx->r_base.p + c + 1, 8, cudaMemcpyDeviceToHost, sOut));
             CK(cudaEventRecord(E.base, sOut));
@@ -1279,9 +1280,9 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     {
         const long long big = (long long)(sc.max_cost + 1) * std::max(m, n);
         // plain values (traceback kernels) and the fill's gap-shifted values, which go down to
-        // -4 * (sum of all gap-extension costs) and must stay clear of L_INVALID
+        // -4 * (sum of all gap-extension costs); both must stay clear of L_INVALID and below L_INF
         const long long vmax = big + (m + n + LBAND + 2) * (long long)sc.max_cost + 3LL * sc.o;
-        if (4 * vmax + 3 >= 0x7f000000LL) return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
+        if (4 * vmax + 3 >= 0x10000000LL) return fail(ctx, GA_E_RANGE, "costs too large for these lengths (4 * value must stay below 2^28)");
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

@@ -22,8 +22,8 @@
 //     globaligner.py:331-363).  The shift is the same for the three candidates of a cell, so every
 //     comparison -- and every tie -- is unchanged.  Exact integers throughout.
 //   * Boundary hand-off.  (h^, U^) of a band's last row go to global memory with one 64-bit store
-//     per column; the consumer fetches them LSYNC columns at a time, one block AHEAD of its
-//     wavefront (the load latency hides behind a block of steps), synchronised by the data itself:
+//     per column; the consumer fetches them LSYNC columns at a time, half a block AHEAD of its
+//     wavefront (the load latency hides behind half a block of steps), synchronised by the data itself:
 //     entries are pre-set to L_INVALID and re-polled only if they have not arrived.  Bands are claimed in
 //     increasing order from an atomic counter, so a band's predecessor is always running or
 //     finished: no deadlock, no co-residency requirement.
@@ -49,10 +49,10 @@
 namespace ga {
 
 #ifndef GA_LONG_ELL
-#define GA_LONG_ELL 3
+#define GA_LONG_ELL 6
 #endif
 #ifndef GA_LONG_NC
-#define GA_LONG_NC 2
+#define GA_LONG_NC 1
 #endif
 constexpr int LELL = GA_LONG_ELL;   // rows per chain (updated one after the other within a step)
 constexpr int LNC = GA_LONG_NC;     // chains per lane (independent within a step)
@@ -193,127 +193,168 @@ __device__ __forceinline__ int long_sub(const FillLane<MODE> &ln, int r, unsigne
 
 // The LELL cells of chain K at its current column.  diag / up: h^(i-1, j-1) and U^(i-1, j) of the
 // row above the chain's first row.
-template <int MODE, int K>
-__device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up, const FillConsts &c) {
+//
+// CHECK (blocks at the edges of the matrix, where a chain's column may not exist yet or any more):
+// the update of an inactive chain is made the IDENTITY by its inputs instead of being skipped --
+// no branch, so a whole unrolled block stays one basic block, and no select behind the update on
+// the dependency chain.  A row's state always satisfies h <= L <= h + 4o; feeding d0 = h (its own
+// value), U-from-above = +inf and an infinite gap-open for the U it hands down gives
+//     h' = min(h, L, inf) = h,   L' = min(h + 4o, L) = L,   U' = min(h + inf, inf) = inf
+// so hl / Lp keep their values (the column-0 boundary before the chain starts, column N after it
+// ends) and the chain below sees +inf, which it ignores for the same reason.  What an inactive
+// chain leaves in hd / ub is never read: the chain below becomes active one step after it.
+constexpr int L_INF = 0x3f000000;       // above every value the range check of ga_align_long admits (|v| < 2^28)
+constexpr int L_BIGADD = 0x4f000000;    // v + L_BIGADD >= L_INF for every admitted v, without overflow
+template <int MODE, int K, bool CHECK>
+__device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up, bool act, const FillConsts &c) {
+    const int ob = (!CHECK || act) ? c.o4b : L_BIGADD;   // inactive: h + ob >= inf, so the U handed down stays +inf
+    if (CHECK && !act) up = L_INF;
 #pragma unroll
     for (int r = K * LELL; r < (K + 1) * LELL; ++r) {
-        const int d0 = (int)((unsigned)diag * c.k1 + (unsigned)ln.sv[r]);           // IMAD
+        int d0 = (int)((unsigned)diag * c.k1 + (unsigned)ln.sv[r]);                 // IMAD
+        if (CHECK && !act) d0 = ln.hl[r];
         const int h = __vimin3_s32(d0, ln.Lp[r], up);
         diag = ln.hl[r];
         ln.hl[r] = h;
         ln.Lp[r] = __viaddmin_s32(h, c.o4, ln.Lp[r]);
-        up = __viaddmin_s32(h, c.o4b, up);
+        up = __viaddmin_s32(h, ob, up);
     }
     ln.hd[K] = diag;
     ln.ub[K] = up;
 }
 
-// chain K of one step: my column is j (chain K lags chain 0 by K columns)
-template <int MODE, bool CHECK, int K>
-__device__ __forceinline__ void long_one_chain(FillLane<MODE> &ln, int j, int N, int diag, int up,
-                                               bool last_lane, int2 *brow_j, const FillConsts &c) {
-    if (!CHECK || (j >= 1 && j <= N)) {
-        long_chain<MODE, K>(ln, diag, up, c);
-        if (K == LNC - 1 && last_lane) __stcg(brow_j, make_int2(ln.hl[LR - 1], ln.ub[LNC - 1]));
-    }
+__device__ __forceinline__ void st_cg_pred(bool p, int2 *dst, int x, int y) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.global.cg.v2.s32 [%1], {%2, %3};\n\t}"
+                 :: "r"((int)p), "l"(dst), "r"(x), "r"(y) : "memory");
 }
 
-// chains K, K-1, ..., 1 of one step (each reads the state its upper neighbour chain had one step ago)
+// chain K (>= 1) of one step: my column is j (chain K lags chain 0 by K columns); it reads the state
+// its upper neighbour chain had one step ago
+template <int MODE, bool CHECK, int K>
+__device__ __forceinline__ void long_one_chain(FillLane<MODE> &ln, int j, int N, bool last_lane, int2 *brow_j,
+                                               const FillConsts &c) {
+    const bool act = !CHECK || (j >= 1 && j <= N);
+    long_chain<MODE, K, CHECK>(ln, ln.hd[K - 1], ln.ub[K - 1], act, c);
+    if (K == LNC - 1) st_cg_pred(last_lane && act, brow_j, ln.hl[LR - 1], ln.ub[LNC - 1]);
+}
+
+// chains K, K-1, ..., 1 of one step
 template <int MODE, bool CHECK, int K>
 __device__ __forceinline__ void long_mid_chains(FillLane<MODE> &ln, int j0, int N, bool last_lane, int2 *brow_j,
                                                 const FillConsts &c) {
     if constexpr (K >= 1) {
-        long_one_chain<MODE, CHECK, K>(ln, j0 - K, N, ln.hd[K - 1], ln.ub[K - 1], last_lane, brow_j, c);
+        long_one_chain<MODE, CHECK, K>(ln, j0 - K, N, last_lane, brow_j, c);
         long_mid_chains<MODE, CHECK, K - 1>(ln, j0, N, last_lane, brow_j, c);
     }
 }
 
-// (h^, L^) of the rows of chain K to the column checkpoint
-template <int MODE, int K>
-__device__ __forceinline__ void long_store_chain(const FillLane<MODE> &ln, int2 *dst) {
-#pragma unroll
-    for (int r = K * LELL; r < (K + 1) * LELL; ++r) __stcg(dst + r, make_int2(ln.hl[r], ln.Lp[r]));
-}
-
-// One block of LSYNC steps of a band sweep, fully unrolled (compile-time store offsets).  CHECK =
-// false is the steady state (every chain inside the matrix for the whole block).  `slot`: shared-
-// space address of this block's LSYNC staged inputs of lane 0: entry u = (h^, U^ of the row above the
-// band at column t0 + 1 + u, letter of the NEXT column), 16 bytes; every lane loads entry u + 1
-// during step u (a broadcast), lane 0 keeps it.
+// One block of LSYNC steps of a band sweep, fully unrolled and BRANCH-FREE (compile-time store
+// offsets, predicated stores, selects).  CHECK = false is the steady state (every chain inside the
+// matrix for the whole block).  `slot`: shared-space address of this block's LSYNC staged inputs of
+// lane 0: entry u = (h^, U^ of the row above the band at column t0 + 1 + u, letter of the NEXT
+// column), 16 bytes; every lane loads entry u + 1 during step u (a broadcast), lane 0 keeps it.
 //
 // A lone warp issues in order, so every value that crosses lanes is requested long before it is
 // used: the bottom row of my last chain is shuffled to the lane below right after that chain's
-// update (first thing in a step) and consumed by the lane below's chain 0 at the END of its next
-// step (ln.rh_in / ln.ru_in carry it across); the letter shuffle is issued first in a step and consumed
-// after all cell updates.
+// update and consumed by the lane below's chain 0 in its NEXT step (ln.rh_in / ln.ru_in carry it
+// across); the letter shuffle is consumed only by the loads of the next step's substitution costs.
+// Without a branch in the block no shuffle needs a convergence check, and the assembler overlaps
+// the chains of a step and consecutive steps.
 //
 // Column checkpoints (CK blocks only): at step t the only chain of the band that can sit on a
-// multiple of LCC is chain (t + 1) mod LCC (if the band has that many chains) -- a warp-uniform
-// fact, so the test is a uniform branch and the store a predicated one in the owning lane.  Blocks
-// in which no step can hit (most of them) are instantiated without that code.
+// multiple of LCC is chain q* = (t + 1) mod LCC (if the band has that many chains).  q* is warp-
+// uniform and, with LNC a power of two, its chain index within the lane is known at compile time:
+// LELL predicated stores in the owning lane.  Blocks in which no step can hit are instantiated
+// without that code.
+// Raw loads for the LSYNC columns of the NEXT block (lanes >= LSYNC duplicate a valid column): the
+// letter of the column AFTER mine and the boundary-row entry above this band (which may still be
+// L_INVALID; band 0: the row-0 running sum instead).  Nothing here USES a loaded value -- a lone
+// warp would stall on it -- that happens at the start of the next block.  Issued from the MIDDLE of
+// a block: early enough to hide the L2 latency behind half a block of steps, late enough that the
+// band above, which runs only a few dozen steps ahead, has already written the entries.
+struct FetchCtx {
+    const uint8_t *s2;
+    const int2 *up_brow;
+    const int *rowsum;
+    int band, cj_next;              // my column of the next block
+    unsigned braw;
+    int2 traw;
+};
+__device__ __forceinline__ void long_fetch(FetchCtx &f, int N) {
+    f.braw = 0u;
+    f.traw = make_int2(0, 0);
+    if (f.cj_next + 1 <= N) f.braw = (unsigned)f.s2[f.cj_next];
+    if (f.cj_next <= N) {
+        if (f.band > 0) f.traw = ld_volatile_int2(f.up_brow + f.cj_next);
+        else f.traw.x = f.rowsum[f.cj_next];
+    }
+}
+
+template <int MODE, bool CHECK, bool CK, int U>
+__device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsigned slot, int g, int q0,
+                                               bool last_lane, int t0, int N, int2 *brow_j0, int2 *band_vchk,
+                                               const FillConsts &c, FetchCtx &f) {
+    if constexpr (U == LSYNC / 2) long_fetch(f, N);
+    const unsigned nbs = __shfl_up_sync(FULL, ln.bv[LNC - 1], 1);      // my chain 0's letter of the NEXT step
+    const int j0 = t0 + U - q0 + 1;                    // column of my chain 0 at this step
+    int rh_next = 0, ru_next = 0;
+    if constexpr (LNC > 1) {
+        long_one_chain<MODE, CHECK, LNC - 1>(ln, j0 - (LNC - 1), N, last_lane, brow_j0 + U, c);
+        rh_next = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
+        ru_next = __shfl_up_sync(FULL, ln.ub[LNC - 1], 1);
+        long_mid_chains<MODE, CHECK, LNC - 2>(ln, j0, N, last_lane, brow_j0 + U, c);
+    }
+    {   // chain 0: the row above is the last row of the lane above (lane 0: of the band above)
+        const int rh = g == 0 ? e.x : ln.rh_in;
+        const int ru = g == 0 ? e.y : ln.ru_in;
+        const bool act = !CHECK || (j0 >= 1 && j0 <= N);
+        // (rh_prev follows the lane above unconditionally: while that lane's last chain is inactive
+        // its hl[LR-1] is h^(ib, 0), exactly what my chain 0 needs as its first diagonal input)
+        const int diag = ln.rh_prev;
+        ln.rh_prev = rh;
+        long_chain<MODE, 0, CHECK>(ln, diag, ru, act, c);
+        if (LNC == 1) st_cg_pred(last_lane && act, brow_j0 + U, ln.hl[LR - 1], ln.ub[0]);
+    }
+    if constexpr (LNC == 1) {
+        rh_next = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
+        ru_next = __shfl_up_sync(FULL, ln.ub[0], 1);
+    }
+    ln.rh_in = rh_next;
+    ln.ru_in = ru_next;
+    // letters and substitution costs of the next step (loads issued now, used a step later)
+    const unsigned nb0 = g == 0 ? (unsigned)e.z : nbs;
+#pragma unroll
+    for (int k = LNC - 1; k >= 0; --k) ln.bv[k] = k == 0 ? nb0 : ln.bv[k - 1];
+#pragma unroll
+    for (int r = 0; r < LR; ++r) ln.sv[r] = long_sub<MODE>(ln, r, ln.bv[r / LELL], c);
+    if constexpr (U + 1 < LSYNC)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                     : "r"(slot + 16u * (U + 1)));
+    if constexpr (CK || CHECK) {
+        constexpr int KS = (U + 1) & (LNC - 1);        // q* mod LNC (t0 and LCC are multiples of LNC)
+        const int tt = t0 + U + 1;
+        const int qs = tt & (LCC - 1);                 // q*, warp-uniform
+        const int j = tt - qs;                         // its column, a multiple of LCC
+        bool hit = qs < 32 * LNC && (qs / LNC) == g;
+        if (CHECK) hit = hit && j >= 1 && j <= N;
+        int2 *dst = band_vchk + ((size_t)(tt / LCC) * 32 + g) * LR;
+#pragma unroll
+        for (int r = KS * LELL; r < (KS + 1) * LELL; ++r) st_cg_pred(hit, dst + r, ln.hl[r], ln.Lp[r]);
+    }
+    if constexpr (U + 1 < LSYNC)
+        long_fill_step<MODE, CHECK, CK, U + 1>(ln, e, slot, g, q0, last_lane, t0, N, brow_j0, band_vchk, c, f);
+}
+
 template <int MODE, bool CHECK, bool CK>
 __device__ __forceinline__ void long_fill_block(FillLane<MODE> &ln, unsigned slot, int g, int t0,
-                                                int N, int2 *my_brow, int2 *band_vchk, const FillConsts &c) {
-    static_assert(32 * LNC <= LCC, "at most one chain of a band on a checkpoint column per step");
+                                                int N, int2 *my_brow, int2 *band_vchk, const FillConsts &c, FetchCtx &f) {
+    static_assert(32 * LNC <= LCC && (LNC & (LNC - 1)) == 0 && LSYNC % LNC == 0,
+                  "at most one chain of a band on a checkpoint column per step; its index in the lane is static");
     const int q0 = g * LNC;
-    const bool last_lane = g == 31;
     int2 *brow_j0 = my_brow + (t0 - (q0 + LNC - 1) + 1);   // column of my last chain at the block's first step
     int4 e;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(slot));
-#pragma unroll
-    for (int u = 0; u < LSYNC; ++u) {
-        const unsigned nbs = __shfl_up_sync(FULL, ln.bv[LNC - 1], 1);      // my chain 0's letter of the NEXT step
-        const int j0 = t0 + u - q0 + 1;                    // column of my chain 0 at this step
-        int rh_next = 0, ru_next = 0;
-        if constexpr (LNC > 1) {
-            long_one_chain<MODE, CHECK, LNC - 1>(ln, j0 - (LNC - 1), N, ln.hd[LNC - 2], ln.ub[LNC - 2], last_lane,
-                                                 brow_j0 + u, c);
-            rh_next = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
-            ru_next = __shfl_up_sync(FULL, ln.ub[LNC - 1], 1);
-            long_mid_chains<MODE, CHECK, LNC - 2>(ln, j0, N, last_lane, brow_j0 + u, c);
-        }
-        {   // chain 0: the row above is the last row of the lane above (lane 0: of the band above)
-            int rh = ln.rh_in, ru = ln.ru_in;
-            if (g == 0) { rh = e.x; ru = e.y; }
-            if (!CHECK || (j0 >= 1 && j0 <= N)) {
-                const int diag = ln.rh_prev;
-                ln.rh_prev = rh;
-                long_chain<MODE, 0>(ln, diag, ru, c);
-                if (LNC == 1 && last_lane) __stcg(brow_j0 + u, make_int2(ln.hl[LR - 1], ln.ub[0]));
-            }
-        }
-        if constexpr (LNC == 1) {
-            rh_next = __shfl_up_sync(FULL, ln.hl[LR - 1], 1);
-            ru_next = __shfl_up_sync(FULL, ln.ub[0], 1);
-        }
-        ln.rh_in = rh_next;
-        ln.ru_in = ru_next;
-        // letters and substitution costs of the next step (loads issued now, used a step later)
-        const unsigned nb0 = g == 0 ? (unsigned)e.z : nbs;
-#pragma unroll
-        for (int k = LNC - 1; k >= 0; --k) ln.bv[k] = k == 0 ? nb0 : ln.bv[k - 1];
-#pragma unroll
-        for (int r = 0; r < LR; ++r) ln.sv[r] = long_sub<MODE>(ln, r, ln.bv[r / LELL], c);
-        if (u + 1 < LSYNC)
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
-                         : "r"(slot + 16u * (u + 1)));
-        if constexpr (CK || CHECK) {
-            const int qs = (t0 + u + 1) & (LCC - 1);       // warp-uniform
-            if (qs < 32 * LNC) {
-                const int gs = qs / LNC, ks = qs - gs * LNC;
-                const int j = t0 + u - qs + 1;             // a multiple of LCC
-                if (!CHECK || (j >= 1 && j <= N)) {
-                    int2 *dst = band_vchk + ((size_t)(j / LCC) * 32 + gs) * LR;
-                    if (g == gs) {
-                        if (LNC > 0 && ks == 0) long_store_chain<MODE, 0>(ln, dst);
-                        if (LNC > 1 && ks == 1) long_store_chain<MODE, (LNC > 1 ? 1 : 0)>(ln, dst);
-                        if (LNC > 2 && ks == 2) long_store_chain<MODE, (LNC > 2 ? 2 : 0)>(ln, dst);
-                        if (LNC > 3 && ks == 3) long_store_chain<MODE, (LNC > 3 ? 3 : 0)>(ln, dst);
-                    }
-                }
-            }
-        }
-    }
+    long_fill_step<MODE, CHECK, CK, 0>(ln, e, slot, g, q0, g == 31, t0, N, brow_j0, band_vchk, c, f);
 }
 
 template <int MODE>
@@ -379,31 +420,24 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
         const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (N + 1);
         int2 *band_vchk = a.vchk + ((size_t)band * a.nck) * (32 * LR);
 
-        // Raw loads for the LSYNC columns from t0 + 1 on (lanes >= LSYNC duplicate a valid column): the
-        // letter of the column AFTER mine and the boundary-row entry above this band (which may still
-        // be L_INVALID; band 0: the row-0 running sum instead).  Nothing here USES a loaded value --
-        // a lone warp would stall on it -- that happens one block later, in `stage`.
-        auto fetch = [&](int t0, unsigned &braw, int2 &traw) {
-            const int cj = t0 + 1 + (g & (LSYNC - 1));
-            braw = 0u;
-            traw = make_int2(0, 0);
-            if (cj + 1 <= N) braw = (unsigned)S2[cj];
-            if (cj <= N) {
-                if (band > 0) traw = ld_volatile_int2(up_brow + cj);
-                else traw.x = ROWSUM[cj];
-            }
-        };
+        FetchCtx f;
+        f.s2 = S2;
+        f.up_brow = up_brow;
+        f.rowsum = ROWSUM;
+        f.band = band;
+        f.cj_next = 1 + (g & (LSYNC - 1));
+        long_fetch(f, N);                   // block 0
         const int nsteps = N + 32 * LNC - 1;
-        unsigned bnext;
-        int2 tnext;
-        fetch(0, bnext, tnext);
-        ln.rh_in = 0;
+        // what the shuffle at the end of a (virtual) step -1 would have delivered: the lane above is
+        // still on column 0 (rh_prev follows rh_in unconditionally, see long_fill_step)
+        ln.rh_in = ln.rh_prev;
         ln.ru_in = 0;
         __syncwarp();                       // the previous band's last reads of the staging area are done
         for (int t0 = 0, blk = 0; t0 < nsteps; t0 += LSYNC, ++blk) {
-            int2 tblk = tnext;
-            const int cj = t0 + 1 + (g & (LSYNC - 1));
-            if (band > 0) {                 // entries requested one block ago: poll only what has not arrived
+            int2 tblk = f.traw;
+            const unsigned bnext = f.braw;
+            const int cj = f.cj_next;       // = t0 + 1 + (g & (LSYNC - 1))
+            if (band > 0) {                 // entries requested half a block ago: poll only what has not arrived
                 if (cj <= N)
                     while (tblk.x == L_INVALID) tblk = ld_volatile_int2(up_brow + cj);
             } else if (cj <= N) {
@@ -413,15 +447,15 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             }
             if (g < LSYNC) my_stage[(blk & 1) * LSYNC + g] = make_int4(tblk.x, tblk.y, (int)(MODE == 1 ? 4u * bnext : bnext), 0);
             __syncwarp();
-            if (t0 + LSYNC < nsteps) fetch(t0 + LSYNC, bnext, tnext);
+            f.cj_next = cj + LSYNC;         // (past the last block the loads are guarded by cj <= N)
             const unsigned slot = stage_base + (unsigned)((blk & 1) * LSYNC * 16);
             const int tq = t0 & (LCC - 1);
             const bool ck = tq < 32 * LNC || tq + LSYNC >= LCC;        // can a step of this block hit a checkpoint column?
             if (t0 >= 32 * LNC && t0 + LSYNC <= N) {
-                if (ck) long_fill_block<MODE, false, true>(ln, slot, g, t0, N, my_brow, band_vchk, c);
-                else long_fill_block<MODE, false, false>(ln, slot, g, t0, N, my_brow, band_vchk, c);
+                if (ck) long_fill_block<MODE, false, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
+                else long_fill_block<MODE, false, false>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
             } else {
-                long_fill_block<MODE, true, true>(ln, slot, g, t0, N, my_brow, band_vchk, c);
+                long_fill_block<MODE, true, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
             }
         }
         // the last active step of every chain was column N: hl[] now holds h^(row, N)

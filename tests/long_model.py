@@ -23,6 +23,7 @@ from __future__ import annotations
 import numpy as np
 
 INVALID = -(2 ** 31) + 0x00808080      # 0x80808080 as int32: "boundary entry not yet written"
+L_INF, L_BIGADD = 0x3F000000, 0x4F000000
 
 
 class Scheme:
@@ -83,6 +84,8 @@ def fill_long(s1, s2, sc: Scheme, ELL=2, NC=2, LANES=4, LSYNC=4, LCC=8):
             for r in range(LR):
                 sv[g][r] = tab[aw[g][r]][bv[g][r // ELL]]
         nsteps = n + LANES * NC - 1
+        rh_in = rh_prev[:]                         # what a shuffle at the end of a virtual step -1 would deliver
+        ru_in = [None] * LANES
         for t0 in range(0, nsteps, LSYNC):
             # staged inputs of lane 0, chain 0: entry u = (h^, U^ of the row above at column c, letter of
             # column c + 1) for c = t0 + 1 + u
@@ -103,38 +106,64 @@ def fill_long(s1, s2, sc: Scheme, ELL=2, NC=2, LANES=4, LSYNC=4, LCC=8):
                     stage.append((0, 0, 0))
             for u in range(LSYNC):
                 t = t0 + u
-                # shuffles first: every lane reads its upper neighbour's state of step t-1
-                rh = [hl[g - 1][LR - 1] if g > 0 else stage[u][0] for g in range(LANES)]
-                ru = [ub[g - 1][NC - 1] if g > 0 else stage[u][1] for g in range(LANES)]
+                # The kernel shuffles the bottom row of a lane's LAST chain right after that chain's
+                # update and the lane below consumes it one step later (rh_in / ru_in); the letter shuffle
+                # reads the letters of the current step.  All lanes move in lock-step: phases.
                 nb = [bv[g - 1][NC - 1] if g > 0 else stage[u][2] for g in range(LANES)]
-                for g in range(LANES):
-                    # letters and substitution costs of the NEXT step
-                    nbv = [nb[g]] + [bv[g][k - 1] for k in range(1, NC)]
-                    svn = [tab[aw[g][r]][nbv[r // ELL]] for r in range(LR)]
-                    for k in range(NC - 1, -1, -1):
-                        q = g * NC + k
-                        j = t - q + 1
-                        if not (1 <= j <= n):
-                            continue
-                        assert bv[g][k] == s2[j - 1]
-                        if k > 0:
-                            diag, up = hd[g][k - 1], ub[g][k - 1]
-                        else:
-                            diag, up = rh_prev[g], ru[g]
-                            rh_prev[g] = rh[g]
+
+                def chain(g, k, diag, up):
+                    """cells of chain k of lane g at this step.  The kernel does not skip an inactive
+                    chain: it runs the update with inputs that make it the identity (d0 = own h, U from
+                    above = +inf, infinite gap open for the U handed down); hd / ub become garbage."""
+                    j = t - (g * NC + k) + 1
+                    if not (1 <= j <= n):
+                        up = L_INF
                         for r in range(k * ELL, (k + 1) * ELL):
-                            d0 = diag + sv[g][r]
-                            h = min(d0, Lp[g][r], up)
-                            diag = hl[g][r]
-                            hl[g][r] = h
-                            Lp[g][r] = min(h + o4, Lp[g][r])
-                            up = min(h + o4, up)
-                        hd[g][k] = diag
-                        ub[g][k] = up
-                        if k == NC - 1 and g == LANES - 1:
-                            brow[band][j] = (hl[g][LR - 1], up)
+                            h = min(hl[g][r], Lp[g][r], up)
+                            assert h == hl[g][r] and min(h + o4, Lp[g][r]) == Lp[g][r], "identity"
+                            up = min(h + L_BIGADD, up)
+                            assert up == L_INF
+                        hd[g][k] = ub[g][k] = None          # garbage, must never be read
+                        return
+                    assert bv[g][k] == s2[j - 1]
+                    for r in range(k * ELL, (k + 1) * ELL):
+                        d0 = diag + sv[g][r]
+                        h = min(d0, Lp[g][r], up)
+                        diag = hl[g][r]
+                        hl[g][r] = h
+                        Lp[g][r] = min(h + o4, Lp[g][r])
+                        up = min(h + o4, up)
+                    hd[g][k] = diag
+                    ub[g][k] = up
+                    if k == NC - 1 and g == LANES - 1:
+                        brow[band][j] = (hl[g][LR - 1], up)
+
+                def shuffle():
+                    return ([hl[g - 1][LR - 1] if g > 0 else None for g in range(LANES)],
+                            [ub[g - 1][NC - 1] if g > 0 else None for g in range(LANES)])
+
+                if NC > 1:
+                    old_hd = [row[:] for row in hd]
+                    old_ub = [row[:] for row in ub]
+                    for g in range(LANES):
+                        chain(g, NC - 1, old_hd[g][NC - 2], old_ub[g][NC - 2])
+                    rh_next, ru_next = shuffle()
+                    for g in range(LANES):
+                        for k in range(NC - 2, 0, -1):
+                            chain(g, k, old_hd[g][k - 1], old_ub[g][k - 1])
+                for g in range(LANES):
+                    rh = stage[u][0] if g == 0 else rh_in[g]
+                    ru = stage[u][1] if g == 0 else ru_in[g]
+                    diag = rh_prev[g]
+                    rh_prev[g] = rh                      # unconditional (see long_fill_step)
+                    chain(g, 0, diag, ru)
+                if NC == 1:
+                    rh_next, ru_next = shuffle()
+                rh_in, ru_in = rh_next, ru_next
+                for g in range(LANES):
+                    nbv = [nb[g]] + [bv[g][k - 1] for k in range(1, NC)]
                     bv[g] = nbv
-                    sv[g] = svn
+                    sv[g] = [tab[aw[g][r]][nbv[r // ELL]] for r in range(LR)]
                 # at most one chain of the band is on a checkpoint column, and which one follows from t alone
                 qs = (t + 1) % LCC
                 if qs < LANES * NC:
