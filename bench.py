@@ -363,8 +363,11 @@ class Env:
             import torch.distributed as dist
             self.dist = dist
             self.host_pg = dist.new_group(backend="gloo")       # host-side waits (no spinning GPU kernel)
+        # one nvidia-smi poller per node: with eight ranks, eight of them (NVML queries every 100 ms)
+        # perturb the host-side copies that the end-to-end number times
         self.sampler = ClockSampler(local_rank)
-        self.sampler.start()
+        if rank == 0:
+            self.sampler.start()
         self._alu = None
 
     def barrier(self):

@@ -170,6 +170,7 @@ struct ga_ctx {
     bool serial = false;
     bool uniform = false;             // every pair has the same (m, n): arithmetic tile descriptors
     bool plan_for_io = false;         // planning on behalf of the host-buffer entry point
+    bool plan_rle = false;            // ... with the compact (RLE) output
     bool persistent = true;           // fill grid: machine-filling + tile counter, or one tile per warp
     int uniM = 0, uniN = 0;
     long long uni_u4 = 0;
@@ -643,9 +644,13 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         } else if (ctx->plan_for_io && tiles_per_warp >= 16.0 && !getenv("GA_CHUNKS")) {
             double edge = 0.125;                       // share of the first and of the last chunk
             if (const char *e = getenv("GA_EDGE_CHUNK")) edge = std::min(0.4, std::max(0.01, atof(e)));
+            // (the compact output's download is a few bytes per pair: no small last chunk needed)
+            bool last_edge = !ctx->plan_rle;
+            if (const char *e = getenv("GA_EDGE_LAST")) last_edge = atoi(e) != 0;
             cuts.push_back(edge);
-            for (int k = 1; k <= mid; ++k) cuts.push_back(edge + (1.0 - 2 * edge) * k / mid);
-            cuts.push_back(1.0);
+            const double rest = last_edge ? 1.0 - 2 * edge : 1.0 - edge;
+            for (int k = 1; k <= mid; ++k) cuts.push_back(edge + rest * k / mid);
+            if (last_edge) cuts.push_back(1.0);
         } else {
             for (int k = 1; k <= mid; ++k) cuts.push_back((double)k / mid);
         }
@@ -1178,9 +1183,11 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     ht0.lap("align: enqueue uploads");
     HostTimer ht;
     ctx->plan_for_io = true;
+    ctx->plan_rle = ro != nullptr;
     rc = implicit ? plan_uniform(ctx, um, un, n_pairs, flags)
                   : ga_plan_batch(ctx, s1_off, s2_off, n_pairs, (cost_only || ro) ? nullptr : out_ops_off, flags);
     ctx->plan_for_io = false;
+    ctx->plan_rle = false;
     if (rc) { cudaStreamSynchronize(sIn); return rc; }
     for (int k = EARLY; k < IN_PIECES; ++k)
         if ((rc = upload_piece(k))) return rc;
@@ -1348,7 +1355,13 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[3], st));
     int launches = 1;
-    const bool parallel = !cost_only && m >= 2 && n >= 2 && !(flags & GA_F_SERIAL);
+    // The band-parallel traceback is five dependent launches; for a pair of a few bands the single
+    // warp that re-fills and walks tile after tile is quicker (GA_LONG_SEQ_BANDS: tuning override).
+    // Measured (tools/probe_small_long.py): 500 x 500 0.24 vs 0.35 ms, 1000 x 1000 0.51 vs 0.56 ms,
+    // 2000 x 2000 1.00 vs 0.72 ms.
+    int seq_bands = 6;
+    if (const char *e = getenv("GA_LONG_SEQ_BANDS")) seq_bands = atoi(e);
+    const bool parallel = !cost_only && m >= 2 && n >= 2 && !(flags & GA_F_SERIAL) && nbands > seq_bands;
     if (!cost_only) {
         TraceOut to;
         to.ops = (uint32_t *)ctx->d_ops.p;

@@ -86,6 +86,10 @@ struct VOps<true, false> {
 // BANKED = 4: 32-bit entries, one wavefront per load.  BANKED = 2: 16-bit entries (half the memory,
 // alphabets up to ~28 letters at three blocks per SM); lanes 2k and 2k+1 then share a bank and
 // conflict when their entries differ in more than parity: ~1.5 wavefronts per load.
+// (Measured and rejected, cfg3 sample, round 2: holding the register allocation to four resident
+// blocks per SM with __launch_bounds__(128, 4) -- 128 registers, 16-96 bytes spilled, 16-bit table so
+// that four blocks fit -- 1,666 vs 1,947 GCUPS; 12 rows per lane 1,805.  The kernel is issue-bound,
+// 3 warps per scheduler already cover most dependency stalls.)
 template <bool PACKED, bool SIMPLE, int R, int G, int BANKED = 0>
 __global__ void __launch_bounds__(128)
 fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const UniformTiles ut, int n_tiles,

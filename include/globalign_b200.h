@@ -163,15 +163,28 @@ int ga_get_plan_info(const ga_ctx *ctx, ga_plan_info *info);
  * can add up to more than GA_T_TOTAL) and the bracketed total on the context stream. */
 int ga_get_timing(ga_ctx *ctx, float *ms /* GA_T_COUNT entries */);
 
-/* One long pair on the whole GPU, linear-space traceback.  Replaces make_dp_array +
+/* One long pair on the whole GPU, CHECKPOINTED traceback.  Replaces make_dp_array +
  * dp_array_forward + dp_array_backward (globaligner.py:756-821, :366-392, :395-593) for a
- * pair whose direction-code matrix should not be stored: the fill (bands of 128 rows
- * pipelined across all SMs) keeps only band-boundary rows and column checkpoints
- * (about 0.13 bytes per cell); the traceback re-fills 128 x <=128 tiles under the path
- * from those checkpoints and walks them -- all bands in parallel once a cheap pass has
- * located the path's crossing of every band boundary (GA_F_SERIAL: tile after tile).  The result is the
- * same canonical alignment as ga_align_batch gives.  Host buffers; out_ops must hold
- * 4 * ceil((m + n) / 16) + 4 bytes (2-bit ops in walk order, as for ga_align_batch).
+ * pair whose direction-code matrix should not be stored: the fill (bands of 192 rows
+ * pipelined across all SMs) keeps only band-boundary rows and column checkpoints; the
+ * traceback re-fills 192 x <=128 tiles under the path from those checkpoints and walks them
+ * -- all bands in parallel once a cheap pass has located the path's crossing of every band
+ * boundary (GA_F_SERIAL: tile after tile).  The result is the same canonical alignment as
+ * ga_align_batch gives.  Host buffers; out_ops must hold 4 * ceil((m + n) / 16) + 4 bytes
+ * (2-bit ops in walk order, as for ga_align_batch).
+ *
+ * Memory: NOT O(m + n).  The checkpoints take
+ *     8 * (n + 1) * ceil(m / 192)  +  8 * 192 * ceil(m / 192) * (n / 128 + 2)   bytes
+ * = about m * n / 9.6 bytes (0.104 bytes per cell: 1.04 GB for 100 kb x 100 kb, where stored
+ * direction codes would take 5 GB; 104 GB for 1 Mb x 1 Mb).  They count against the scratch
+ * limit (ga_ctx_set_scratch_limit, default 64 GiB: pairs up to about 780 kb x 780 kb; a B200
+ * holds about 1.2 Mb x 1.2 Mb); beyond it GA_E_NOMEM is returned.  With GA_F_COST_ONLY the
+ * same checkpoints are written (the fill kernel is the same).  A divide-and-conquer
+ * (Hirschberg / Myers-Miller) form with O(m + n) memory is not implemented: reproducing the
+ * reference's tie order exactly needs the forward values on the path, which is what the
+ * checkpoints provide.
+ * Values: 4 * (every cost on a path + the sentinel) must stay below 2^28 (GA_E_RANGE otherwise),
+ * e.g. DNA with costs <= 5 up to about 4 M letters per sequence.
  * The reference refuses len(seq_1) * len(seq_2) >= 2e7 (start.py:213); this entry point
  * has no such guard. */
 typedef struct {

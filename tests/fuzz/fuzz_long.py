@@ -2,6 +2,7 @@
 """Randomised parity sweep of the long-pair path (ga_align_long: band-pipelined fill + linear-space
 traceback, parallel and sequential forms) against the C oracle's full-table alignment.
 Usage: fuzz_long.py [seconds] [seed]"""
+import os
 import random
 import sys
 import time
@@ -49,6 +50,7 @@ def main():
         else:
             b = np.array([rng.randrange(A) for _ in range(n)], dtype=np.uint8)
         flags = _native.GA_F_SERIAL if rng.random() < 0.25 else 0
+        os.environ["GA_LONG_SEQ_BANDS"] = rng.choice(["0", "0", "6"])      # band-parallel traceback also for small pairs
         ctx.set_scheme(dense)
         desc = dict(A=A, simple=simple, m=len(a), n=len(b), flags=flags, o=dense.gap_open, seed=seed, run=runs)
         cost, ops, status, info = ctx.align_long(a, b, flags=flags)

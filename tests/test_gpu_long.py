@@ -1,5 +1,6 @@
 """The long-pair path (ga_align_long: whole-chip band pipeline + checkpointed linear-space
 traceback) against the oracle.  Bit-exact costs and canonical alignments."""
+import os
 import random
 
 import numpy as np
@@ -23,7 +24,17 @@ def _check(ctx, dense, s1, s2, full_oracle=True):
     if status == 0:
         assert np.array_equal(ops, ops_s)
     if len(s1) >= 2 and len(s2) >= 2:
-        assert info["trace_mode"] in (1, 2)
+        # pairs of a few bands take the sequential form by default: force the band-parallel one too
+        os.environ["GA_LONG_SEQ_BANDS"] = "0"
+        try:
+            cost_p, ops_p, status_p, info_p = ctx.align_long(s1, s2)
+        finally:
+            os.environ.pop("GA_LONG_SEQ_BANDS", None)
+        assert info_p["trace_mode"] in (1, 2) and (cost_p, status_p) == (cost, status)
+        if status == 0:
+            assert np.array_equal(ops_p, ops)
+        if len(s1) > 6 * info["tile_rows"]:
+            assert info["trace_mode"] in (1, 2)
     d = _oracle_dense(dense)
     if full_oracle:
         o_ops, o_cost, rc = c_oracle.align_codes(s1, s2, d)
@@ -93,7 +104,13 @@ def test_long_path_equals_batched_kernel_and_golden_cfg1():
     assert list(batch.render(ops, s1, s2)) + [cost] == row["out"][:4]
     bc, bops, boff, blen, bst = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
     assert bc[0] == cost and np.array_equal(_native.unpack_ops(bops, 0, int(blen[0])), ops)
-    assert info["trace_mode"] == 1 and info["retraced_tiles"] >= 4
+    assert info["trace_mode"] == 0 and info["retraced_tiles"] >= 4      # 1 kb x 1 kb: six bands, sequential traceback
+    os.environ["GA_LONG_SEQ_BANDS"] = "0"                               # ... and the band-parallel form on the same pair
+    try:
+        cost_p, ops_p, status_p, info_p = ctx.align_long(b.s1, b.s2)
+    finally:
+        os.environ.pop("GA_LONG_SEQ_BANDS", None)
+    assert info_p["trace_mode"] == 1 and cost_p == cost and np.array_equal(ops_p, ops)
     ctx.close()
 
 

@@ -398,6 +398,31 @@ def test_config2_full_size_properties():
     ctx.close()
 
 
+@pytest.mark.parametrize("name,n_pairs", [("cfg3", 10_000), ("cfg5", 12_000)])
+def test_config3_and_config5_shapes_10k_pairs_against_the_oracle(name, n_pairs):
+    """BASELINE configs[2] (protein pairs 300-1000 aa, BLOSUM62, asymmetric 9/10 gap costs from the
+    score -> cost transform, start.py:500-557) and configs[4] (250 bp DNA pairs): >= 10,000 pairs of the
+    workload's own shape through the kernel the planner picks, every cost and every traceback op
+    against the C oracle; the compact (RLE) output of the same call against the fixed-slice one."""
+    b = synth.workload(name, n_pairs=n_pairs)
+    scheme = batch.Scheme(**synth.SCHEMES[name])
+    dense = scheme.dense_for(sorted(b.alphabet))
+    remap = np.array([dense.index[ch] for ch in b.alphabet], dtype=np.uint8)
+    s1, s2 = remap[b.s1], remap[b.s2]
+    ctx = _native.Context(0)
+    ctx.set_scheme(dense)
+    out = ctx.align_batch(s1, b.off1, s2, b.off2)
+    info = ctx.plan_info()
+    assert info["packed16"] and info["fill_kernel"] == {"cfg3": "fill_p16b_r16_g32", "cfg5": "fill_p16_r16_g16"}[name]
+    _compare_with_oracle(s1, b.off1, s2, b.off2, dense, out)
+    res, rle, roff = ctx.align_batch_rle(s1, b.off1, s2, b.off2)
+    assert np.array_equal(res["cost"], out[0]) and not (res["nops_status"] >> 31).any()
+    for k in range(0, n_pairs, 7):
+        assert np.array_equal(_native.unpack_rle(rle, int(roff[k]), int(roff[k + 1])),
+                              _native.unpack_ops(out[1], int(out[2][k]), int(out[3][k]))), k
+    ctx.close()
+
+
 # ------------------------------------------------------------------ f1: seeded replay of random ties
 def test_seeded_replay_reproduces_unpatched_reference(monkeypatch):
     """With TIE_BREAKING = 'reference_random', random.seed(s) + find_global_alignment gives what the

@@ -38,7 +38,7 @@ def main():
     vdir = ROOT / "globalign_b200" / "_variants"
     variants = sys.argv[1:] or ([""] + sorted(p.name for p in vdir.glob("*.so")))
     for v in variants:
-        for bps in (1, 2):
+        for bps in [int(x) for x in os.environ.get("DIAG_BPS", "1,2").split(",")]:
             env = dict(os.environ, GA_LONG_BLOCKS_PER_SM=str(bps))
             if v:
                 env["GA_B200_LIB"] = str(vdir / v)
