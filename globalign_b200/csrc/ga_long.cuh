@@ -205,7 +205,7 @@ __device__ __forceinline__ int long_sub(const FillLane<MODE> &ln, int r, unsigne
 // chain leaves in hd / ub is never read: the chain below becomes active one step after it.
 constexpr int L_INF = 0x3f000000;       // above every value the range check of ga_align_long admits (|v| < 2^28)
 constexpr int L_BIGADD = 0x4f000000;    // v + L_BIGADD >= L_INF for every admitted v, without overflow
-template <int MODE, int K, bool CHECK>
+template <int MODE, int K, int CHECK>
 __device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up, bool act, const FillConsts &c) {
     const int ob = (!CHECK || act) ? c.o4b : L_BIGADD;   // inactive: h + ob >= inf, so the U handed down stays +inf
     if (CHECK && !act) up = L_INF;
@@ -230,16 +230,16 @@ __device__ __forceinline__ void st_cg_pred(bool p, int2 *dst, int x, int y) {
 
 // chain K (>= 1) of one step: my column is j (chain K lags chain 0 by K columns); it reads the state
 // its upper neighbour chain had one step ago
-template <int MODE, bool CHECK, int K>
+template <int MODE, int CHECK, int K>
 __device__ __forceinline__ void long_one_chain(FillLane<MODE> &ln, int j, int N, bool last_lane, int2 *brow_j,
                                                const FillConsts &c) {
-    const bool act = !CHECK || (j >= 1 && j <= N);
+    const bool act = CHECK == 0 || (j >= 1 && (CHECK == 1 || j <= N));
     long_chain<MODE, K, CHECK>(ln, ln.hd[K - 1], ln.ub[K - 1], act, c);
     if (K == LNC - 1) st_cg_pred(last_lane && act, brow_j, ln.hl[LR - 1], ln.ub[LNC - 1]);
 }
 
 // chains K, K-1, ..., 1 of one step
-template <int MODE, bool CHECK, int K>
+template <int MODE, int CHECK, int K>
 __device__ __forceinline__ void long_mid_chains(FillLane<MODE> &ln, int j0, int N, bool last_lane, int2 *brow_j,
                                                 const FillConsts &c) {
     if constexpr (K >= 1) {
@@ -249,8 +249,8 @@ __device__ __forceinline__ void long_mid_chains(FillLane<MODE> &ln, int j0, int 
 }
 
 // One block of LSYNC steps of a band sweep, fully unrolled and BRANCH-FREE (compile-time store
-// offsets, predicated stores, selects).  CHECK = false is the steady state (every chain inside the
-// matrix for the whole block).  `slot`: shared-space address of this block's LSYNC staged inputs of
+// offsets, predicated stores, selects).  CHECK = 0 is the steady state (every chain inside the
+// matrix for the whole block), 1 the ramp-in of a band (columns >= 1 to be tested only), 2 the general edge block.  `slot`: shared-space address of this block's LSYNC staged inputs of
 // lane 0: entry u = (h^, U^ of the row above the band at column t0 + 1 + u, letter of the NEXT
 // column), 16 bytes; every lane loads entry u + 1 during step u (a broadcast), lane 0 keeps it.
 //
@@ -290,7 +290,7 @@ __device__ __forceinline__ void long_fetch(FetchCtx &f, int N) {
     }
 }
 
-template <int MODE, bool CHECK, bool CK, int U>
+template <int MODE, int CHECK, bool CK, int U>
 __device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsigned slot, int g, int q0,
                                                bool last_lane, int t0, int N, int2 *brow_j0, int2 *band_vchk,
                                                const FillConsts &c, FetchCtx &f) {
@@ -307,7 +307,7 @@ __device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsi
     {   // chain 0: the row above is the last row of the lane above (lane 0: of the band above)
         const int rh = g == 0 ? e.x : ln.rh_in;
         const int ru = g == 0 ? e.y : ln.ru_in;
-        const bool act = !CHECK || (j0 >= 1 && j0 <= N);
+        const bool act = CHECK == 0 || (j0 >= 1 && (CHECK == 1 || j0 <= N));
         // (rh_prev follows the lane above unconditionally: while that lane's last chain is inactive
         // its hl[LR-1] is h^(ib, 0), exactly what my chain 0 needs as its first diagonal input)
         const int diag = ln.rh_prev;
@@ -330,13 +330,13 @@ __device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsi
     if constexpr (U + 1 < LSYNC)
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
                      : "r"(slot + 16u * (U + 1)));
-    if constexpr (CK || CHECK) {
+    if constexpr (CK || CHECK == 2) {
         constexpr int KS = (U + 1) & (LNC - 1);        // q* mod LNC (t0 and LCC are multiples of LNC)
         const int tt = t0 + U + 1;
         const int qs = tt & (LCC - 1);                 // q*, warp-uniform
         const int j = tt - qs;                         // its column, a multiple of LCC
         bool hit = qs < 32 * LNC && (qs / LNC) == g;
-        if (CHECK) hit = hit && j >= 1 && j <= N;
+        if (CHECK == 2) hit = hit && j >= 1 && j <= N;
         int2 *dst = band_vchk + ((size_t)(tt / LCC) * 32 + g) * LR;
 #pragma unroll
         for (int r = KS * LELL; r < (KS + 1) * LELL; ++r) st_cg_pred(hit, dst + r, ln.hl[r], ln.Lp[r]);
@@ -345,7 +345,7 @@ __device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsi
         long_fill_step<MODE, CHECK, CK, U + 1>(ln, e, slot, g, q0, last_lane, t0, N, brow_j0, band_vchk, c, f);
 }
 
-template <int MODE, bool CHECK, bool CK>
+template <int MODE, int CHECK, bool CK>
 __device__ __forceinline__ void long_fill_block(FillLane<MODE> &ln, unsigned slot, int g, int t0,
                                                 int N, int2 *my_brow, int2 *band_vchk, const FillConsts &c, FetchCtx &f) {
     static_assert(32 * LNC <= LCC && (LNC & (LNC - 1)) == 0 && LSYNC % LNC == 0,
@@ -452,10 +452,14 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             const int tq = t0 & (LCC - 1);
             const bool ck = tq < 32 * LNC || tq + LSYNC >= LCC;        // can a step of this block hit a checkpoint column?
             if (t0 >= 32 * LNC && t0 + LSYNC <= N) {
-                if (ck) long_fill_block<MODE, false, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
-                else long_fill_block<MODE, false, false>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
+                if (ck) long_fill_block<MODE, 0, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
+                else long_fill_block<MODE, 0, false>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
+            } else if (t0 + LSYNC <= N && t0 + LSYNC < LCC) {
+                // ramp-in: chains may not have started yet, none can be past column N or on a
+                // checkpoint column.  These blocks set the lag between consecutive bands.
+                long_fill_block<MODE, 1, false>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
             } else {
-                long_fill_block<MODE, true, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
+                long_fill_block<MODE, 2, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
             }
         }
         // the last active step of every chain was column N: hl[] now holds h^(row, N)
