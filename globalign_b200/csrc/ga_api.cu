@@ -1313,7 +1313,9 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         return fail(ctx, GA_E_NOMEM, "checkpoints need %zu bytes, above the scratch limit", brow_b + vchk_b);
     const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
     int rc;
-    if ((rc = ensure(ctx, ctx->d_s1, (size_t)m + 16)) || (rc = ensure(ctx, ctx->d_s2, (size_t)n + 16)) ||
+    // (seq_2 carries slack: the fill kernel's TMA tiles of the run-out steps reach up to
+    // 2 * LTCOLS + 64 bytes behind the last letter; what they hold there is never used)
+    if ((rc = ensure(ctx, ctx->d_s1, (size_t)m + 16)) || (rc = ensure(ctx, ctx->d_s2, (size_t)n + 2048)) ||
         (rc = ensure(ctx, ctx->l_colsum, colsum.size() * 4)) || (rc = ensure(ctx, ctx->l_rowsum, rowsum.size() * 4)) ||
         (rc = ensure(ctx, ctx->l_brow, brow_b)) || (rc = ensure(ctx, ctx->l_vchk, vchk_b)) ||
         (rc = ensure(ctx, ctx->l_misc, 256)) ||
@@ -1372,12 +1374,18 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         const int *skip = nullptr;
         if (parallel) {
             // parallel traceback: X-propagation over a diagonal corridor, chain, per-band detail, pack
+            // The corridor is tried narrow first (similar sequences stay within a few hundred
+            // columns of the straight diagonal; its width is the cost of the X-propagation), then
+            // wide, on the device without a host round trip: the second pair of launches returns
+            // at once when the first chain succeeded.
             ParTrace pt;
-            pt.W = 512 + (int)((m + n) / 128);
+            const int W_try[2] = {192 + (int)((m + n) / 1024), 512 + (int)((m + n) / 128)};
+            pt.run_if = nullptr;
+            pt.W = W_try[1];
             pt.XW = 2 * pt.W + (int)(((int64_t)LBAND * n + m - 1) / m) + LCC + 8;
             pt.seg_cap = 2 * (m + n) + 4096 + (int64_t)nbands * 4;
             const size_t xrow_b = (size_t)nbands * pt.XW * 3 * 4;
-            const size_t meta_b = (size_t)nbands * (16 + 8 + 4 + 8) + 64;
+            const size_t meta_b = (size_t)nbands * (16 + 8 + 4 + 8 + 8) + 64;
             if ((rc = ensure(ctx, ctx->l_xrow, xrow_b)) || (rc = ensure(ctx, ctx->l_meta, meta_b)) ||
                 (rc = ensure(ctx, ctx->l_seg, (size_t)pt.seg_cap + 64)))
                 return rc;
@@ -1387,19 +1395,29 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
             pt.seg_pos = (long long *)(meta + (size_t)nbands * 8);
             pt.entry = (int *)(meta + (size_t)nbands * 16);
             pt.seg_len = (int *)(meta + (size_t)nbands * 32);
+            pt.corr = (int *)(meta + (size_t)nbands * 36);
             pt.seg_ops = (uint8_t *)ctx->l_seg.p;
             pt.xlast = misc + 7;
             pt.failed = misc + 6;
             pt.tiles = misc + 3;
+            int n_try = 2;
+            if (const char *e = getenv("GA_LONG_CORRIDORS")) n_try = atoi(e) == 1 ? 1 : 2;      // 1: the wide corridor only
+            for (int k = 2 - n_try; k < 2; ++k) {
+                ParTrace q = pt;
+                q.W = W_try[k];
+                q.XW = 2 * q.W + (int)(((int64_t)LBAND * n + m - 1) / m) + LCC + 8;
+                q.run_if = (k == 1 && n_try == 2) ? pt.failed : nullptr;
+                if (sc.simple) long_xprop_kernel<true><<<(nbands + LWARPS - 1) / LWARPS, 32 * LWARPS, 0, st>>>(sc, a, q);
+                else long_xprop_kernel<false><<<(nbands + LWARPS - 1) / LWARPS, 32 * LWARPS, table, st>>>(sc, a, q);
+                long_chain_kernel<<<1, 32, 0, st>>>(a, q);
+                launches += 2;
+            }
+            launches -= 2;              // (the five counted below include one X-propagation + chain)
             if (sc.simple) {
                 CK(cudaFuncSetAttribute(long_detail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-                long_xprop_kernel<true><<<(nbands + LWARPS - 1) / LWARPS, 32 * LWARPS, 0, st>>>(sc, a, pt);
-                long_chain_kernel<<<1, 32, 0, st>>>(a, pt);
                 long_detail_kernel<true><<<nbands, 32, tsmem, st>>>(sc, a, pt);
             } else {
                 CK(cudaFuncSetAttribute(long_detail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-                long_xprop_kernel<false><<<(nbands + LWARPS - 1) / LWARPS, 32 * LWARPS, table, st>>>(sc, a, pt);
-                long_chain_kernel<<<1, 32, 0, st>>>(a, pt);
                 long_detail_kernel<false><<<nbands, 32, tsmem, st>>>(sc, a, pt);
             }
             long_prefix_kernel<<<1, 32, 0, st>>>(a, pt, to.n_ops, to.status);

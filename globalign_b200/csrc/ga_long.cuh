@@ -199,16 +199,46 @@ __device__ __forceinline__ int long_sub(const FillLane<MODE> &ln, int r, unsigne
 // no branch, so a whole unrolled block stays one basic block, and no select behind the update on
 // the dependency chain.  A row's state always satisfies h <= L <= h + 4o; feeding d0 = h (its own
 // value), U-from-above = +inf and an infinite gap-open for the U it hands down gives
-//     h' = min(h, L, inf) = h,   L' = min(h + 4o, L) = L,   U' = min(h + inf, inf) = inf
+//     e = min(h, L) = h,  h' = min3(h, inf, inf) = h,  L' = min(h + 4o, L) = L,  U' = min(h + inf, inf) = inf
 // so hl / Lp keep their values (the column-0 boundary before the chain starts, column N after it
 // ends) and the chain below sees +inf, which it ignores for the same reason.  What an inactive
 // chain leaves in hd / ub is never read: the chain below becomes active one step after it.
+#ifndef GA_LONG_UFREE
+#define GA_LONG_UFREE 1
+#endif
 constexpr int L_INF = 0x3f000000;       // above every value the range check of ga_align_long admits (|v| < 2^28)
 constexpr int L_BIGADD = 0x4f000000;    // v + L_BIGADD >= L_INF for every admitted v, without overflow
 template <int MODE, int K, int CHECK>
 __device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up, bool act, const FillConsts &c) {
-    const int ob = (!CHECK || act) ? c.o4b : L_BIGADD;   // inactive: h + ob >= inf, so the U handed down stays +inf
+    // The textbook order  h_r = min(d0_r, L_r, U_{r-1});  U_r = min(h_r + 4o, U_{r-1})  threads U through
+    // all rows of the chain: 8 cycles of dependent latency per row, then a 24-cycle shuffle to the lane
+    // below -- which needs it for ITS first row of the next step.  With e_r = min(d0_r, L_r) (no U in
+    // it) and gap_open >= 0:
+    //     U_r = min(e_r + 4o, U_{r-1} + 4o, U_{r-1}) = min(e_r + 4o, U_{r-1})
+    //         = min(P_r, U_in),      P_r = min_{k <= r} e_k + 4o      (a chain that never sees U_in)
+    //     h_r = min(e_r, U_{r-1}) = min3(e_r, P_{r-1}, U_in)
+    // so every row's h is ONE instruction behind U_in, the U handed down is min(P_last, U_in), and
+    // what is left on the path from lane to lane is that minimum plus the shuffle (28 cycles per
+    // step instead of 72).  One more ALU instruction per cell (4 instead of 3); exact -- plain
+    // integer minima, no tags in this kernel.
+    const int ob = (!CHECK || act) ? c.o4b : L_BIGADD;   // inactive: e + ob >= inf, so the U handed down stays +inf
     if (CHECK && !act) up = L_INF;
+#if GA_LONG_UFREE
+    int P = L_INF;
+#pragma unroll
+    for (int r = K * LELL; r < (K + 1) * LELL; ++r) {
+        int d0 = (int)((unsigned)diag * c.k1 + (unsigned)ln.sv[r]);                 // IMAD
+        if (CHECK && !act) d0 = ln.hl[r];
+        const int e = min(d0, ln.Lp[r]);
+        const int h = __vimin3_s32(e, P, up);
+        P = __viaddmin_s32(e, ob, P);
+        diag = ln.hl[r];
+        ln.hl[r] = h;
+        ln.Lp[r] = __viaddmin_s32(h, c.o4, ln.Lp[r]);
+    }
+    ln.hd[K] = diag;
+    ln.ub[K] = min(P, up);
+#else
 #pragma unroll
     for (int r = K * LELL; r < (K + 1) * LELL; ++r) {
         int d0 = (int)((unsigned)diag * c.k1 + (unsigned)ln.sv[r]);                 // IMAD
@@ -221,8 +251,26 @@ __device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up,
     }
     ln.hd[K] = diag;
     ln.ub[K] = up;
+#endif
 }
 
+// a value the compiler must keep in a register (it cannot re-derive it from where it came from)
+__device__ __forceinline__ int pin_reg(int v) {
+    int r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ T *pin_reg(T *v) {
+    T *r;
+    asm volatile("mov.b64 %0, %1;" : "=l"(r) : "l"(v));
+    return r;
+}
+
+__device__ __forceinline__ void st_cg_pred4(bool p, int2 *dst, int x, int y, int z, int w) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.global.cg.v4.s32 [%1], {%2, %3, %4, %5};\n\t}"
+                 :: "r"((int)p), "l"(dst), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void st_cg_pred(bool p, int2 *dst, int x, int y) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.global.cg.v2.s32 [%1], {%2, %3};\n\t}"
                  :: "r"((int)p), "l"(dst), "r"(x), "r"(y) : "memory");
@@ -266,8 +314,49 @@ __device__ __forceinline__ void long_mid_chains(FillLane<MODE> &ln, int j0, int 
 // uniform and, with LNC a power of two, its chain index within the lane is known at compile time:
 // LELL predicated stores in the owning lane.  Blocks in which no step can hit are instantiated
 // without that code.
+// ---- TMA staging of the sequence tile (cp.async.bulk + mbarrier; SASS: UBLKCP / SYNCS)
+// The letters of seq_2 a band sweeps over arrive in TILES of LTCOLS columns: tile S is the 16-byte
+// aligned piece seq_2[S * LTCOLS .. + LTILE) -- the letters of columns S*LTCOLS + 1 .. (S+1)*LTCOLS + 16,
+// what the blocks of steps t0 in [S*LTCOLS, (S+1)*LTCOLS) look up.  The TMA engine copies a tile
+// into one of the warp's two shared-memory slots and signals the slot's mbarrier; no thread holds
+// the data in flight.  One elected lane requests tile S+2 when the warp moves from tile S to S+1
+// (a whole tile of steps ahead); the wait at that point finds tile S+1 long complete.
+// (Waiting once per BLOCK on a 32-byte tile cost 10 % of the fill: a lone in-order warp pays the
+// mbarrier round trip and the dependent shared-memory load every 16 steps.)
+constexpr int LTCOLS = 512;             // columns per tile
+constexpr int LTILE = LTCOLS + 16;      // bytes per tile: one more 16-byte piece for the look-ahead letters of the last block
+static_assert(LSYNC <= 16 && LTCOLS % LSYNC == 0, "the look-ahead of a tile's last block stays inside the extra 16 bytes");
+__device__ __forceinline__ void tma_bar_init(unsigned bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_bar_init_done() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_tile(unsigned dst, const void *src, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(LTILE) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(LTILE), "r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned ld_shared_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// (warp-uniform spin, like every loop of the fill kernel whose trip count the compiler cannot see:
+// behind a per-lane spin loop the hardware may let part of the warp run ahead for good, and a split
+// warp takes the slow collective path of every shuffle)
+__device__ __forceinline__ void tma_bar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!__all_sync(FULL, done != 0u));
+}
+
 // Raw loads for the LSYNC columns of the NEXT block (lanes >= LSYNC duplicate a valid column): the
-// letter of the column AFTER mine and the boundary-row entry above this band (which may still be
+// sequence tile (TMA) and the boundary-row entry above this band (which may still be
 // L_INVALID; band 0: the row-0 running sum instead).  Nothing here USES a loaded value -- a lone
 // warp would stall on it -- that happens at the start of the next block.  Issued from the MIDDLE of
 // a block: early enough to hide the L2 latency behind half a block of steps, late enough that the
@@ -277,13 +366,24 @@ struct FetchCtx {
     const int2 *up_brow;
     const int *rowsum;
     int band, cj_next;              // my column of the next block
-    unsigned braw;
     int2 traw;
+    unsigned tile0, bar0;           // shared-space addresses: the warp's two sequence-tile slots and their mbarriers
+    unsigned seq0;                  // number (per warp, over all its bands) of this band's tile 0: tile k uses slot k & 1, phase (k >> 1) & 1
+    unsigned laddr;                 // shared-space address of the letter my lane looks up for the next block
+    unsigned braw;
+    __device__ __forceinline__ unsigned tile(unsigned k) const { return tile0 + (k & 1u) * LTILE; }
+    __device__ __forceinline__ unsigned bar(unsigned k) const { return bar0 + (k & 1u) * 8u; }
+    __device__ __forceinline__ void request(int S) const {        // one lane only
+        tma_load_tile(tile(seq0 + S), s2 + (size_t)S * LTCOLS, bar(seq0 + S));
+    }
+    __device__ __forceinline__ void wait(int S) const { tma_bar_wait(bar(seq0 + S), ((seq0 + S) >> 1) & 1u); }
 };
 __device__ __forceinline__ void long_fetch(FetchCtx &f, int N) {
-    f.braw = 0u;
+    // the letter of the column after mine (0-based index cj_next of seq_2) out of its tile: the
+    // block loop has waited for that tile.  Past the end of the sequence this reads slack bytes,
+    // discarded at the use.
+    f.braw = ld_shared_u8(f.laddr);
     f.traw = make_int2(0, 0);
-    if (f.cj_next + 1 <= N) f.braw = (unsigned)f.s2[f.cj_next];
     if (f.cj_next <= N) {
         if (f.band > 0) f.traw = ld_volatile_int2(f.up_brow + f.cj_next);
         else f.traw.x = f.rowsum[f.cj_next];
@@ -338,8 +438,14 @@ __device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsi
         bool hit = qs < 32 * LNC && (qs / LNC) == g;
         if (CHECK == 2) hit = hit && j >= 1 && j <= N;
         int2 *dst = band_vchk + ((size_t)(tt / LCC) * 32 + g) * LR;
+        if constexpr (LELL % 2 == 0) {      // two rows per 16-byte store (a lane's LR entries are 16-byte aligned)
 #pragma unroll
-        for (int r = KS * LELL; r < (KS + 1) * LELL; ++r) st_cg_pred(hit, dst + r, ln.hl[r], ln.Lp[r]);
+            for (int r = KS * LELL; r < (KS + 1) * LELL; r += 2)
+                st_cg_pred4(hit, dst + r, ln.hl[r], ln.Lp[r], ln.hl[r + 1], ln.Lp[r + 1]);
+        } else {
+#pragma unroll
+            for (int r = KS * LELL; r < (KS + 1) * LELL; ++r) st_cg_pred(hit, dst + r, ln.hl[r], ln.Lp[r]);
+        }
     }
     if constexpr (U + 1 < LSYNC)
         long_fill_step<MODE, CHECK, CK, U + 1>(ln, e, slot, g, q0, last_lane, t0, N, brow_j0, band_vchk, c, f);
@@ -362,6 +468,13 @@ __global__ void __launch_bounds__(32 * LWARPS)
 long_fill_kernel(const SchemeDev sc, const LongArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int4 s_stage[LWARPS][2][LSYNC];          // lane 0's inputs, two blocks per warp
+    __shared__ __align__(16) uint8_t s_tile[LWARPS][2][LTILE];   // TMA-staged tiles of seq_2, two per warp
+    __shared__ __align__(8) unsigned long long s_bar[LWARPS][2];  // their mbarriers
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * LWARPS; ++k) tma_bar_init((unsigned)__cvta_generic_to_shared(&s_bar[0][0] + k));
+        tma_bar_init_done();
+    }
     int *s_tab = reinterpret_cast<int *>(smem_raw);
     if (MODE == 1) {
         // shifted substitution costs 4*(sub(a,b) - gap_h[b] - gap_v[a]); row A = padding letter
@@ -371,8 +484,8 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             const int ai = k / sc.A, b = k - ai * sc.A;
             s_tab[k] = sc.sub4[k] - 4 * sc.gh_raw[b] - 4 * sc.gv_raw[ai];
         }
-        __syncthreads();
     }
+    __syncthreads();
     const unsigned tab_base = (unsigned)__cvta_generic_to_shared(s_tab);
     const int g = threadIdx.x & 31;     // the warps of a block never synchronise with each other again
     int4 *my_stage = &s_stage[threadIdx.x >> 5][0][0];
@@ -386,10 +499,14 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
     const unsigned big = a.big;
     // hot fields in registers (kernel parameters live in constant memory; an LDC inside
     // the step loop sits on the critical path of a lone warp)
-    const int N = a.n, M = a.m;
+    // (pinned: a plain copy is rematerialised as a constant-bank load wherever it is used -- 3 % of
+    // the kernel's time sat on those loads in the block prologue)
+    const int N = pin_reg(a.n), M = a.m;
     const uint8_t *const S2 = a.s2;
     const int *const ROWSUM = a.rowsum;
     const int O = sc.o;
+    const int wi = threadIdx.x >> 5;
+    unsigned tile_seq = 0;              // sequence tiles this warp has consumed (slot = seq & 1, barrier phase = (seq >> 1) & 1)
     for (;;) {
         int band = 0;
         if (g == 0) band = atomicAdd(a.band_counter, 1);
@@ -416,9 +533,9 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             const int cs = a.colsum[min(ib, M)];
             ln.rh_prev = 4 * ((int)min(big, (unsigned)cs) - (cs - O));
         }
-        int2 *my_brow = a.brow + (size_t)band * (N + 1);
-        const int2 *up_brow = a.brow + (size_t)(band > 0 ? band - 1 : 0) * (N + 1);
-        int2 *band_vchk = a.vchk + ((size_t)band * a.nck) * (32 * LR);
+        int2 *my_brow = pin_reg(a.brow + (size_t)band * (N + 1));
+        const int2 *up_brow = pin_reg(a.brow + (size_t)(band > 0 ? band - 1 : 0) * (N + 1));
+        int2 *band_vchk = pin_reg(a.vchk + ((size_t)band * a.nck) * (32 * LR));
 
         FetchCtx f;
         f.s2 = S2;
@@ -426,6 +543,12 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
         f.rowsum = ROWSUM;
         f.band = band;
         f.cj_next = 1 + (g & (LSYNC - 1));
+        f.tile0 = (unsigned)__cvta_generic_to_shared(&s_tile[wi][0][0]);
+        f.bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[wi][0]);
+        f.seq0 = tile_seq;
+        if (g == 0) { f.request(0); f.request(1); }
+        f.wait(0);
+        f.laddr = f.tile(f.seq0) + 1u + (unsigned)(g & (LSYNC - 1));
         long_fetch(f, N);                   // block 0
         const int nsteps = N + 32 * LNC - 1;
         // what the shuffle at the end of a (virtual) step -1 would have delivered: the lane above is
@@ -435,11 +558,20 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
         __syncwarp();                       // the previous band's last reads of the staging area are done
         for (int t0 = 0, blk = 0; t0 < nsteps; t0 += LSYNC, ++blk) {
             int2 tblk = f.traw;
-            const unsigned bnext = f.braw;
             const int cj = f.cj_next;       // = t0 + 1 + (g & (LSYNC - 1))
-            if (band > 0) {                 // entries requested half a block ago: poll only what has not arrived
-                if (cj <= N)
-                    while (tblk.x == L_INVALID) tblk = ld_volatile_int2(up_brow + cj);
+            const unsigned bnext = cj + 1 <= N ? f.braw : 0u;      // letter of the column after mine
+            if (band > 0) {
+                // entries requested half a block ago: poll only what has not arrived.  The loop is
+                // warp-uniform (vote), the reload predicated: no lane leaves the others behind, the
+                // warp enters the unrolled block converged (a split warp runs every shuffle of the
+                // block through the slow collective path -- 7x slower).
+                bool miss = cj <= N && tblk.x == L_INVALID;
+                while (__any_sync(FULL, miss)) {
+                    if (miss) {
+                        tblk = ld_volatile_int2(up_brow + cj);
+                        miss = tblk.x == L_INVALID;
+                    }
+                }
             } else if (cj <= N) {
                 const int rj = tblk.x;
                 const int ghs = rj - O;
@@ -448,6 +580,16 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             if (g < LSYNC) my_stage[(blk & 1) * LSYNC + g] = make_int4(tblk.x, tblk.y, (int)(MODE == 1 ? 4u * bnext : bnext), 0);
             __syncwarp();
             f.cj_next = cj + LSYNC;         // (past the last block the loads are guarded by cj <= N)
+            f.laddr += LSYNC;
+            if (((t0 + LSYNC) & (LTCOLS - 1)) == 0) {
+                // this block's fetch crosses into the next tile: it must have landed; the tile behind
+                // us (whose letters all sit in registers or the staging area by now) gives its slot
+                // to the tile after the next
+                const int S = t0 / LTCOLS;
+                f.wait(S + 1);
+                if (g == 0) f.request(S + 2);
+                f.laddr = f.tile(f.seq0 + S + 1) + 1u + (unsigned)(g & (LSYNC - 1));
+            }
             const unsigned slot = stage_base + (unsigned)((blk & 1) * LSYNC * 16);
             const int tq = t0 & (LCC - 1);
             const bool ck = tq < 32 * LNC || tq + LSYNC >= LCC;        // can a step of this block hit a checkpoint column?
@@ -461,6 +603,11 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             } else {
                 long_fill_block<MODE, 2, true>(ln, slot, g, t0, N, my_brow, band_vchk, c, f);
             }
+        }
+        {   // the last tile requested is never used; retire it so that the barrier phases stay in step
+            const int S_last = ((nsteps + LSYNC - 1) / LSYNC * LSYNC) / LTCOLS + 1;    // tiles 0 .. S_last were requested
+            f.wait(S_last);
+            tile_seq = f.seq0 + (unsigned)S_last + 1u;
         }
         // the last active step of every chain was column N: hl[] now holds h^(row, N)
         if (band == (M - 1) / LBAND && g == ((M - 1) % LBAND) / LR) {
@@ -693,9 +840,13 @@ __host__ __device__ inline int x_top(int j, int L) { return j * 4 + L; }
 __host__ __device__ inline int x_left(int i) { return -i - 1; }
 
 struct ParTrace {
+    const int *run_if;          // nullptr: always; else the X-propagation and the chain run only if *run_if != 0
+                                // (second attempt with a wider corridor, only when the first one failed)
     int W;                      // corridor half-width (columns)
     int XW;                     // row stride of xrow (entries)
     int *xrow;                  // nbands x XW x 3
+    int *corr;                  // nbands x 2: the corridor [lo, hi] of every band (written by the X-propagation,
+                                // so that the serial chain does no 64-bit divisions)
     int *xlast;                 // X_0(m, n)
     int *entry;                 // nbands x 4: i, j, L, kind (0 walk, 1 vertical run only, 2 not on the path)
     long long *seg_off;         // nbands: start of the band's ops in seg_ops
@@ -722,6 +873,7 @@ long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *s_sub = reinterpret_cast<int *>(smem_raw);
     int *s_gh;
+    if (pt.run_if && *pt.run_if == 0) return;
     long_load_tables<SIMPLE>(sc, s_sub, s_gh);
     const int g = threadIdx.x & 31;
     const int band = blockIdx.x * LWARPS + (threadIdx.x >> 5);
@@ -729,6 +881,7 @@ long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
     const TraceConsts k{4u * sc.o, 4u * sc.mm, 4u * sc.gh + 1u, a.big};
     int lo, hi;
     long_corridor(band, a.m, a.n, pt.W, lo, hi);
+    if (g == 0) { pt.corr[2 * band] = lo; pt.corr[2 * band + 1] = hi; }
     const int width = hi - lo;
     const int ib = band * LBAND + g * LR;
     LongLane<SIMPLE> ln;
@@ -827,9 +980,11 @@ long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
 
 __global__ void long_chain_kernel(const LongArgs a, const ParTrace pt) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (pt.run_if && *pt.run_if == 0) return;
     const int nb = a.nbands;
     for (int b = 0; b < nb; ++b) pt.entry[b * 4 + 3] = 2;
     int b = nb - 1, X = *pt.xlast;
+    int lo_next = nb >= 2 ? pt.corr[2 * (nb - 2)] : 0, hi_next = nb >= 2 ? pt.corr[2 * (nb - 2) + 1] : 0;
     int ei = a.m, ej = a.n, eL = 0;
     long long off = 0;
     bool ok = true;
@@ -872,8 +1027,8 @@ __global__ void long_chain_kernel(const LongArgs a, const ParTrace pt) {
             }
             break;
         }
-        int lo, hi;
-        long_corridor(b, a.m, a.n, pt.W, lo, hi);
+        const int lo = lo_next, hi = hi_next;          // corridor of band b, requested an iteration ago
+        if (b > 0) { lo_next = pt.corr[2 * (b - 1)]; hi_next = pt.corr[2 * (b - 1) + 1]; }
         if (!(ej > lo && ej <= hi)) { ok = false; break; }
         X = pt.xrow[((size_t)b * pt.XW + (ej - lo)) * 3 + eL];
     }

@@ -14,6 +14,8 @@ GV(i) = sum_{t<=i} gap_v[s1[t-1]].  Then
     d0 = h^(i-1,j-1) + 4*(sub(a,b) - gap_h[b] - gap_v[a])
     h  = min(d0, L^(i,j-1), U^(i-1,j))
     L^(i,j) = min(h + 4o, L^(i,j-1)),   U^(i,j) = min(h + 4o, U^(i-1,j))
+(the kernel evaluates the U recurrence of a chain of rows in an equivalent form that keeps U off the
+row-to-row dependency, see chain() below)
 where L(i,j) = min(D0+o, D1, D2+o)(i,j) is the level-1 candidate handed to column j+1 and
 U(i,j) = min(D0+o, D1+o, D2)(i,j) the level-2 candidate handed to row i+1: the gap-extension
 additions disappear from the cell update.
@@ -116,27 +118,39 @@ def fill_long(s1, s2, sc: Scheme, ELL=2, NC=2, LANES=4, LSYNC=4, LCC=8):
                     chain: it runs the update with inputs that make it the identity (d0 = own h, U from
                     above = +inf, infinite gap open for the U handed down); hd / ub become garbage."""
                     j = t - (g * NC + k) + 1
+                    # The kernel keeps U off the row-to-row path: e_r = min(d0_r, L_r),
+                    # P_r = min(e_r + 4o, P_{r-1}) (never sees U_in), h_r = min3(e_r, P_{r-1}, U_in),
+                    # U handed down = min(P_last, U_in).  `ref_*` below is the textbook order it must equal.
                     if not (1 <= j <= n):
                         up = L_INF
+                        P = L_INF
                         for r in range(k * ELL, (k + 1) * ELL):
-                            h = min(hl[g][r], Lp[g][r], up)
+                            e = min(hl[g][r], Lp[g][r])
+                            h = min(e, P, up)
+                            P = min(e + L_BIGADD, P)
                             assert h == hl[g][r] and min(h + o4, Lp[g][r]) == Lp[g][r], "identity"
-                            up = min(h + L_BIGADD, up)
-                            assert up == L_INF
+                            assert P == L_INF
+                        assert min(P, up) == L_INF
                         hd[g][k] = ub[g][k] = None          # garbage, must never be read
                         return
                     assert bv[g][k] == s2[j - 1]
+                    P = L_INF
+                    ref_up = up
                     for r in range(k * ELL, (k + 1) * ELL):
                         d0 = diag + sv[g][r]
-                        h = min(d0, Lp[g][r], up)
+                        e = min(d0, Lp[g][r])
+                        h = min(e, P, up)
+                        P = min(e + o4, P)
+                        assert h == min(d0, Lp[g][r], ref_up), "U-free form of h"
+                        ref_up = min(h + o4, ref_up)
+                        assert min(P, up) == ref_up, "U-free form of U"
                         diag = hl[g][r]
                         hl[g][r] = h
                         Lp[g][r] = min(h + o4, Lp[g][r])
-                        up = min(h + o4, up)
                     hd[g][k] = diag
-                    ub[g][k] = up
+                    ub[g][k] = min(P, up)
                     if k == NC - 1 and g == LANES - 1:
-                        brow[band][j] = (hl[g][LR - 1], up)
+                        brow[band][j] = (hl[g][LR - 1], ub[g][k])
 
                 def shuffle():
                     return ([hl[g - 1][LR - 1] if g > 0 else None for g in range(LANES)],

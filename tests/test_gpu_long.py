@@ -160,6 +160,29 @@ def test_config4_100kb_linear_space():
     ctx.close()
 
 
+def test_second_corridor_attempt_catches_a_path_off_the_narrow_corridor():
+    """The band-parallel traceback tries a narrow corridor around the straight diagonal first and a
+    wide one only if the path leaves it (both on the device, no host round trip).  A 350-letter
+    insertion pushes the path out of the first (192 + (m+n)/1024 columns) but not the second."""
+    rng = np.random.default_rng(6)
+    ctx = _native.Context(0)
+    dense = _simple_dense(4, 3, 1, 1, 2)
+    ctx.set_scheme(dense)
+    s1 = rng.integers(0, 4, 6000).astype(np.uint8)
+    s2 = np.concatenate([rng.integers(0, 4, 350).astype(np.uint8), s1[:5650]])
+    cost, ops, status, info = ctx.align_long(s1, s2)
+    assert status == 0 and info["trace_mode"] == 1
+    rc, vcost = c_oracle.verify_path(s1, s2, _oracle_dense(dense), ops)
+    assert rc == 0 and vcost == cost
+    os.environ["GA_LONG_CORRIDORS"] = "1"                  # the wide corridor alone gives the same path
+    try:
+        cost_w, ops_w, status_w, info_w = ctx.align_long(s1, s2)
+    finally:
+        os.environ.pop("GA_LONG_CORRIDORS", None)
+    assert (cost_w, status_w, info_w["trace_mode"]) == (cost, 0, 1) and np.array_equal(ops_w, ops)
+    ctx.close()
+
+
 def test_parallel_trace_falls_back_outside_the_corridor():
     """Unrelated sequences of very different composition push the path far off the diagonal;
     whichever form runs, the result is the canonical alignment."""

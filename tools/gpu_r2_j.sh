@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, GPU call J: source-level counters of the long-pair fill (where does a lone warp stall?)
+mkdir -p gpurun_out/r2j
+O=gpurun_out/r2j
+python tools/prof_long.py 100000 > $O/plain.txt 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:long_fill -c 1 -o /tmp/lf python tools/prof_long.py 100000 > $O/ncu.txt 2>&1
+ncu -i /tmp/lf.ncu-rep --page raw --csv > $O/long_fill_raw.csv 2>/dev/null
+ncu -i /tmp/lf.ncu-rep --page details --csv > $O/long_fill_details.csv 2>/dev/null
+ncu -i /tmp/lf.ncu-rep --page source --csv > $O/long_fill_src.csv 2>/dev/null
+tail -1 $O/plain.txt; ls -la $O
