@@ -1313,9 +1313,10 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         return fail(ctx, GA_E_NOMEM, "checkpoints need %zu bytes, above the scratch limit", brow_b + vchk_b);
     const size_t ops_words = (size_t)((m + n + 15) / 16 + 1);
     int rc;
-    // (seq_2 carries slack: the fill kernel's TMA tiles of the run-out steps reach up to
-    // 2 * LTCOLS + 64 bytes behind the last letter; what they hold there is never used)
-    if ((rc = ensure(ctx, ctx->d_s1, (size_t)m + 16)) || (rc = ensure(ctx, ctx->d_s2, (size_t)n + 2048)) ||
+    // (seq_2 carries zeroed slack: the fill kernel's TMA tiles of the run-out steps reach up to
+    // 2 * LTCOLS + 96 bytes behind the last letter; lanes whose column does not exist look letters
+    // up there -- their results are discarded, but a table address is formed from them)
+    if ((rc = ensure(ctx, ctx->d_s1, (size_t)m + 16)) || (rc = ensure(ctx, ctx->d_s2, (size_t)n + 2560)) ||
         (rc = ensure(ctx, ctx->l_colsum, colsum.size() * 4)) || (rc = ensure(ctx, ctx->l_rowsum, rowsum.size() * 4)) ||
         (rc = ensure(ctx, ctx->l_brow, brow_b)) || (rc = ensure(ctx, ctx->l_vchk, vchk_b)) ||
         (rc = ensure(ctx, ctx->l_misc, 256)) ||
@@ -1323,6 +1324,7 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         return rc;
     CK(cudaMemcpyAsync(ctx->d_s1.p, s1, (size_t)m, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_s2.p, s2, (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync((uint8_t *)ctx->d_s2.p + n, 0, 2560, st));
     CK(cudaMemcpyAsync(ctx->l_colsum.p, colsum.data(), colsum.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->l_rowsum.p, rowsum.data(), rowsum.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->l_brow.p, 0x80, brow_b, st));      // L_INVALID = boundary entry not yet written
@@ -1352,7 +1354,11 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     const int grid = std::min((nbands + LWARPS - 1) / LWARPS, ctx->sm_count * blocks_per_sm);
     const bool fill_table = sc.A <= 64;          // shifted substitution table in shared memory
     CK(cudaEventRecord(ctx->ev[2], st));
-    if (fill_table) long_fill_kernel<1><<<grid, 32 * LWARPS, (size_t)(sc.A + 1) * sc.A * 4, st>>>(sc, a);
+    // small alphabets: one table entry per pair of rows (GA_LONG_PAIR_TABLE=0: the single-row table, for A/B runs)
+    bool pair_table = LONG_PAIR_TABLE_OK && sc.A <= 8;
+    if (const char *e = getenv("GA_LONG_PAIR_TABLE")) pair_table = pair_table && atoi(e) != 0;
+    if (pair_table) long_fill_kernel<2><<<grid, 32 * LWARPS, (size_t)(sc.A + 1) * (sc.A + 1) * sc.A * 8, st>>>(sc, a);
+    else if (fill_table) long_fill_kernel<1><<<grid, 32 * LWARPS, (size_t)(sc.A + 1) * sc.A * 4, st>>>(sc, a);
     else long_fill_kernel<0><<<grid, 32 * LWARPS, 0, st>>>(sc, a);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[3], st));

@@ -150,6 +150,7 @@ __device__ __forceinline__ void long_cells(const SchemeDev &sc, const int *s_sub
 // ---------------------------------------------------------------------------- K2
 constexpr int LWARPS = 4;           // independent band-sweeping warps per block (one per scheduler)
 
+constexpr bool LONG_PAIR_TABLE_OK = LELL % 2 == 0;     // MODE 2 needs the rows of a chain in pairs
 // MODE 1: substitution costs (already shifted by the gap costs) from a table in shared memory --
 // any scheme with A <= 64 letters.  MODE 0: compare-and-select for simple schemes over larger
 // alphabets (the table would not fit).
@@ -183,12 +184,35 @@ struct FillConsts {
 // shifted substitution cost of row r against column letter b
 template <int MODE>
 __device__ __forceinline__ int long_sub(const FillLane<MODE> &ln, int r, unsigned b, const FillConsts &c) {
-    if (MODE == 1) {
+    if (MODE != 0) {
         int v;
         asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(ln.aw[r] * c.k1 + b));        // address add as IMAD (FMA pipe)
         return v;
     }
     return ln.aw[r] != b ? c.cx4 : c.cm4;
+}
+
+// MODE 2 (alphabets up to 8 letters, an even number of rows per chain): the table is indexed by the
+// letters of TWO consecutive rows, an entry holds both costs -- one 8-byte load and one address per
+// two rows.  (Shared-memory instructions are what four band-sweeping warps of an SM contend for.)
+template <int MODE>
+__host__ __device__ constexpr unsigned long_letter_scale() { return MODE == 1 ? 4u : MODE == 2 ? 8u : 1u; }
+
+// substitution costs of rows [r0, r1) against the column letter with (scaled) offset b
+template <int MODE>
+__device__ __forceinline__ void long_sub_rows(FillLane<MODE> &ln, int r0, int r1, unsigned b, const FillConsts &c) {
+    if (MODE == 2) {
+#pragma unroll
+        for (int r = r0; r < r1; r += 2) {
+            int v0, v1;
+            asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(ln.aw[r] * c.k1 + b));
+            ln.sv[r] = v0;
+            ln.sv[r + 1] = v1;
+        }
+    } else {
+#pragma unroll
+        for (int r = r0; r < r1; ++r) ln.sv[r] = long_sub<MODE>(ln, r, b, c);
+    }
 }
 
 // The LELL cells of chain K at its current column.  diag / up: h^(i-1, j-1) and U^(i-1, j) of the
@@ -227,9 +251,10 @@ __device__ __forceinline__ void long_chain(FillLane<MODE> &ln, int diag, int up,
     int P = L_INF;
 #pragma unroll
     for (int r = K * LELL; r < (K + 1) * LELL; ++r) {
-        int d0 = (int)((unsigned)diag * c.k1 + (unsigned)ln.sv[r]);                 // IMAD
-        if (CHECK && !act) d0 = ln.hl[r];
-        const int e = min(d0, ln.Lp[r]);
+        // e = min(diag + sub', L): one fused add-min (inactive: min(own h + 0, L) = own h)
+        const int dg = (CHECK && !act) ? ln.hl[r] : diag;
+        const int sv = (CHECK && !act) ? 0 : ln.sv[r];
+        const int e = __viaddmin_s32(dg, sv, ln.Lp[r]);
         const int h = __vimin3_s32(e, P, up);
         P = __viaddmin_s32(e, ob, P);
         diag = ln.hl[r];
@@ -355,6 +380,12 @@ __device__ __forceinline__ void tma_bar_wait(unsigned bar, unsigned parity) {
     } while (!__all_sync(FULL, done != 0u));
 }
 
+// (Measured and rejected, round 2: handing the last row of a lane to the lane below through a
+// shared-memory exchange area (one STS.64 + one LDS.64 per step, volatile so that the assembler keeps
+// their order) with every lane reading its own column letter from a TMA-fed ring -- no shuffle and no
+// lane-0 select left, 42 instead of 52 instructions per step, 25 instead of 28 on the ALU pipe -- ran
+// 8.53 ms against 8.16 ms for this form at 100 kb x 100 kb: the four band-sweeping warps of an SM
+// queue on the shared-memory pipe (10 of its instructions per step each), which the shuffles do not.)
 // Raw loads for the LSYNC columns of the NEXT block (lanes >= LSYNC duplicate a valid column): the
 // sequence tile (TMA) and the boundary-row entry above this band (which may still be
 // L_INVALID; band 0: the row-0 running sum instead).  Nothing here USES a loaded value -- a lone
@@ -426,7 +457,7 @@ __device__ __forceinline__ void long_fill_step(FillLane<MODE> &ln, int4 &e, unsi
 #pragma unroll
     for (int k = LNC - 1; k >= 0; --k) ln.bv[k] = k == 0 ? nb0 : ln.bv[k - 1];
 #pragma unroll
-    for (int r = 0; r < LR; ++r) ln.sv[r] = long_sub<MODE>(ln, r, ln.bv[r / LELL], c);
+    for (int k = 0; k < LNC; ++k) long_sub_rows<MODE>(ln, k * LELL, (k + 1) * LELL, ln.bv[k], c);
     if constexpr (U + 1 < LSYNC)
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
                      : "r"(slot + 16u * (U + 1)));
@@ -484,6 +515,14 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
             const int ai = k / sc.A, b = k - ai * sc.A;
             s_tab[k] = sc.sub4[k] - 4 * sc.gh_raw[b] - 4 * sc.gv_raw[ai];
         }
+    } else if (MODE == 2) {
+        // the same costs for every PAIR of row letters (a0, a1): entry b of pair row a0 * (A+1) + a1
+        const int A1 = sc.A + 1, n_ent = A1 * A1 * sc.A;
+        for (int k = threadIdx.x; k < n_ent; k += blockDim.x) {
+            const int b = k % sc.A, pr = k / sc.A, a0 = pr / A1, a1 = pr - a0 * A1;
+            s_tab[2 * k] = sc.sub4[a0 * sc.A + b] - 4 * sc.gh_raw[b] - 4 * sc.gv_raw[a0];
+            s_tab[2 * k + 1] = sc.sub4[a1 * sc.A + b] - 4 * sc.gh_raw[b] - 4 * sc.gv_raw[a1];
+        }
     }
     __syncthreads();
     const unsigned tab_base = (unsigned)__cvta_generic_to_shared(s_tab);
@@ -516,18 +555,23 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
         FillLane<MODE> ln;
 #pragma unroll
         for (int k = 0; k < LNC; ++k) { ln.ub[k] = 0; ln.hd[k] = 0; ln.bv[k] = 0u; }
-        if (g == 0) ln.bv[0] = MODE == 1 ? 4u * (unsigned)S2[0] : (unsigned)S2[0];     // chain 0 of lane 0 starts on column 1
+        if (g == 0) ln.bv[0] = long_letter_scale<MODE>() * (unsigned)S2[0];     // chain 0 of lane 0 starts on column 1
 #pragma unroll
         for (int r = 0; r < LR; ++r) {
             const int row = ib + r;
-            if (MODE == 1) ln.aw[r] = tab_base + 4u * (unsigned)sc.A * (row < M ? (unsigned)a.s1[row] : (unsigned)sc.A);
-            else ln.aw[r] = row < M ? (unsigned)a.s1[row] : (unsigned)PAD_A;
+            const unsigned la = row < M ? (unsigned)a.s1[row] : (unsigned)sc.A;
+            if (MODE == 2) {        // even rows: the pair row of (my letter, the next row's letter)
+                const unsigned lb = row + 1 < M ? (unsigned)a.s1[min(row + 1, M - 1)] : (unsigned)sc.A;
+                ln.aw[r] = tab_base + 8u * (unsigned)sc.A * (la * (unsigned)(sc.A + 1) + lb);
+            } else if (MODE == 1) ln.aw[r] = tab_base + 4u * (unsigned)sc.A * la;
+            else ln.aw[r] = row < M ? la : (unsigned)PAD_A;
             const int cs = a.colsum[min(ib + r + 1, M)];
             const int gvs = cs - O;
             ln.hl[r] = 4 * ((int)min(big, (unsigned)cs) - gvs);
             ln.Lp[r] = 4 * ((int)min(big, (unsigned)(cs + O)) - gvs);
-            ln.sv[r] = long_sub<MODE>(ln, r, ln.bv[r / LELL], c);
         }
+#pragma unroll
+        for (int k = 0; k < LNC; ++k) long_sub_rows<MODE>(ln, k * LELL, (k + 1) * LELL, ln.bv[k], c);
         ln.rh_prev = 0;
         if (ib != 0) {
             const int cs = a.colsum[min(ib, M)];
@@ -577,7 +621,7 @@ long_fill_kernel(const SchemeDev sc, const LongArgs a) {
                 const int ghs = rj - O;
                 tblk = make_int2(4 * ((int)min(big, (unsigned)rj) - ghs), 4 * ((int)min(big, (unsigned)(rj + O)) - ghs));
             }
-            if (g < LSYNC) my_stage[(blk & 1) * LSYNC + g] = make_int4(tblk.x, tblk.y, (int)(MODE == 1 ? 4u * bnext : bnext), 0);
+            if (g < LSYNC) my_stage[(blk & 1) * LSYNC + g] = make_int4(tblk.x, tblk.y, (int)(long_letter_scale<MODE>() * bnext), 0);
             __syncwarp();
             f.cj_next = cj + LSYNC;         // (past the last block the loads are guarded by cj <= N)
             f.laddr += LSYNC;
