@@ -9,6 +9,8 @@ cost far more than the alignment itself).
 
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 from . import _native, start
@@ -173,12 +175,42 @@ def _lower_batch(seqs_1, seqs_2, limit, scheme):
     return up1, up2, dense, np.concatenate(enc1), off1, np.concatenate(enc2), off2
 
 
-def _lower_native(seqs_1, seqs_2, limit, scheme):
-    """The all-ASCII case through the `_strings` extension (csrc/ga_strings.c): two parallel passes
-    over the strings' own buffers -- which byte values occur, then every letter mapped through one
-    256-entry table (case folding + letter -> index) -- instead of join / encode / translate in
-    Python (~5x faster on a million read pairs).  -> None when the extension is not built, the
-    inputs are not lists of ASCII str, or anything needs the per-pair path's exact error."""
+_PINNED = threading.local()
+
+
+def _pinned_bytes(role: str, nbytes: int) -> np.ndarray:
+    """A reusable page-locked host buffer (per thread and role) as a uint8 array: the letters are
+    written once, by the lowering threads, where the copy engine reads them from.  Plain memory
+    when there is no CUDA device (CPU-only tests of the lowering)."""
+    pool = _PINNED.__dict__.setdefault("pool", {})
+    t = pool.get(role)
+    if t is None or t.numel() < nbytes:
+        import torch
+        cap = max(nbytes, 1 << 20) * 5 // 4
+        t = torch.empty(cap, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        pool[role] = t
+    return t.numpy()[:nbytes]
+
+
+def _letters_of(cat: np.ndarray, off: np.ndarray, k: int, bits: int) -> np.ndarray:
+    """Letter indices of sequence k of a lowered batch (bits = 8: one byte per letter; 2 / 4: the
+    C-ABI's packed letter streams)."""
+    lo, hi = int(off[k]), int(off[k + 1])
+    if bits == 8:
+        return cat[lo:hi]
+    per = 8 // bits
+    at = np.arange(lo, hi)
+    return (cat[at // per] >> ((at % per) * bits).astype(np.uint8)) & ((1 << bits) - 1)
+
+
+def _lower_native(seqs_1, seqs_2, limit, scheme, pack=False):
+    """The all-ASCII case through the `_strings` extension (csrc/ga_strings.c): threaded passes
+    over the strings' own buffers -- headers, which byte values occur, then every letter mapped
+    through one 256-entry table (case folding + letter -> index) straight into page-locked
+    memory -- instead of join / encode / translate in Python.  `pack`: alphabets of up to 4 / 16
+    letters are written as the C-ABI's 2-bit / 4-bit letter streams (a quarter / half of the
+    upload).  -> (..., bits) or None when the extension is not built, the inputs are not lists of
+    ASCII str, or anything needs the per-pair path's exact error."""
     try:
         from . import _strings
     except ImportError:
@@ -205,14 +237,19 @@ def _lower_native(seqs_1, seqs_2, limit, scheme):
             table[ord(ch)] = k
             table[ord(ch.lower())] = k
     table = bytes(table)
-    cat1 = np.frombuffer(_strings.translate(h1, table), dtype=np.uint8)
-    cat2 = np.frombuffer(_strings.translate(h2, table), dtype=np.uint8)
+    bits = 8
+    if pack:
+        bits = 2 if dense.A <= 4 else 4 if dense.A <= 16 else 8
+    cat1 = _pinned_bytes("s1", (_t1 * bits + 7) // 8 + 16)
+    cat2 = _pinned_bytes("s2", (_t2 * bits + 7) // 8 + 16)
+    _strings.translate_into(h1, table, cat1, bits)
+    _strings.translate_into(h2, table, cat2, bits)
     n = len(seqs_1)
     off1 = np.zeros(n + 1, dtype=np.int64)
     off2 = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(m_len, out=off1[1:])
     np.cumsum(n_len, out=off2[1:])
-    return _LazyUpper(seqs_1), _LazyUpper(seqs_2), dense, cat1, off1, cat2, off2
+    return _LazyUpper(seqs_1), _LazyUpper(seqs_2), dense, cat1, off1, cat2, off2, bits
 
 
 def _lower_ascii_batch(seqs_1, seqs_2, limit, scheme):
@@ -302,12 +339,17 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
     limit = start.MAX_SEQ_LEN_PRODUCT if max_seq_len_prod is None else max_seq_len_prod
     scheme = Scheme(scoring_mat_name, scoring_mat_path, match_score, mismatch_score, mismatch_cost,
                     gap_open_score, gap_open_cost, gap_extension_score, gap_extension_cost)
-    lowered = _lower_native(seqs_1, seqs_2, limit, scheme)
+    one_gpu = devices is None or len(devices) <= 1
+    bits = 8
+    lowered = _lower_native(seqs_1, seqs_2, limit, scheme, pack=one_gpu)    # (shards are cut at letter offsets: bytes)
+    if lowered is not None:
+        bits, lowered = lowered[-1], lowered[:-1]
     if lowered is None:
         lowered = _lower_ascii_batch(seqs_1, seqs_2, limit, scheme)
     if lowered is None:
         lowered = _lower_batch(seqs_1, seqs_2, limit, scheme)
     up1, up2, dense, cat1, off1, cat2, off2 = lowered
+    seq_flags = {8: 0, 4: _native.GA_F_SEQ_4BIT, 2: _native.GA_F_SEQ_2BIT}[bits]
     def on_device(dev, c1, o1, c2, o2):
         """-> (cost, rle, rle_off, ops_len, status): the compact result stream of one GPU."""
         ctx = _native.default_context(dev)
@@ -317,25 +359,25 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
         if n_pairs > 1 and o1[-1] == m0 * n_pairs and o2[-1] == n0 * n_pairs and \
                 np.array_equal(o1, np.arange(n_pairs + 1) * m0) and np.array_equal(o2, np.arange(n_pairs + 1) * n0):
             # fixed-length batch (reads of one length): the entry point without offset arrays
-            res, rle, rle_off = ctx.align_batch_rle(c1, None, c2, None, m0, n0, n_pairs)
+            res, rle, rle_off = ctx.align_batch_rle(c1, None, c2, None, m0, n0, n_pairs, flags=seq_flags)
         else:
-            res, rle, rle_off = ctx.align_batch_rle(c1, o1, c2, o2)
+            res, rle, rle_off = ctx.align_batch_rle(c1, o1, c2, o2, flags=seq_flags)
         nops = res["nops_status"]
         return (res["cost"].copy(), rle[: int(rle_off[-1])], rle_off, (nops & 0x7FFFFFFF).astype(np.int32),
                 (nops >> 31).astype(np.int32))
 
-    if devices is None or len(devices) <= 1:
+    if one_gpu:
         cost, ops, ops_off, ops_len, status = on_device(device if not devices else devices[0], cat1, off1, cat2, off2)
     else:
         from .parallel import align_on_devices
         cost, ops, ops_off, ops_len, status = align_on_devices(on_device, cat1, off1, cat2, off2, list(devices))
     res = BatchAlignment(up1, up2, cost, ops, ops_off, ops_len, status, scheme, rle=True,
                          lens=(np.diff(off1), np.diff(off2)))
-    _realign_single_letter_pairs(res, dense, cat1, off1, cat2, off2, scheme, device if not devices else devices[0])
+    _realign_single_letter_pairs(res, dense, cat1, off1, cat2, off2, scheme, device if not devices else devices[0], bits)
     return res
 
 
-def _realign_single_letter_pairs(res: "BatchAlignment", dense, cat1, off1, cat2, off2, scheme, device):
+def _realign_single_letter_pairs(res: "BatchAlignment", dense, cat1, off1, cat2, off2, scheme, device, bits=8):
     """Simple schemes build their matrices over the letters of the PAIR (start.py:319-343), so a
     pair made of one repeated letter has no mismatch entry and a smaller max_cost -- hence a
     smaller boundary sentinel (globaligner.py:777) -- than the batch-wide tables give it.  The
@@ -351,8 +393,8 @@ def _realign_single_letter_pairs(res: "BatchAlignment", dense, cat1, off1, cat2,
     ctx = _native.default_context(device)
     patched = {}
     for k in short:
-        a = cat1[off1[k]:off1[k + 1]]
-        b = cat2[off2[k]:off2[k + 1]]
+        a = _letters_of(cat1, off1, int(k), bits)
+        b = _letters_of(cat2, off2, int(k), bits)
         if not (a.min() == a.max() == b.min() == b.max()):
             continue
         s1, s2 = res.seqs_1[int(k)], res.seqs_2[int(k)]

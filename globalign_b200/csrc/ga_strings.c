@@ -11,6 +11,14 @@
  *                            takes the general Python path)
  *   translate(handle, t)  -> bytes: every letter of every sequence mapped through the 256-entry
  *                            table t (case folding and letter -> index in one pass), concatenated
+ *   translate_into(handle, t, buffer, bits)
+ *                         -> None: the same into a writable buffer the caller owns (pinned host
+ *                            memory: no page faults, and the upload is a plain DMA), one byte per
+ *                            letter (bits = 8) or as the C-ABI's 2-bit / 4-bit little-endian
+ *                            letter streams (GA_F_SEQ_2BIT / GA_F_SEQ_4BIT, include/globalign_b200.h)
+ *
+ * The strings of a million read pairs are two million separate heap objects: even reading their
+ * headers (type, kind, length, data pointer) is a cache miss each, so that pass is threaded too.
  *
  * The GIL is held throughout (the worker threads touch no Python object, only the character
  * buffers the handle points into; the handle keeps the list alive).  No alignment work happens
@@ -45,7 +53,59 @@ typedef struct {
     unsigned char seen[256];
     const unsigned char *table;
     unsigned char *out;
+    PyObject **items;        /* header pass: the list's items */
+    int64_t *lens;
+    int bad;                 /* header pass: an item is not a compact ASCII str */
+    int bits;                /* translate_into: 8, 4 or 2 */
 } Job;
+
+/* type, kind, length and data pointer of every string of [lo, hi): reads object headers only (no
+ * reference counts, no allocation); the calling thread holds the GIL throughout, so nothing can
+ * change them */
+static void *header_job(void *arg) {
+    Job *j = (Job *)arg;
+    Handle *h = (Handle *)j->h;
+    j->bad = 0;
+    for (Py_ssize_t k = j->lo; k < j->hi; ++k) {
+        PyObject *s = j->items[k];
+        if (!PyUnicode_Check(s) || !PyUnicode_IS_COMPACT_ASCII(s)) { j->bad = 1; return NULL; }
+        h->ptr[k] = (const unsigned char *)PyUnicode_1BYTE_DATA(s);
+        j->lens[k] = (int64_t)PyUnicode_GET_LENGTH(s);
+    }
+    return NULL;
+}
+
+/* my sequences as a little-endian stream of `bits`-wide fields (letter k of the concatenation in
+ * bits [k*bits, (k+1)*bits) of the output).  A byte that two sequences share is written first by
+ * the tail of the earlier one (assignment, upper fields zero) and then OR-ed into by the head of
+ * the later one; jobs start on byte boundaries (run_jobs), so both happen in one thread. */
+static void *pack_job(void *arg) {
+    Job *j = (Job *)arg;
+    const int bits = j->bits, per = 8 / bits;
+    const unsigned char *t = j->table;
+    for (Py_ssize_t k = j->lo; k < j->hi; ++k) {
+        const unsigned char *p = j->h->ptr[k];
+        int64_t at = j->h->off[k];
+        const int64_t end = j->h->off[k + 1];
+        while (at < end && at % per) {                          /* head */
+            j->out[at / per] |= (unsigned char)(t[*p++] << ((at % per) * bits));
+            ++at;
+        }
+        unsigned char *o = j->out + at / per;
+        if (bits == 2) {
+            for (; at + 4 <= end; at += 4, p += 4)
+                *o++ = (unsigned char)(t[p[0]] | (t[p[1]] << 2) | (t[p[2]] << 4) | (t[p[3]] << 6));
+        } else {
+            for (; at + 2 <= end; at += 2, p += 2) *o++ = (unsigned char)(t[p[0]] | (t[p[1]] << 4));
+        }
+        if (at < end) {                                         /* tail */
+            unsigned v = 0;
+            for (int f = 0; at < end; ++at, ++f) v |= (unsigned)t[*p++] << (f * bits);
+            *o = (unsigned char)v;
+        }
+    }
+    return NULL;
+}
 
 static void *scan_job(void *arg) {
     Job *j = (Job *)arg;
@@ -78,7 +138,7 @@ static int n_threads(Py_ssize_t n) {
 }
 
 /* split [0, n) so that every thread gets about the same number of LETTERS */
-static void run_jobs(const Handle *h, void *(*fn)(void *), Job *jobs, int T) {
+static void run_jobs(const Handle *h, void *(*fn)(void *), Job *jobs, int T, int per) {
     pthread_t th[16];
     const int64_t total = h->off[h->n];
     Py_ssize_t at = 0;
@@ -91,6 +151,7 @@ static void run_jobs(const Handle *h, void *(*fn)(void *), Job *jobs, int T) {
             Py_ssize_t mid = (lo + hi) / 2;
             if (h->off[mid] >= want) hi = mid; else lo = mid + 1;
         }
+        while (lo < h->n && h->off[lo] % per) ++lo;        /* packed output: jobs start on a byte boundary */
         at = t + 1 == T ? h->n : lo;
         jobs[t].hi = at;
     }
@@ -110,20 +171,32 @@ static PyObject *py_scan(PyObject *self, PyObject *arg) {
     if (!h->ptr || !h->off) { free(h->ptr); free(h->off); free(h); return PyErr_NoMemory(); }
     h->n = n;
     h->off[0] = 0;
-    for (Py_ssize_t k = 0; k < n; ++k) {
-        PyObject *s = PyList_GET_ITEM(arg, k);
-        if (!PyUnicode_Check(s) || !PyUnicode_IS_COMPACT_ASCII(s)) {       /* not ASCII: general path */
+    Job jobs[16];
+    const int T = n_threads(n);
+    {   /* headers, threaded over equal slices of the list; lengths land in off[1..] and are summed after */
+        pthread_t th[16];
+        PyObject **items = ((PyListObject *)arg)->ob_item;
+        for (int t = 0; t < T; ++t) {
+            jobs[t].h = h;
+            jobs[t].items = items;
+            jobs[t].lens = h->off + 1;
+            jobs[t].lo = n * t / T;
+            jobs[t].hi = n * (t + 1) / T;
+        }
+        for (int t = 1; t < T; ++t) pthread_create(&th[t], NULL, header_job, &jobs[t]);
+        header_job(&jobs[0]);
+        for (int t = 1; t < T; ++t) pthread_join(th[t], NULL);
+        int bad = 0;
+        for (int t = 0; t < T; ++t) bad |= jobs[t].bad;
+        if (bad) {                                                          /* not ASCII: general path */
             free(h->ptr); free(h->off); free(h);
             Py_RETURN_NONE;
         }
-        h->ptr[k] = (const unsigned char *)PyUnicode_1BYTE_DATA(s);
-        h->off[k + 1] = h->off[k] + (int64_t)PyUnicode_GET_LENGTH(s);
+        for (Py_ssize_t k = 0; k < n; ++k) h->off[k + 1] += h->off[k];
     }
     Py_INCREF(arg);
     h->list = arg;
-    Job jobs[16];
-    const int T = n_threads(n);
-    run_jobs(h, scan_job, jobs, T);
+    run_jobs(h, scan_job, jobs, T, 1);
     unsigned char seen[256];
     memset(seen, 0, sizeof seen);
     for (int t = 0; t < T; ++t)
@@ -156,14 +229,46 @@ static PyObject *py_translate(PyObject *self, PyObject *args) {
         jobs[t].table = (const unsigned char *)table.buf;
         jobs[t].out = (unsigned char *)PyBytes_AS_STRING(out);
     }
-    run_jobs(h, translate_job, jobs, T);
+    run_jobs(h, translate_job, jobs, T, 1);
     PyBuffer_Release(&table);
     return out;
+}
+
+static PyObject *py_translate_into(PyObject *self, PyObject *args) {
+    (void)self;
+    PyObject *cap;
+    Py_buffer table, out;
+    int bits = 8;
+    if (!PyArg_ParseTuple(args, "Oy*w*|i", &cap, &table, &out, &bits)) return NULL;
+    Handle *h = (Handle *)PyCapsule_GetPointer(cap, "ga_strings.handle");
+    const char *err = NULL;
+    if (!h) { PyBuffer_Release(&table); PyBuffer_Release(&out); return NULL; }
+    if (table.len != 256) err = "translate_into() needs a 256-byte table";
+    else if (bits != 8 && bits != 4 && bits != 2) err = "bits must be 8, 4 or 2";
+    else if ((int64_t)out.len < (h->off[h->n] * bits + 7) / 8) err = "output buffer too small";
+    if (err) {
+        PyBuffer_Release(&table); PyBuffer_Release(&out);
+        PyErr_SetString(PyExc_ValueError, err);
+        return NULL;
+    }
+    Job jobs[16];
+    const int T = n_threads(h->n);
+    for (int t = 0; t < T; ++t) {
+        jobs[t].table = (const unsigned char *)table.buf;
+        jobs[t].out = (unsigned char *)out.buf;
+        jobs[t].bits = bits;
+    }
+    run_jobs(h, bits == 8 ? translate_job : pack_job, jobs, T, 8 / bits);
+    PyBuffer_Release(&table);
+    PyBuffer_Release(&out);
+    Py_RETURN_NONE;
 }
 
 static PyMethodDef methods[] = {
     {"scan", py_scan, METH_O, "scan(list[str]) -> (handle, total, lengths int64 bytes, seen[256]) | None"},
     {"translate", py_translate, METH_VARARGS, "translate(handle, table256) -> bytes"},
+    {"translate_into", py_translate_into, METH_VARARGS,
+     "translate_into(handle, table256, writable buffer, bits=8): letters (bits = 8) or packed 4-/2-bit letter streams"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_strings", "string-list lowering for globalign_b200", -1,

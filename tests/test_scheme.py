@@ -242,3 +242,39 @@ def test_fastq_pair_reader(tmp_path):
         batch.read_pairs_from_fastq(odd)
     with pytest.raises(RuntimeError):
         batch.read_pairs_from_fastq(one, odd)
+
+
+def test_native_lowering_equals_python_lowering():
+    """batch._lower_native (csrc/ga_strings.c: threaded header pass, occurrence scan and translation
+    straight into a caller-owned buffer) must give the letters, offsets and alphabet of the Python
+    lowering -- as bytes and as the C-ABI's packed 2-bit / 4-bit letter streams -- and must leave
+    every error case to the paths that raise the reference's message."""
+    import numpy as np
+    from globalign_b200 import batch
+
+    sch = batch.Scheme(match_score=2, mismatch_score=-3, gap_open_score=-10, gap_extension_score=-1)
+    rng = random.Random(11)
+    for letters, want_bits in (("ACGTacgt", 2), ("ACGTNacgtnRY", 4), ("ACDEFGHIKLMNPQRSTVWY", 8)):
+        # > 4096 sequences: the threaded code paths; lengths 1..37: sequences sharing packed bytes
+        s1 = ["".join(rng.choice(letters) for _ in range(rng.randint(1, 37))) for _ in range(9000)]
+        s2 = ["".join(rng.choice(letters) for _ in range(rng.randint(1, 37))) for _ in range(9000)]
+        ref = batch._lower_ascii_batch(s1, s2, start.MAX_SEQ_LEN_PRODUCT, sch)
+        for pack in (False, True):
+            out = batch._lower_native(s1, s2, start.MAX_SEQ_LEN_PRODUCT, sch, pack=pack)
+            assert out is not None
+            bits = out[-1]
+            assert bits == (want_bits if pack else 8)
+            assert out[2].letters == ref[2].letters and out[2].sub.tolist() == ref[2].sub.tolist()
+            assert out[4].tolist() == ref[4].tolist() and out[6].tolist() == ref[6].tolist()
+            assert list(out[0][:50]) == list(ref[0][:50]) and list(out[1][:50]) == list(ref[1][:50])
+            for cat, off, rcat in ((out[3], out[4], ref[3]), (out[5], out[6], ref[5])):
+                total = int(off[-1])
+                at = np.arange(total)
+                per = 8 // bits
+                got = (cat[at // per] >> ((at % per) * bits).astype(np.uint8)) & ((1 << bits) - 1) if bits < 8 else cat[:total]
+                assert np.array_equal(got, rcat[:total])
+                for k in (0, 1, 4567, 8999):
+                    assert np.array_equal(batch._letters_of(cat, off, k, bits), rcat[off[k]:off[k + 1]])
+    # anything unusual is left to the other paths
+    for a, b in ((["AC-T"], ["ACGT"]), ([""], ["A"]), (["ACGé"], ["ACG"]), (["A" * 5000], ["C" * 5000]), (("AC",), ("AC",))):
+        assert batch._lower_native(a, b, start.MAX_SEQ_LEN_PRODUCT, sch) is None
