@@ -33,6 +33,30 @@ def test_library_is_sm100a_only(built):
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
 
 
+def test_long_fill_kernel_uses_the_tma_engine_and_the_fused_integer_minima(built):
+    """What DESIGN.md says about the long-pair fill, read back from the SASS of the built library: the
+    sequence tiles arrive by TMA bulk copy (UBLKCP) with mbarrier completion (SYNCS), the cell update
+    is VIADDMNMX / VIMNMX3, and the kernel holds no non-reconvergent convergence barrier -- the kind
+    the assembler puts around a per-lane spin loop, behind which a warp was found to stay split
+    (every spin loop of this kernel is warp-uniform)."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", str(_native.LIB_PATH)], capture_output=True, text=True).stdout
+    kernels, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            kernels[cur] = []
+        elif cur is not None:
+            kernels[cur].append(line)
+    fills = {k: "\n".join(v) for k, v in kernels.items() if "long_fill_kernel" in k}
+    assert len(fills) >= 3, sorted(kernels)[:5]            # MODE 0, 1, 2
+    for name, text in fills.items():
+        for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "VIADDMNMX", "VIMNMX3", "SHFL.UP"):
+            assert mnemonic in text, (name, mnemonic)
+        plain = [ln for ln in text.splitlines() if "BSSY" in ln and "RECONVERGENT" not in ln]
+        assert not plain, (name, plain[:3])
+
+
 def test_no_cpu_fallback():
     import ctypes as C
     n = C.c_int(0)
