@@ -136,7 +136,20 @@ struct ChunkEvents {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    void *raw = nullptr;     // what cudaMalloc returned (== p unless guard bands are on)
+    size_t req = 0;          // guard mode: bytes of the last request (the rear band starts there)
 };
+
+// GA_DEBUG_GUARD=1 (tests): every scratch buffer of a context is allocated at exactly the requested
+// size between two bands of GUARD_BYTES filled with a pattern, and the bands are checked after
+// every call (guard_check) -- compute-sanitizer is not available on the GPU pool, this catches a
+// kernel writing past either end of any internal buffer.
+constexpr size_t GUARD_BYTES = 4096;
+constexpr int GUARD_PATTERN = 0xC5;
+static bool guard_mode() {
+    static const bool on = getenv("GA_DEBUG_GUARD") != nullptr && atoi(getenv("GA_DEBUG_GUARD")) != 0;
+    return on;
+}
 
 struct ga_ctx {
     int device = 0;
@@ -238,13 +251,61 @@ static int fail(ga_ctx *c, int code, const char *fmt, ...) {
     } while (0)
 
 static int ensure(ga_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (guard_mode()) {
+        const size_t want = (std::max(bytes, (size_t)16) + 15) & ~(size_t)15;
+        if (want == b.req && b.p) return GA_OK;
+        if (b.raw) CK(cudaFree(b.raw));
+        b = DevBuf{};
+        CK(cudaMalloc(&b.raw, want + 2 * GUARD_BYTES));
+        CK(cudaMemset(b.raw, GUARD_PATTERN, GUARD_BYTES));
+        CK(cudaMemset((uint8_t *)b.raw + GUARD_BYTES + want, GUARD_PATTERN, GUARD_BYTES));
+        b.p = (uint8_t *)b.raw + GUARD_BYTES;
+        b.cap = b.req = want;
+        // GA_DEBUG_GUARD=2: self-test -- plant one stray byte behind the buffer; the next check must report it
+        if (atoi(getenv("GA_DEBUG_GUARD")) == 2) CK(cudaMemset((uint8_t *)b.p + want, 0, 1));
+        return GA_OK;
+    }
     if (bytes <= b.cap) return GA_OK;
-    if (b.p) CK(cudaFree(b.p));
-    b.p = nullptr;
-    b.cap = 0;
+    if (b.raw) CK(cudaFree(b.raw));
+    b = DevBuf{};
     const size_t want = std::max(bytes, (size_t)256);
-    CK(cudaMalloc(&b.p, want));
+    CK(cudaMalloc(&b.raw, want));
+    b.p = b.raw;
     b.cap = want;
+    return GA_OK;
+}
+
+static std::vector<std::pair<const char *, DevBuf *>> all_buffers(ga_ctx *ctx);
+
+__global__ void guard_scan_kernel(const uint8_t *front, const uint8_t *rear, int n, int which, int *fault) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (front[k] != (uint8_t)GUARD_PATTERN) atomicCAS(fault, 0, 2 * which + 1);
+    if (rear[k] != (uint8_t)GUARD_PATTERN) atomicCAS(fault, 0, 2 * which + 2);
+}
+
+static int guard_check(ga_ctx *ctx);
+static inline int guarded(ga_ctx *ctx, int rc) { return rc == GA_OK ? guard_check(ctx) : rc; }
+
+// after a call has finished on the device: are all guard bands intact?
+static int guard_check(ga_ctx *ctx) {
+    if (!guard_mode()) return GA_OK;
+    CK(cudaDeviceSynchronize());
+    int *d_fault = nullptr, fault = 0;
+    CK(cudaMalloc(&d_fault, sizeof(int)));
+    CK(cudaMemset(d_fault, 0, sizeof(int)));
+    const auto bufs = all_buffers(ctx);
+    for (size_t k = 0; k < bufs.size(); ++k) {
+        const DevBuf *b = bufs[k].second;
+        if (!b->raw) continue;
+        guard_scan_kernel<<<(int)(GUARD_BYTES / 256), 256>>>((const uint8_t *)b->raw, (const uint8_t *)b->p + b->req,
+                                                            (int)GUARD_BYTES, (int)k, d_fault);
+    }
+    CK(cudaMemcpy(&fault, d_fault, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_fault);
+    if (fault)
+        return fail(ctx, GA_E_CUDA, "GA_DEBUG_GUARD: a kernel wrote %s scratch buffer %s", (fault & 1) ? "in front of" : "behind",
+                    bufs[(size_t)((fault - 1) / 2)].first);
     return GA_OK;
 }
 
@@ -286,19 +347,61 @@ extern "C" int ga_ctx_create(int device, ga_ctx **out) {
     return GA_OK;
 }
 
+static std::vector<std::pair<const char *, DevBuf *>> all_buffers(ga_ctx *ctx) {
+    return {
+        {"d_sub4", &ctx->d_sub4},
+        {"d_gh4t", &ctx->d_gh4t},
+        {"d_gv4t", &ctx->d_gv4t},
+        {"d_gvraw", &ctx->d_gvraw},
+        {"d_ghraw", &ctx->d_ghraw},
+        {"d_tiles", &ctx->d_tiles},
+        {"d_perm", &ctx->d_perm},
+        {"d_codes[0]", &ctx->d_codes[0]},
+        {"d_codes[1]", &ctx->d_codes[1]},
+        {"d_bnd[0]", &ctx->d_bnd[0]},
+        {"d_bnd[1]", &ctx->d_bnd[1]},
+        {"d_counter", &ctx->d_counter},
+        {"d_s1", &ctx->d_s1},
+        {"d_s2", &ctx->d_s2},
+        {"d_off1", &ctx->d_off1},
+        {"d_off2", &ctx->d_off2},
+        {"d_cost", &ctx->d_cost},
+        {"d_ops", &ctx->d_ops},
+        {"d_opsoff", &ctx->d_opsoff},
+        {"d_len", &ctx->d_len},
+        {"d_status", &ctx->d_status},
+        {"l_colsum", &ctx->l_colsum},
+        {"l_rowsum", &ctx->l_rowsum},
+        {"l_brow", &ctx->l_brow},
+        {"l_vchk", &ctx->l_vchk},
+        {"l_prog", &ctx->l_prog},
+        {"l_misc", &ctx->l_misc},
+        {"l_xrow", &ctx->l_xrow},
+        {"l_meta", &ctx->l_meta},
+        {"l_seg", &ctx->l_seg},
+        {"v_s1", &ctx->v_s1},
+        {"v_s2", &ctx->v_s2},
+        {"v_tab", &ctx->v_tab},
+        {"v_draws", &ctx->v_draws},
+        {"v_ops", &ctx->v_ops},
+        {"v_misc", &ctx->v_misc},
+        {"r_rle", &ctx->r_rle},
+        {"r_len", &ctx->r_len},
+        {"r_rel", &ctx->r_rel},
+        {"r_off", &ctx->r_off},
+        {"r_res", &ctx->r_res},
+        {"r_base", &ctx->r_base},
+        {"r_tmp", &ctx->r_tmp},
+        {"r_flag", &ctx->r_flag},
+    };
+}
+
 extern "C" int ga_ctx_destroy(ga_ctx *ctx) {
     if (!ctx) return GA_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->d_sub4, &ctx->d_gh4t, &ctx->d_gv4t, &ctx->d_gvraw, &ctx->d_ghraw,
-                      &ctx->d_tiles, &ctx->d_perm, &ctx->d_codes[0], &ctx->d_codes[1], &ctx->d_bnd[0], &ctx->d_bnd[1],
-                      &ctx->d_counter, &ctx->d_s1,
-                      &ctx->d_s2, &ctx->d_off1, &ctx->d_off2, &ctx->d_cost, &ctx->d_ops,
-                      &ctx->d_opsoff, &ctx->d_len, &ctx->d_status, &ctx->l_colsum, &ctx->l_rowsum,
-                      &ctx->l_brow, &ctx->l_vchk, &ctx->l_prog, &ctx->l_misc, &ctx->l_xrow, &ctx->l_meta,
-                      &ctx->l_seg, &ctx->v_s1, &ctx->v_s2, &ctx->v_tab, &ctx->v_draws, &ctx->v_ops, &ctx->v_misc,
-                      &ctx->r_rle, &ctx->r_len, &ctx->r_rel, &ctx->r_off, &ctx->r_res, &ctx->r_base, &ctx->r_tmp, &ctx->r_flag})
-        if (b->p) cudaFree(b->p);
+    for (auto &nb : all_buffers(ctx))
+        if (nb.second->raw) cudaFree(nb.second->raw);
     if (ctx->h_base) cudaFreeHost(ctx->h_base);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->in_piece) if (e) cudaEventDestroy(e);
@@ -330,7 +433,7 @@ extern "C" int ga_sync(ga_ctx *ctx) {
     if (!ctx) return GA_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    return GA_OK;
+    return guard_check(ctx);
 }
 
 // ------------------------------------------------------------------ scheme
@@ -1243,8 +1346,8 @@ extern "C" int ga_align_batch_rle(ga_ctx *ctx, const uint8_t *s1, const int64_t 
         return fail(ctx, GA_E_ARG, "null host buffer");
     if (!s1_off && (m < 1 || n < 1)) return fail(ctx, GA_E_ARG, "fixed-length form needs m >= 1 and n >= 1");
     const RleOut ro{reinterpret_cast<PairResult *>(out_res), out_rle, rle_capacity, out_rle_off};
-    return align_batch_impl(ctx, s1, s1_off, s2, s2_off, s1_off ? 0 : m, s1_off ? 0 : n, n_pairs, nullptr, nullptr,
-                            nullptr, nullptr, nullptr, flags, &ro);
+    return guarded(ctx, align_batch_impl(ctx, s1, s1_off, s2, s2_off, s1_off ? 0 : m, s1_off ? 0 : n, n_pairs, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, flags, &ro));
 }
 
 extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_off,
@@ -1256,8 +1359,8 @@ extern "C" int ga_align_batch(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_
     if (!s1 || !s2 || !s1_off || !s2_off || !out_cost ||
         (!cost_only && (!out_ops || !out_ops_off || !out_ops_len || !out_status)))
         return fail(ctx, GA_E_ARG, "null host buffer");
-    return align_batch_impl(ctx, s1, s1_off, s2, s2_off, 0, 0, n_pairs, out_cost, out_ops, out_ops_off,
-                            out_ops_len, out_status, flags);
+    return guarded(ctx, align_batch_impl(ctx, s1, s1_off, s2, s2_off, 0, 0, n_pairs, out_cost, out_ops, out_ops_off,
+                            out_ops_len, out_status, flags));
 }
 
 extern "C" int ga_align_batch_uniform(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
@@ -1267,8 +1370,8 @@ extern "C" int ga_align_batch_uniform(ga_ctx *ctx, const uint8_t *s1, int64_t m,
     const bool cost_only = (flags & GA_F_COST_ONLY) != 0;
     if (!s1 || !s2 || !out_cost || m < 1 || n < 1 || (!cost_only && (!out_ops || !out_ops_len || !out_status)))
         return fail(ctx, GA_E_ARG, "null host buffer or empty sequences");
-    return align_batch_impl(ctx, s1, nullptr, s2, nullptr, m, n, n_pairs, out_cost, out_ops, nullptr,
-                            out_ops_len, out_status, flags);
+    return guarded(ctx, align_batch_impl(ctx, s1, nullptr, s2, nullptr, m, n, n_pairs, out_cost, out_ops, nullptr,
+                            out_ops_len, out_status, flags));
 }
 
 // ------------------------------------------------------------------ one long pair
@@ -1466,7 +1569,7 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
         info->checkpoint_bytes = (int64_t)(brow_b + vchk_b);
         info->cells = m * n;
     }
-    return GA_OK;
+    return guard_check(ctx);
 }
 
 // ------------------------------------------------------------------ full value table (kernels: ga_values.cuh)
@@ -1566,8 +1669,8 @@ extern "C" int ga_align_replay(ga_ctx *ctx, const uint8_t *s1, int64_t m, const 
         if (big + (m + n + 2) * (long long)ctx->sc.max_cost + 3LL * ctx->sc.o >= 0x7fffffffLL)
             return fail(ctx, GA_E_RANGE, "costs could overflow int32 for these lengths");
     }
-    return replay_impl(ctx, s1, m, s2, n, nullptr, draws, n_draws, out_cost, out_ops, out_n_ops, out_n_eval,
-                       out_status);
+    return guarded(ctx, replay_impl(ctx, s1, m, s2, n, nullptr, draws, n_draws, out_cost, out_ops, out_n_ops, out_n_eval,
+                       out_status));
 }
 
 extern "C" int ga_walk_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const uint8_t *s2, int64_t n,
@@ -1578,8 +1681,8 @@ extern "C" int ga_walk_values(ga_ctx *ctx, const uint8_t *s1, int64_t m, const u
     if (!s1 || !s2 || !table || !out_cost || !out_ops || !out_n_ops || !out_n_eval || !out_status || m < 1 ||
         n < 1 || (draws && n_draws < m + n) || (m + 1) * (n + 1) > (int64_t)60'000'000)
         return fail(ctx, GA_E_ARG, "ga_walk_values: single pairs up to 6e7 table cells, m+n draws or none");
-    return replay_impl(ctx, s1, m, s2, n, table, draws, n_draws, out_cost, out_ops, out_n_ops, out_n_eval,
-                       out_status);
+    return guarded(ctx, replay_impl(ctx, s1, m, s2, n, table, draws, n_draws, out_cost, out_ops, out_n_ops, out_n_eval,
+                       out_status));
 }
 
 // ------------------------------------------------------------------ float-valued penalties (f64)

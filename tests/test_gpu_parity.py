@@ -945,3 +945,26 @@ def test_integration_md_ctypes_stub_runs_as_written():
         ref = find_global_alignment(**kw)
         got = gpu_dp(s1, s2, ref.costing_mat, ref.gap_open_cost)
         assert list(got) == rec["out"][:4]
+
+
+@pytest.mark.gpu
+def test_guard_band_mode_detects_a_stray_write_and_passes_a_clean_run():
+    """GA_DEBUG_GUARD=1 puts every scratch buffer of a context between two pattern-filled bands and
+    checks them after each call (compute-sanitizer is not available on the pool).  A clean batch
+    passes; with GA_DEBUG_GUARD=2 the library plants one stray byte behind a buffer and the same
+    call must fail with the guard's message."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    code = (
+        "import numpy as np\n"
+        "from globalign_b200 import batch\n"
+        "r = batch.find_global_alignments(['ACGTACGTAC', 'TTTT'], ['ACGTTCGTAC', 'TTAT'])\n"
+        "print('costs', r.cost.tolist())\n")
+    root = str(Path(__file__).resolve().parents[1])
+    outs = {}
+    for mode in ("1", "2"):
+        env = dict(os.environ, GA_DEBUG_GUARD=mode, PYTHONPATH=root)
+        outs[mode] = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
+    assert outs["1"].returncode == 0 and "costs" in outs["1"].stdout, outs["1"].stderr[-500:]
+    assert outs["2"].returncode != 0 and "GA_DEBUG_GUARD" in outs["2"].stderr, outs["2"].stderr[-500:]
