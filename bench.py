@@ -589,7 +589,7 @@ def bench_batched(env, name, per_rank, steps, warmup, *, scaling="weak", first_r
                                       _native.unpack_ops(keep["ops"], int(keep["off"][k]), int(keep["len"][k]))), k
         return dt_s, h2d_bytes, ctx.timing(), int(res.nbytes + roff.nbytes + int(roff[-1]))
 
-    seq_bits = 2 if len(dense.letters) <= 4 else (4 if len(dense.letters) <= 16 else 8)
+    seq_bits = 2 if len(dense.letters) <= 4 else (4 if len(dense.letters) <= 16 else (5 if len(dense.letters) <= 32 else 8))
     e2e_fixed = time_e2e(seq_bits, fixed)
     e2e_s, h2d, e2e_phase, d2h_rle = time_e2e_rle(seq_bits)
     e2e_offsets = time_e2e(seq_bits, False) if (fixed and e2e_variants) else e2e_fixed

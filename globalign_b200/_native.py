@@ -25,6 +25,7 @@ GA_F_COST_ONLY = 2
 GA_F_SERIAL = 4
 GA_F_SEQ_4BIT = 8
 GA_F_SEQ_2BIT = 16
+GA_F_SEQ_5BIT = 64
 GA_F_KEEP_ORDER = 32
 T_H2D, T_FILL, T_WALK, T_D2H, T_TOTAL, T_COUNT = 0, 1, 2, 3, 4, 5
 
@@ -381,10 +382,21 @@ class Context:
 
 
 def pack_letters(codes: np.ndarray, bits: int) -> np.ndarray:
-    """uint8 letter indices -> little-endian `bits`-bit stream (bits = 2 or 4), the layout
-    GA_F_SEQ_2BIT / GA_F_SEQ_4BIT expect (letter k in bits [k*bits, (k+1)*bits))."""
+    """uint8 letter indices -> little-endian `bits`-bit stream (bits = 2, 4 or 5), the layout
+    GA_F_SEQ_2BIT / GA_F_SEQ_4BIT / GA_F_SEQ_5BIT expect (letter k in bits [k*bits, (k+1)*bits))."""
     if bits == 8:
         return np.ascontiguousarray(codes, dtype=np.uint8)
+    if bits == 5:                      # 8 letters -> 5 bytes
+        n = len(codes)
+        padded = np.zeros(-(-n // 8) * 8, dtype=np.uint64)
+        padded[:n] = codes
+        word = np.zeros(len(padded) // 8, dtype=np.uint64)
+        for k in range(8):
+            word |= padded[k::8] << np.uint64(5 * k)
+        out = np.zeros((len(word), 5), dtype=np.uint8)
+        for b in range(5):
+            out[:, b] = (word >> np.uint64(8 * b)) & np.uint64(0xFF)
+        return out.reshape(-1)[: (n * 5 + 7) // 8 + 1]
     per = 8 // bits
     n = len(codes)
     padded = np.zeros(-(-n // per) * per, dtype=np.uint8)
@@ -397,7 +409,7 @@ def pack_letters(codes: np.ndarray, bits: int) -> np.ndarray:
 
 
 def seq_flag(bits: int) -> int:
-    return {8: 0, 4: GA_F_SEQ_4BIT, 2: GA_F_SEQ_2BIT}[bits]
+    return {8: 0, 5: GA_F_SEQ_5BIT, 4: GA_F_SEQ_4BIT, 2: GA_F_SEQ_2BIT}[bits]
 
 
 def ops_offsets(off1, off2) -> np.ndarray:

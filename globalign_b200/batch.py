@@ -198,18 +198,18 @@ def _letters_of(cat: np.ndarray, off: np.ndarray, k: int, bits: int) -> np.ndarr
     lo, hi = int(off[k]), int(off[k + 1])
     if bits == 8:
         return cat[lo:hi]
-    per = 8 // bits
-    at = np.arange(lo, hi)
-    return (cat[at // per] >> ((at % per) * bits).astype(np.uint8)) & ((1 << bits) - 1)
+    bit = np.arange(lo, hi, dtype=np.int64) * bits
+    two = cat[bit >> 3].astype(np.uint16) | (cat[np.minimum((bit >> 3) + 1, len(cat) - 1)].astype(np.uint16) << 8)
+    return ((two >> (bit & 7).astype(np.uint16)) & ((1 << bits) - 1)).astype(np.uint8)
 
 
 def _lower_native(seqs_1, seqs_2, limit, scheme, pack=False):
     """The all-ASCII case through the `_strings` extension (csrc/ga_strings.c): threaded passes
     over the strings' own buffers -- headers, which byte values occur, then every letter mapped
     through one 256-entry table (case folding + letter -> index) straight into page-locked
-    memory -- instead of join / encode / translate in Python.  `pack`: alphabets of up to 4 / 16
-    letters are written as the C-ABI's 2-bit / 4-bit letter streams (a quarter / half of the
-    upload).  -> (..., bits) or None when the extension is not built, the inputs are not lists of
+    memory -- instead of join / encode / translate in Python.  `pack`: alphabets of up to 4 / 16 /
+    32 letters are written as the C-ABI's 2- / 4- / 5-bit letter streams (a quarter / half / five
+    eighths of the upload).  -> (..., bits) or None when the extension is not built, the inputs are not lists of
     ASCII str, or anything needs the per-pair path's exact error."""
     try:
         from . import _strings
@@ -239,7 +239,7 @@ def _lower_native(seqs_1, seqs_2, limit, scheme, pack=False):
     table = bytes(table)
     bits = 8
     if pack:
-        bits = 2 if dense.A <= 4 else 4 if dense.A <= 16 else 8
+        bits = 2 if dense.A <= 4 else 4 if dense.A <= 16 else 5 if dense.A <= 32 else 8
     cat1 = _pinned_bytes("s1", (_t1 * bits + 7) // 8 + 16)
     cat2 = _pinned_bytes("s2", (_t2 * bits + 7) // 8 + 16)
     _strings.translate_into(h1, table, cat1, bits)
@@ -349,7 +349,7 @@ def find_global_alignments(seqs_1, seqs_2, *, device: int = 0, devices=None, max
     if lowered is None:
         lowered = _lower_batch(seqs_1, seqs_2, limit, scheme)
     up1, up2, dense, cat1, off1, cat2, off2 = lowered
-    seq_flags = {8: 0, 4: _native.GA_F_SEQ_4BIT, 2: _native.GA_F_SEQ_2BIT}[bits]
+    seq_flags = _native.seq_flag(bits)
     def on_device(dev, c1, o1, c2, o2):
         """-> (cost, rle, rle_off, ops_len, status): the compact result stream of one GPU."""
         ctx = _native.default_context(dev)

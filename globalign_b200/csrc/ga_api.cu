@@ -593,6 +593,13 @@ static size_t fill_smem_bytes(const ga_ctx *ctx, const KernelCfg *cfg, int maxN)
 static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off, int64_t n_pairs,
                        uint32_t flags, int maxM, int maxN, int minM, int minN, int64_t cells, HostTimer &ht);
 
+// bits per input letter named by the flags (-1: more than one packing flag)
+static int seq_bits_of(uint32_t flags) {
+    const int n = ((flags & GA_F_SEQ_2BIT) != 0) + ((flags & GA_F_SEQ_4BIT) != 0) + ((flags & GA_F_SEQ_5BIT) != 0);
+    if (n > 1) return -1;
+    return (flags & GA_F_SEQ_2BIT) ? 2 : (flags & GA_F_SEQ_4BIT) ? 4 : (flags & GA_F_SEQ_5BIT) ? 5 : 8;
+}
+
 extern "C" int ga_plan_batch(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off,
                              int64_t n_pairs, const int64_t *out_ops_off, uint32_t flags) {
     if (!ctx) return GA_E_ARG;
@@ -667,8 +674,8 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
     for (float &v : ctx->ms) v = 0.f;
     ctx->timing_valid = false;          // the chunk events now belong to a plan that has not run
     {
-        const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
-        if ((flags & GA_F_SEQ_2BIT) && (flags & GA_F_SEQ_4BIT)) return fail(ctx, GA_E_ARG, "choose one sequence packing");
+        const int bits = seq_bits_of(flags);
+        if (bits < 0) return fail(ctx, GA_E_ARG, "choose one sequence packing");
         if (ctx->sc.A > (1 << bits)) return fail(ctx, GA_E_ARG, "alphabet of %d letters does not fit %d-bit packed sequences", ctx->sc.A, bits);
         ctx->sc.seq_bits = bits;
         const char *e = getenv("GA_CODE_PAIRS");
@@ -1225,7 +1232,8 @@ static int align_batch_impl(ga_ctx *ctx, const uint8_t *s1, const int64_t *s1_of
     const int64_t t1 = implicit ? um * n_pairs : s1_off[n_pairs], t2 = implicit ? un * n_pairs : s2_off[n_pairs];
     if (t1 < n_pairs || t2 < n_pairs || (!implicit && (s1_off[0] != 0 || s2_off[0] != 0)))
         return fail(ctx, GA_E_ARG, "offset arrays must start at 0 and be increasing");
-    const int bits = (flags & GA_F_SEQ_2BIT) ? 2 : ((flags & GA_F_SEQ_4BIT) ? 4 : 8);
+    const int bits = seq_bits_of(flags);
+    if (bits < 0) return fail(ctx, GA_E_ARG, "choose one sequence packing");
     const size_t b1 = (size_t)((t1 * bits + 7) / 8), b2 = (size_t)((t2 * bits + 7) / 8);
     const size_t offb = (size_t)(n_pairs + 1) * 8;
     const int64_t ops_stride = ((((um + un) + 3) / 4) + 3) & ~(int64_t)3;

@@ -48,7 +48,7 @@ struct SchemeDev {
     // the cell update (profiles/README.md), the FMA pipe would otherwise idle.
     unsigned k_one, k_four, k_minus_one;
     int code_pairs;      // direction-code layout: 1 = two consecutive 2-step blocks of a lane per 32-byte sector
-    int seq_bits;        // letters per input byte: 8 (one letter per byte), 4 or 2 (bit-packed stream)
+    int seq_bits;        // bits per input letter: 8 (one letter per byte), 5, 4 or 2 (bit-packed stream)
 };
 
 struct TileDesc {
@@ -58,12 +58,15 @@ struct TileDesc {
     int M, N;            // longest seq_1 / seq_2 in the tile
 };
 
-// Letter k of a sequence buffer.  seq_bits = 8: one letter per byte.  4 / 2: the letters form a
-// little-endian bit stream (letter k in bits [k*bits, (k+1)*bits) of the byte array), the usual
-// packed nucleotide layouts; offsets stay in letters.
+// Letter k of a sequence buffer.  seq_bits = 8: one letter per byte.  5 / 4 / 2: the letters form
+// a little-endian bit stream (letter k in bits [k*bits, (k+1)*bits) of the byte array) -- the usual
+// packed nucleotide layouts, and 5 bits for amino acids; offsets stay in letters.  A 5-bit letter
+// may straddle two bytes (the buffers carry slack behind their last byte).
 __device__ __forceinline__ unsigned ld_letter(const uint8_t *__restrict__ s, long long k, int bits) {
     const long long bit = k * bits;
-    return ((unsigned)s[bit >> 3] >> (unsigned)(bit & 7)) & ((1u << bits) - 1u);
+    unsigned v = (unsigned)s[bit >> 3];
+    if (bits == 5) v |= (unsigned)s[(bit >> 3) + 1] << 8;
+    return (v >> (unsigned)(bit & 7)) & ((1u << bits) - 1u);
 }
 
 // When every pair of a chunk has the same (m, n) the tile descriptors are arithmetic and are

@@ -14,8 +14,8 @@
  *   translate_into(handle, t, buffer, bits)
  *                         -> None: the same into a writable buffer the caller owns (pinned host
  *                            memory: no page faults, and the upload is a plain DMA), one byte per
- *                            letter (bits = 8) or as the C-ABI's 2-bit / 4-bit little-endian
- *                            letter streams (GA_F_SEQ_2BIT / GA_F_SEQ_4BIT, include/globalign_b200.h)
+ *                            letter (bits = 8) or as the C-ABI's 2- / 4- / 5-bit little-endian
+ *                            letter streams (GA_F_SEQ_2BIT / _4BIT / _5BIT, include/globalign_b200.h)
  *
  * The strings of a million read pairs are two million separate heap objects: even reading their
  * headers (type, kind, length, data pointer) is a cache miss each, so that pass is threaded too.
@@ -56,7 +56,7 @@ typedef struct {
     PyObject **items;        /* header pass: the list's items */
     int64_t *lens;
     int bad;                 /* header pass: an item is not a compact ASCII str */
-    int bits;                /* translate_into: 8, 4 or 2 */
+    int bits;                /* translate_into: 8, 5, 4 or 2 */
 } Job;
 
 /* type, kind, length and data pointer of every string of [lo, hi): reads object headers only (no
@@ -102,6 +102,44 @@ static void *pack_job(void *arg) {
             unsigned v = 0;
             for (int f = 0; at < end; ++at, ++f) v |= (unsigned)t[*p++] << (f * bits);
             *o = (unsigned char)v;
+        }
+    }
+    return NULL;
+}
+
+/* 5-bit fields (amino acids): letter k in bits [5k, 5k + 5), so a letter may straddle two bytes and
+ * eight letters fill five.  Jobs start on multiples of eight letters (run_jobs), i.e. on a byte
+ * boundary; each job zeroes its own bytes first and ORs the letters in. */
+static void *pack5_job(void *arg) {
+    Job *j = (Job *)arg;
+    const unsigned char *t = j->table;
+    if (j->lo >= j->hi) return NULL;
+    {
+        const int64_t b0 = j->h->off[j->lo] * 5 / 8, b1 = (j->h->off[j->hi] * 5 + 7) / 8;
+        memset(j->out + b0, 0, (size_t)(b1 - b0));
+    }
+    for (Py_ssize_t k = j->lo; k < j->hi; ++k) {
+        const unsigned char *p = j->h->ptr[k];
+        int64_t at = j->h->off[k];
+        const int64_t end = j->h->off[k + 1];
+        for (; at < end && (at & 7); ++at) {                    /* head: up to the next 5-byte group */
+            const int64_t bit = at * 5;
+            const unsigned v = (unsigned)t[*p++] << (bit & 7);
+            j->out[bit >> 3] |= (unsigned char)v;
+            if (v >> 8) j->out[(bit >> 3) + 1] |= (unsigned char)(v >> 8);
+        }
+        for (; at + 8 <= end; at += 8, p += 8) {                /* whole groups: 8 letters -> 5 bytes */
+            uint64_t w = 0;
+            for (int f = 0; f < 8; ++f) w |= (uint64_t)t[p[f]] << (5 * f);
+            unsigned char *o = j->out + at * 5 / 8;
+            o[0] = (unsigned char)w; o[1] = (unsigned char)(w >> 8); o[2] = (unsigned char)(w >> 16);
+            o[3] = (unsigned char)(w >> 24); o[4] = (unsigned char)(w >> 32);
+        }
+        for (; at < end; ++at) {                                /* tail */
+            const int64_t bit = at * 5;
+            const unsigned v = (unsigned)t[*p++] << (bit & 7);
+            j->out[bit >> 3] |= (unsigned char)v;
+            if (v >> 8) j->out[(bit >> 3) + 1] |= (unsigned char)(v >> 8);
         }
     }
     return NULL;
@@ -244,7 +282,7 @@ static PyObject *py_translate_into(PyObject *self, PyObject *args) {
     const char *err = NULL;
     if (!h) { PyBuffer_Release(&table); PyBuffer_Release(&out); return NULL; }
     if (table.len != 256) err = "translate_into() needs a 256-byte table";
-    else if (bits != 8 && bits != 4 && bits != 2) err = "bits must be 8, 4 or 2";
+    else if (bits != 8 && bits != 5 && bits != 4 && bits != 2) err = "bits must be 8, 5, 4 or 2";
     else if ((int64_t)out.len < (h->off[h->n] * bits + 7) / 8) err = "output buffer too small";
     if (err) {
         PyBuffer_Release(&table); PyBuffer_Release(&out);
@@ -258,7 +296,8 @@ static PyObject *py_translate_into(PyObject *self, PyObject *args) {
         jobs[t].out = (unsigned char *)out.buf;
         jobs[t].bits = bits;
     }
-    run_jobs(h, bits == 8 ? translate_job : pack_job, jobs, T, 8 / bits);
+    if (bits == 5) run_jobs(h, pack5_job, jobs, T, 8);
+    else run_jobs(h, bits == 8 ? translate_job : pack_job, jobs, T, 8 / bits);
     PyBuffer_Release(&table);
     PyBuffer_Release(&out);
     Py_RETURN_NONE;

@@ -18,9 +18,10 @@
  * Conventions
  *   - Sequences are "lowered": one uint8 letter index (0 .. A-1) per residue,
  *     pairs concatenated, CSR offsets (int64, n_pairs+1 entries, in letters).
- *     With GA_F_SEQ_4BIT / GA_F_SEQ_2BIT (batch entry points) the letter buffers are
- *     little-endian bit streams instead: letter k of the concatenation occupies bits
- *     [k*b, (k+1)*b) of the byte array (b = 4 or 2); offsets stay in letters.
+ *     With GA_F_SEQ_5BIT / GA_F_SEQ_4BIT / GA_F_SEQ_2BIT (batch entry points) the letter buffers
+ *     are little-endian bit streams instead: letter k of the concatenation occupies bits
+ *     [k*b, (k+1)*b) of the byte array (b = 5, 4 or 2; a 5-bit letter may straddle two bytes);
+ *     offsets stay in letters.
  *   - The scheme is a dense costing matrix (ga_set_scheme), exactly the
  *     reference's costing_mat with its "-" row/column split out:
  *         sub[a*A+b] = costing_mat[a][b]
@@ -68,6 +69,7 @@ enum {
     GA_F_SERIAL = 4,          /* one stream, no fill/walk/copy overlap (isolated kernel timing) */
     GA_F_SEQ_4BIT = 8,        /* s1/s2 are 4-bit packed letter streams (alphabet <= 16) */
     GA_F_SEQ_2BIT = 16,       /* s1/s2 are 2-bit packed letter streams (alphabet <= 4) */
+    GA_F_SEQ_5BIT = 64,       /* s1/s2 are 5-bit packed letter streams (alphabet <= 32: amino acids) */
     GA_F_KEEP_ORDER = 32      /* ragged batches: form tiles in the caller's pair order instead of ordering
                                  each chunk's pairs by length first (results are the same either way) */
 };

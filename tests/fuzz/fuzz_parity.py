@@ -114,9 +114,11 @@ def main():
             flags |= _native.GA_F_KEEP_ORDER
         bits = 8
         if A <= 4 and rng.random() < 0.4:
-            bits = rng.choice([2, 4])
+            bits = rng.choice([2, 4, 5])
         elif A <= 16 and rng.random() < 0.3:
-            bits = 4
+            bits = rng.choice([4, 5])
+        elif A <= 32 and rng.random() < 0.3:
+            bits = 5
         flags |= _native.seq_flag(bits)
         ctx.set_scheme(dense)
         ctx.set_scratch_limit(rng.choice([64 << 30, 64 << 30, 32 << 20, 8 << 20]))

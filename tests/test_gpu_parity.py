@@ -488,10 +488,11 @@ def test_fasta_batch_and_batch_writer(tmp_path):
 
 
 # ------------------------------------------------------------------ bit-packed sequence input
-@pytest.mark.parametrize("bits,A", [(2, 4), (4, 4), (4, 13), (2, 3)])
+@pytest.mark.parametrize("bits,A", [(2, 4), (4, 4), (4, 13), (2, 3), (5, 24), (5, 32), (5, 4)])
 def test_packed_sequence_streams_give_identical_results(bits, A):
-    """GA_F_SEQ_2BIT / GA_F_SEQ_4BIT: the same batch as little-endian 2-bit / 4-bit letter
-    streams (what packed nucleotide files hold) must give byte-identical outputs."""
+    """GA_F_SEQ_2BIT / GA_F_SEQ_4BIT / GA_F_SEQ_5BIT: the same batch as little-endian 2- / 4- / 5-bit
+    letter streams (what packed nucleotide files hold; 5 bits for amino acids, letters straddling
+    bytes) must give byte-identical outputs."""
     rng = random.Random(bits * 100 + A)
     ctx = _native.Context(0)
     for dense in (_simple_dense(A, 4, 2, 1, 6), _table_dense(rng, A, 3)):

@@ -254,7 +254,8 @@ def test_native_lowering_equals_python_lowering():
 
     sch = batch.Scheme(match_score=2, mismatch_score=-3, gap_open_score=-10, gap_extension_score=-1)
     rng = random.Random(11)
-    for letters, want_bits in (("ACGTacgt", 2), ("ACGTNacgtnRY", 4), ("ACDEFGHIKLMNPQRSTVWY", 8)):
+    for letters, want_bits in (("ACGTacgt", 2), ("ACGTNacgtnRY", 4), ("ACDEFGHIKLMNPQRSTVWY", 5),
+                               ("ABCDEFGHIJKLMNOPQRSTUVWXYZabc*.0123456", 8)):
         # > 4096 sequences: the threaded code paths; lengths 1..37: sequences sharing packed bytes
         s1 = ["".join(rng.choice(letters) for _ in range(rng.randint(1, 37))) for _ in range(9000)]
         s2 = ["".join(rng.choice(letters) for _ in range(rng.randint(1, 37))) for _ in range(9000)]
@@ -269,10 +270,12 @@ def test_native_lowering_equals_python_lowering():
             assert list(out[0][:50]) == list(ref[0][:50]) and list(out[1][:50]) == list(ref[1][:50])
             for cat, off, rcat in ((out[3], out[4], ref[3]), (out[5], out[6], ref[5])):
                 total = int(off[-1])
-                at = np.arange(total)
-                per = 8 // bits
-                got = (cat[at // per] >> ((at % per) * bits).astype(np.uint8)) & ((1 << bits) - 1) if bits < 8 else cat[:total]
+                bit = np.arange(total, dtype=np.int64) * bits
+                two = cat[bit >> 3].astype(np.uint16) | (cat[(bit >> 3) + 1].astype(np.uint16) << 8)      # (buffers carry 16 bytes of slack)
+                got = ((two >> (bit & 7).astype(np.uint16)) & ((1 << bits) - 1)).astype(np.uint8) if bits < 8 else cat[:total]
                 assert np.array_equal(got, rcat[:total])
+                from globalign_b200 import _native
+                assert np.array_equal(_native.pack_letters(rcat[:total], bits)[: (total * bits + 7) // 8], cat[: (total * bits + 7) // 8])
                 for k in (0, 1, 4567, 8999):
                     assert np.array_equal(batch._letters_of(cat, off, k, bits), rcat[off[k]:off[k + 1]])
     # anything unusual is left to the other paths
