@@ -14,9 +14,17 @@
 //   * Gap-shifted values.  X^(i,j) = 4 * (X(i,j) - GH(j) - GV(i)) with GH / GV the running sums of
 //     the per-letter horizontal / vertical gap-extension costs.  In this domain
 //         d0 = h^(i-1,j-1) + 4*(sub(a,b) - gap_h[b] - gap_v[a])          (one table load + add)
-//         h  = min3(d0, L^(i,j-1), U^(i-1,j))                            VIMNMX3
-//         L^ = min(h + 4o, L^(i,j-1)),  U^ = min(h + 4o, U^(i-1,j))      2 x VIADDMNMX
+//         h  = min3(d0, L^(i,j-1), U^(i-1,j))
+//         L^ = min(h + 4o, L^(i,j-1)),  U^ = min(h + 4o, U^(i-1,j))
 //     -- the two gap-extension additions per cell are gone, and per-letter gap costs cost nothing.
+//     (long_chain evaluates these in an equivalent order that keeps U off the row-to-row
+//     dependency: 3 x VIADDMNMX + 1 x VIMNMX3 per cell.)
+//   * Sequence tiles by TMA.  seq_2 reaches a band in tiles of LTCOLS letters copied by the TMA
+//     engine (cp.async.bulk, mbarrier completion) into two shared-memory slots per warp, two tiles
+//     ahead of the wavefront.
+//   * Every spin loop is warp-uniform (votes): behind a per-lane spin loop the hardware may leave
+//     the warp split for the rest of the band, and a split warp takes the collective slow path of
+//     every shuffle.
 //     L(i,j) = min(D0+o, D1, D2+o) is the level-1 candidate handed to column j+1, U(i,j) =
 //     min(D0+o, D1+o, D2) the level-2 candidate handed to row i+1 (reference cell update,
 //     globaligner.py:331-363).  The shift is the same for the three candidates of a cell, so every
