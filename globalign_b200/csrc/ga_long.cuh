@@ -1030,37 +1030,79 @@ long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
     }
 }
 
-__global__ void long_chain_kernel(const LongArgs a, const ParTrace pt) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// One warp.  The chain is one dependent lookup per band -- X of band b names the column at which
+// the walk enters band b-1 -- and a lone thread pays an L2 round trip for each (0.28 ms for the
+// 521 bands of a 100 kb pair).  The path moves on by about LBAND * n / m columns per band, so the
+// records it will need are predictable: the warp keeps CHAIN_D windows of 32 columns x 3 levels
+// in flight (cp.async into shared memory, issued CHAIN_D bands ahead around the extrapolated
+// column) and the lookup of a band is a shared-memory read; a miss (the path drifted out of the
+// window) falls back to the global load.  All lanes follow the same control flow on the same
+// values; lane 0 writes.
+constexpr int CHAIN_D = 8;
+__global__ void __launch_bounds__(32)
+long_chain_kernel(const LongArgs a, const ParTrace pt) {
+    constexpr int CORR_CAP = 4096;                  // bands whose corridor is kept in shared memory
+    __shared__ int s_win[CHAIN_D][32 * 3];
+    __shared__ int s_base[CHAIN_D], s_band[CHAIN_D];
+    __shared__ int s_corr[2 * CORR_CAP];
+    if (blockIdx.x != 0) return;
     if (pt.run_if && *pt.run_if == 0) return;
+    const int lane = threadIdx.x;
     const int nb = a.nbands;
-    for (int b = 0; b < nb; ++b) pt.entry[b * 4 + 3] = 2;
+    for (int b = lane; b < nb; b += 32) pt.entry[b * 4 + 3] = 2;
+    for (int k = lane; k < 2 * min(nb, CORR_CAP); k += 32) s_corr[k] = pt.corr[k];
+    if (lane < CHAIN_D) s_band[lane] = -1;
+    __syncwarp();
+    auto corr = [&](int band, int k) { return band < CORR_CAP ? s_corr[2 * band + k] : pt.corr[2 * band + k]; };
+    const long long dj = (long long)LBAND * a.n / a.m;          // columns per band along the main diagonal
+    // request the records of band `band` around entry column `col` (index space: column - lo(band))
+    auto request = [&](int band, long long col) {
+        if (band >= 0) {
+            const int slot = band % CHAIN_D;
+            const int lo = corr(band, 0), hi = corr(band, 1);
+            int base = (int)max(0LL, min((long long)(hi - lo) - 31, col - lo - 16));
+            if (base < 0) base = 0;
+            if (lane == 0) { s_base[slot] = base; s_band[slot] = band; }
+            const int idx = base + lane;
+            if (idx <= hi - lo && idx < pt.XW) {
+                const int *src = pt.xrow + ((size_t)band * pt.XW + idx) * 3;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_win[slot][lane * 3]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4u * k), "l"(src + k) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     int b = nb - 1, X = *pt.xlast;
-    int lo_next = nb >= 2 ? pt.corr[2 * (nb - 2)] : 0, hi_next = nb >= 2 ? pt.corr[2 * (nb - 2) + 1] : 0;
     int ei = a.m, ej = a.n, eL = 0;
     long long off = 0;
     bool ok = true;
+    // band nb-1 is looked up through xlast; windows for the CHAIN_D bands below it
+    for (int d = 1; d <= CHAIN_D; ++d) request(nb - 1 - d, (long long)(nb - d) * LBAND * a.n / a.m);     // the diagonal at the band's last row
     for (;;) {
         const int ib = b * LBAND;
-        pt.entry[b * 4 + 0] = ei;
-        pt.entry[b * 4 + 1] = ej;
-        pt.entry[b * 4 + 2] = eL;
-        pt.entry[b * 4 + 3] = 0;
+        if (lane == 0) {
+            pt.entry[b * 4 + 0] = ei;
+            pt.entry[b * 4 + 1] = ej;
+            pt.entry[b * 4 + 2] = eL;
+            pt.entry[b * 4 + 3] = 0;
+        }
         if (X == X_OUT) { ok = false; break; }
         int jx = X < 0 ? 0 : (X >> 2);                 // column at which the walk leaves the band
         long long cap = (long long)(ei - ib) + (ej - jx) + 2;
         if (b == 0 && X >= 0) cap += jx;               // trailing run along row 0
-        pt.seg_off[b] = off;
+        if (lane == 0) pt.seg_off[b] = off;
         off += cap;
-        if (X < 0) {                                   // reached column 0 inside band b: the rest is vertical
-            for (int c = b - 1; c >= 0; --c) {
+        if (X < 0 || (b > 0 && jx == 0)) {             // reached column 0 (inside band b, or exactly on its upper edge): the rest is vertical
+            for (int c = b - 1 - lane; c >= 0; c -= 32) {
                 pt.entry[c * 4 + 0] = (c + 1) * LBAND;
                 pt.entry[c * 4 + 1] = 0;
                 pt.entry[c * 4 + 2] = 2;
                 pt.entry[c * 4 + 3] = 1;
-                pt.seg_off[c] = off;
-                off += LBAND;
+                pt.seg_off[c] = off + (long long)(b - 1 - c) * LBAND;
             }
+            off += (long long)b * LBAND;
             break;
         }
         if (b == 0) break;
@@ -1068,24 +1110,21 @@ __global__ void long_chain_kernel(const LongArgs a, const ParTrace pt) {
         ei = (b + 1) * LBAND;
         ej = jx;
         eL = X & 3;
-        if (ej == 0) {                                 // crossed exactly into column 0
-            for (int c = b; c >= 0; --c) {
-                pt.entry[c * 4 + 0] = (c + 1) * LBAND;
-                pt.entry[c * 4 + 1] = 0;
-                pt.entry[c * 4 + 2] = 2;
-                pt.entry[c * 4 + 3] = 1;
-                pt.seg_off[c] = off;
-                off += LBAND;
-            }
-            break;
-        }
-        const int lo = lo_next, hi = hi_next;          // corridor of band b, requested an iteration ago
-        if (b > 0) { lo_next = pt.corr[2 * (b - 1)]; hi_next = pt.corr[2 * (b - 1) + 1]; }
+        // the window of band b was requested CHAIN_D iterations ago: everything but the newest CHAIN_D - 1 groups has landed
+        asm volatile("cp.async.wait_group %0;" :: "n"(CHAIN_D - 1) : "memory");
+        __syncwarp();
+        const int slot = b % CHAIN_D;
+        const int lo = corr(b, 0), hi = corr(b, 1);
         if (!(ej > lo && ej <= hi)) { ok = false; break; }
-        X = pt.xrow[((size_t)b * pt.XW + (ej - lo)) * 3 + eL];
+        const int idx = ej - lo, base = s_base[slot];
+        if (s_band[slot] == b && idx >= base && idx < base + 32) X = s_win[slot][(idx - base) * 3 + eL];
+        else X = pt.xrow[((size_t)b * pt.XW + idx) * 3 + eL];
+        __syncwarp();                                   // the slot is read before it is given to band b - CHAIN_D
+        request(b - CHAIN_D, (long long)ej - (long long)CHAIN_D * dj);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (off > pt.seg_cap) ok = false;
-    *pt.failed = ok ? 0 : 1;
+    if (lane == 0) *pt.failed = ok ? 0 : 1;
 }
 
 template <bool SIMPLE>
