@@ -919,6 +919,12 @@ __host__ __device__ inline void long_corridor(int band, int m, int n, int W, int
     hi = (int)c1;
 }
 
+__device__ __forceinline__ int selp_s32(bool p, int a, int b) {
+    int r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tselp.s32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((int)p));
+    return r;
+}
+
 template <bool SIMPLE>
 __global__ void __launch_bounds__(32 * LWARPS)
 long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
@@ -998,10 +1004,12 @@ long_xprop_kernel(const SchemeDev sc, const LongArgs a, const ParTrace pt) {
                 const unsigned hq = (unsigned)__vimin3_s32((int)d0, (int)d1, (int)d2);
                 const unsigned Lq = (unsigned)__viaddmin_s32((int)hq, (int)k.o4, (int)d1);
                 const unsigned Uq = (unsigned)__viaddmin_s32((int)hq, (int)k.o4, (int)d2);
+                // (selp, not ?: -- the compiler turned the nested conditional into a divergent branch
+                // per select, seven reconvergence points per row)
                 const unsigned c0 = hq & 3u;
-                const int X0 = c0 == 0u ? xdiag : (c0 == 1u ? x1[r] : xup);
-                const int X1 = (Lq & 1u) ? x1[r] : X0;
-                const int X2 = (Uq & 2u) ? xup : X0;
+                const int X0 = selp_s32(c0 == 0u, xdiag, selp_s32(c0 == 1u, x1[r], xup));
+                const int X1 = selp_s32((Lq & 1u) != 0u, x1[r], X0);
+                const int X2 = selp_s32((Uq & 2u) != 0u, xup, X0);
                 xdiag = x0[r];
                 x0[r] = X0;
                 x1[r] = X1;
