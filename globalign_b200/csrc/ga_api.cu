@@ -1476,9 +1476,9 @@ extern "C" int ga_align_long(ga_ctx *ctx, const uint8_t *s1, int64_t m, const ui
     int launches = 1;
     // The band-parallel traceback is five dependent launches; for a pair of a few bands the single
     // warp that re-fills and walks tile after tile is quicker (GA_LONG_SEQ_BANDS: tuning override).
-    // Measured (tools/probe_small_long.py): 500 x 500 0.24 vs 0.35 ms, 1000 x 1000 0.51 vs 0.56 ms,
-    // 2000 x 2000 1.00 vs 0.72 ms.
-    int seq_bands = 6;
+    // Measured (tools/prof_long.py with GA_LONG_SEQ_BANDS = 6 / 0), sequential vs band-parallel traceback:
+    // 300 x 300 0.16 vs 0.20 ms, 500 x 500 0.24 vs 0.27 ms, 700 x 700 0.35 vs 0.30 ms, 1000 x 1000 0.50 vs 0.33 ms.
+    int seq_bands = 3;
     if (const char *e = getenv("GA_LONG_SEQ_BANDS")) seq_bands = atoi(e);
     const bool parallel = !cost_only && m >= 2 && n >= 2 && !(flags & GA_F_SERIAL) && nbands > seq_bands;
     if (!cost_only) {

@@ -104,13 +104,13 @@ def test_long_path_equals_batched_kernel_and_golden_cfg1():
     assert list(batch.render(ops, s1, s2)) + [cost] == row["out"][:4]
     bc, bops, boff, blen, bst = ctx.align_batch(b.s1, b.off1, b.s2, b.off2)
     assert bc[0] == cost and np.array_equal(_native.unpack_ops(bops, 0, int(blen[0])), ops)
-    assert info["trace_mode"] == 0 and info["retraced_tiles"] >= 4      # 1 kb x 1 kb: six bands, sequential traceback
-    os.environ["GA_LONG_SEQ_BANDS"] = "0"                               # ... and the band-parallel form on the same pair
+    assert info["trace_mode"] == 1 and info["retraced_tiles"] >= 4      # 1 kb x 1 kb: six bands, band-parallel traceback
+    os.environ["GA_LONG_SEQ_BANDS"] = "6"                               # ... and the sequential form on the same pair
     try:
         cost_p, ops_p, status_p, info_p = ctx.align_long(b.s1, b.s2)
     finally:
         os.environ.pop("GA_LONG_SEQ_BANDS", None)
-    assert info_p["trace_mode"] == 1 and cost_p == cost and np.array_equal(ops_p, ops)
+    assert info_p["trace_mode"] == 0 and cost_p == cost and np.array_equal(ops_p, ops)
     ctx.close()
 
 
