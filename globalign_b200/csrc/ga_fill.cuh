@@ -338,6 +338,15 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                 unsigned hb = 0, ub = 0, bv = 0;
                 int rowj = sc.o;                       // TABLE: running row-0 value (pass 0, lane g == 0)
                 int rowjB = sc.o;                      // PT: the same for pair B
+                // PT kernels with one group per warp, pass 0: the row-0 values h(0, j), U(0, j) -- running sums
+                // of per-letter gap costs, clamped by the sentinel -- used to be computed step by step by
+                // lane 0 alone, a divergent stretch of ~50 instructions with two dependent loads in which
+                // the other 31 lanes waited (ncu source counters, cfg3: 4 % of the instructions, 10 % of
+                // the time).  Now every 32 steps each lane computes them for ONE column (its letters, a
+                // warp scan over the gap costs) and lane 0 picks up the column of the step by shuffle.
+                constexpr bool ROW0_AHEAD = PT && G == 32;
+                unsigned r0h = 0, r0u = 0;             // ROW0_AHEAD: packed h / U of row 0 at column t0 + lane + 1
+                int r0baseA = sc.o, r0baseB = sc.o;    // ... running sums up to column t0
                 int2 nxt = make_int2(0, 0);
                 if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
                 uint4 *cbase = codes + td.code_off + (size_t)p * ((nTB + 1) / 2) * (L::WPP * 64);
@@ -348,13 +357,36 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                     for (int u = 0; u < L::S; ++u) {
                         const int t = tb * L::S + u;
                         const int j = t - g + 1;
+                        if (ROW0_AHEAD && p == 0 && (t & 31) == 0) {
+                            const int c = t + lane;                        // letter index of column c + 1
+                            const unsigned lw = c < sb_len ? (unsigned)myb[c] : (padb | (padb << 16));
+                            int ga = (s_gh[lw & 0xFFFFu] - 1) >> 2, gb = (s_gh[lw >> 16] - 1) >> 2;   // (padding letter: 0)
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const int va = __shfl_up_sync(FULL, ga, d), vb = __shfl_up_sync(FULL, gb, d);
+                                if (lane >= d) { ga += va; gb += vb; }
+                            }
+                            const unsigned rjA = (unsigned)(r0baseA + ga), rjB = (unsigned)(r0baseB + gb);
+                            r0h = V::pk(min(bigA, rjA), min(bigB, rjB)) << 2;
+                            r0u = V::pk(min(bigA, rjA + sc.o), min(bigB, rjB + sc.o)) << 2;
+                            r0baseA += __shfl_sync(FULL, ga, 31);
+                            r0baseB += __shfl_sync(FULL, gb, 31);
+                        }
+                        unsigned row0h = 0, row0u = 0;
+                        if (ROW0_AHEAD && p == 0) {
+                            row0h = __shfl_sync(FULL, r0h, t & 31);
+                            row0u = __shfl_sync(FULL, r0u, t & 31);
+                        }
                         unsigned rh = __shfl_up_sync(FULL, hb, 1);
                         unsigned ru = __shfl_up_sync(FULL, ub, 1);
                         unsigned bin = __shfl_up_sync(FULL, bv, 1);
                         const unsigned bnew = (unsigned)myb[t];
                         if (g == 0) {
                             bin = bnew;
-                            if (p == 0) {
+                            if (ROW0_AHEAD && p == 0) {
+                                rh = row0h;
+                                ru = row0u;
+                            } else if (p == 0) {
                                 unsigned rj, rjB;      // row-0 value at column t+1 (level 1)
                                 if (PT) {
                                     // the padding letter A costs nothing: past the end of a pair the
