@@ -192,6 +192,8 @@ struct ga_ctx {
     int n_bufs = 1;                    // code buffers of the current plan (1 serial, else 2)
     // staging for the host-buffer entry point
     DevBuf d_s1, d_s2, d_off1, d_off2, d_cost, d_ops, d_opsoff, d_len, d_status;
+    DevBuf d_u1, d_u2;                  // GA_F_SEQ_5BIT: the letters of the batch unpacked to bytes (chunk by chunk)
+    int in_bits = 8;                    // bits per letter of the caller's sequence buffers (5: unpacked before the kernels)
     // long-pair path
     DevBuf l_colsum, l_rowsum, l_brow, l_vchk, l_prog, l_misc, l_xrow, l_meta, l_seg;
     // single-pair value-table paths (ga_fill_values, ga_align_replay): kept between calls
@@ -363,6 +365,8 @@ static std::vector<std::pair<const char *, DevBuf *>> all_buffers(ga_ctx *ctx) {
         {"d_counter", &ctx->d_counter},
         {"d_s1", &ctx->d_s1},
         {"d_s2", &ctx->d_s2},
+        {"d_u1", &ctx->d_u1},
+        {"d_u2", &ctx->d_u2},
         {"d_off1", &ctx->d_off1},
         {"d_off2", &ctx->d_off2},
         {"d_cost", &ctx->d_cost},
@@ -677,7 +681,13 @@ static int plan_common(ga_ctx *ctx, const int64_t *s1_off, const int64_t *s2_off
         const int bits = seq_bits_of(flags);
         if (bits < 0) return fail(ctx, GA_E_ARG, "choose one sequence packing");
         if (ctx->sc.A > (1 << bits)) return fail(ctx, GA_E_ARG, "alphabet of %d letters does not fit %d-bit packed sequences", ctx->sc.A, bits);
-        ctx->sc.seq_bits = bits;
+        ctx->in_bits = bits;
+        ctx->sc.seq_bits = bits == 5 ? 8 : bits;        // 5-bit streams are unpacked to bytes per chunk (run_pipeline)
+        if (bits == 5) {
+            const int64_t t1 = s1_off ? s1_off[n_pairs] : (int64_t)maxM * n_pairs, t2 = s2_off ? s2_off[n_pairs] : (int64_t)maxN * n_pairs;
+            int rc;
+            if ((rc = ensure(ctx, ctx->d_u1, (size_t)t1 + 32)) || (rc = ensure(ctx, ctx->d_u2, (size_t)t2 + 32))) return rc;
+        }
         const char *e = getenv("GA_CODE_PAIRS");
         ctx->sc.code_pairs = e ? (atoi(e) != 0) : 1;
     }
@@ -1013,10 +1023,13 @@ struct HostIO {
 // but the step time does not change -- fill and walk share the same SM slots either way.)  Everything is
 // bracketed by ev[0] / ev[1] on the caller-visible stream, which finally waits for
 // all auxiliary streams.
-static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_off, const uint8_t *d_s2,
+static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1_in, const int64_t *d_s1_off, const uint8_t *d_s2_in,
                         const int64_t *d_s2_off, int32_t *d_cost, uint8_t *d_ops, const int64_t *d_ops_off,
                         int32_t *d_len, int32_t *d_status, const HostIO *io) {
     const KernelCfg *cfg = ctx->cfg;
+    // (5-bit letter streams are unpacked chunk by chunk into d_u1 / d_u2, see below)
+    const uint8_t *d_s1 = ctx->in_bits == 5 ? (const uint8_t *)ctx->d_u1.p : d_s1_in;
+    const uint8_t *d_s2 = ctx->in_bits == 5 ? (const uint8_t *)ctx->d_u2.p : d_s2_in;
     const bool cost_only = (ctx->plan_flags & GA_F_COST_ONLY) != 0;
     const bool serial = ctx->serial || ctx->chunks.size() == 1;
     cudaStream_t main = ctx->stream;
@@ -1048,6 +1061,12 @@ static int run_pipeline(ga_ctx *ctx, const uint8_t *d_s1, const int64_t *d_s1_of
         }
         if (!serial && c >= (size_t)ctx->n_bufs) CK(cudaStreamWaitEvent(sF, ctx->cev[c - ctx->n_bufs].w1, 0));   // code buffer free
         CK(cudaEventRecord(E.f0, sF));
+        if (ctx->in_bits == 5) {    // this chunk's letters as bytes; the kernels below read those
+            const int ug = ctx->sm_count * 8;
+            unpack5_kernel<<<ug, 256, 0, sF>>>(d_s1_in, (const long long *)d_s1_off, ctx->uniM, ch.pair_lo, ch.pair_hi, (uint8_t *)ctx->d_u1.p);
+            unpack5_kernel<<<ug, 256, 0, sF>>>(d_s2_in, (const long long *)d_s2_off, ctx->uniN, ch.pair_lo, ch.pair_hi, (uint8_t *)ctx->d_u2.p);
+            CK(cudaGetLastError());
+        }
         const bool persistent = ctx->persistent || serial;
         const int grid = persistent ? std::min(ctx->grid, (n_tiles + 3) / 4) : (n_tiles + 3) / 4;
         const TileDesc *d_tiles = ctx->uniform ? nullptr : (const TileDesc *)ctx->d_tiles.p + ch.tile_lo;

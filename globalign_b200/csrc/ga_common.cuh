@@ -48,7 +48,7 @@ struct SchemeDev {
     // the cell update (profiles/README.md), the FMA pipe would otherwise idle.
     unsigned k_one, k_four, k_minus_one;
     int code_pairs;      // direction-code layout: 1 = two consecutive 2-step blocks of a lane per 32-byte sector
-    int seq_bits;        // bits per input letter: 8 (one letter per byte), 5, 4 or 2 (bit-packed stream)
+    int seq_bits;        // bits per input letter as the kernels see them: 8 (one letter per byte), 4 or 2 (bit-packed stream)
 };
 
 struct TileDesc {
@@ -58,15 +58,44 @@ struct TileDesc {
     int M, N;            // longest seq_1 / seq_2 in the tile
 };
 
-// Letter k of a sequence buffer.  seq_bits = 8: one letter per byte.  5 / 4 / 2: the letters form
-// a little-endian bit stream (letter k in bits [k*bits, (k+1)*bits) of the byte array) -- the usual
-// packed nucleotide layouts, and 5 bits for amino acids; offsets stay in letters.  A 5-bit letter
-// may straddle two bytes (the buffers carry slack behind their last byte).
+// Letter k of a sequence buffer.  seq_bits = 8: one letter per byte.  4 / 2: the letters form a
+// little-endian bit stream (letter k in bits [k*bits, (k+1)*bits) of the byte array), the usual
+// packed nucleotide layouts; offsets stay in letters.  (5-bit streams, GA_F_SEQ_5BIT, never reach
+// the kernels: the host side unpacks every chunk to bytes on the device first, unpack5_kernel --
+// a second load in here for letters that straddle two bytes cost the DNA kernels 2.3 %.)
 __device__ __forceinline__ unsigned ld_letter(const uint8_t *__restrict__ s, long long k, int bits) {
     const long long bit = k * bits;
-    unsigned v = (unsigned)s[bit >> 3];
-    if (bits == 5) v |= (unsigned)s[(bit >> 3) + 1] << 8;
-    return (v >> (unsigned)(bit & 7)) & ((1u << bits) - 1u);
+    return ((unsigned)s[bit >> 3] >> (unsigned)(bit & 7)) & ((1u << bits) - 1u);
+}
+
+// Letters [off[pair_lo], off[pair_hi]) of a 5-bit letter stream (letter k in bits [5k, 5k + 5)) as
+// bytes: out[k] = letter k.  Grid-stride over groups of eight letters (five bytes in, eight out);
+// only letters of the range are written (its edges letter by letter), so the chunks of a pipeline
+// can unpack concurrently.
+__global__ void unpack5_kernel(const uint8_t *__restrict__ packed, const long long *__restrict__ off, long long uni_len,
+                               int pair_lo, int pair_hi, uint8_t *__restrict__ out) {
+    const long long lo = off ? off[pair_lo] : (long long)pair_lo * uni_len;
+    const long long hi = off ? off[pair_hi] : (long long)pair_hi * uni_len;
+    const long long q0 = lo >> 3, q1 = (hi + 7) >> 3;
+    for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < q1; q += (long long)gridDim.x * blockDim.x) {
+        const long long k0 = q << 3;
+        if (k0 >= lo && k0 + 8 <= hi) {
+            const uint8_t *p = packed + 5 * q;
+            const unsigned long long w = (unsigned long long)p[0] | ((unsigned long long)p[1] << 8) | ((unsigned long long)p[2] << 16) |
+                                         ((unsigned long long)p[3] << 24) | ((unsigned long long)p[4] << 32);
+            uint2 v;
+            v.x = (unsigned)(w & 31) | ((unsigned)((w >> 5) & 31) << 8) | ((unsigned)((w >> 10) & 31) << 16) | ((unsigned)((w >> 15) & 31) << 24);
+            v.y = (unsigned)((w >> 20) & 31) | ((unsigned)((w >> 25) & 31) << 8) | ((unsigned)((w >> 30) & 31) << 16) | ((unsigned)((w >> 35) & 31) << 24);
+            *reinterpret_cast<uint2 *>(out + k0) = v;
+        } else {                                   // an edge of the range: only the bytes that hold its letters are read
+            for (long long k = max(k0, lo); k < min(k0 + 8, hi); ++k) {
+                const long long bit = 5 * k;
+                unsigned v = packed[bit >> 3];
+                if ((bit & 7) > 3) v |= (unsigned)packed[(bit >> 3) + 1] << 8;
+                out[k] = (uint8_t)((v >> (bit & 7)) & 31u);
+            }
+        }
+    }
 }
 
 // When every pair of a chunk has the same (m, n) the tile descriptors are arithmetic and are
