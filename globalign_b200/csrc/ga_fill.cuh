@@ -348,7 +348,11 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                 unsigned r0h = 0, r0u = 0;             // ROW0_AHEAD: packed h / U of row 0 at column t0 + lane + 1
                 int r0baseA = sc.o, r0baseB = sc.o;    // ... running sums up to column t0
                 int2 nxt = make_int2(0, 0);
-                if (p > 0 && g == 0) nxt = __ldcg(my_bnd + 1);
+                if (p > 0 && g == 0 && !ROW0_AHEAD) nxt = __ldcg(my_bnd + 1);
+                // ROW0_AHEAD, later passes: the boundary row of the pass above, 32 columns per coalesced load, fetched
+                // 32 steps before lane 0 needs them (lane l holds column t0 + l + 1)
+                int2 bcur = make_int2(0, 0), bnext = make_int2(0, 0);
+                if (ROW0_AHEAD && p > 0) bnext = __ldcg(my_bnd + min(lane + 1, td.N));
                 uint4 *cbase = codes + td.code_off + (size_t)p * ((nTB + 1) / 2) * (L::WPP * 64);
 
                 for (int tb = 0; tb < nTB; ++tb) {
@@ -372,10 +376,14 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                             r0baseA += __shfl_sync(FULL, ga, 31);
                             r0baseB += __shfl_sync(FULL, gb, 31);
                         }
+                        if (ROW0_AHEAD && p > 0 && (t & 31) == 0) {
+                            bcur = bnext;
+                            bnext = __ldcg(my_bnd + min(t + 32 + lane + 1, td.N));
+                        }
                         unsigned row0h = 0, row0u = 0;
-                        if (ROW0_AHEAD && p == 0) {
-                            row0h = __shfl_sync(FULL, r0h, t & 31);
-                            row0u = __shfl_sync(FULL, r0u, t & 31);
+                        if (ROW0_AHEAD) {
+                            row0h = __shfl_sync(FULL, p == 0 ? r0h : (unsigned)bcur.x, t & 31);
+                            row0u = __shfl_sync(FULL, p == 0 ? r0u : (unsigned)bcur.y, t & 31);
                         }
                         unsigned rh = __shfl_up_sync(FULL, hb, 1);
                         unsigned ru = __shfl_up_sync(FULL, ub, 1);
@@ -383,7 +391,7 @@ fill_kernel(const SchemeDev sc, const TileDesc *__restrict__ tiles, const Unifor
                         const unsigned bnew = (unsigned)myb[t];
                         if (g == 0) {
                             bin = bnew;
-                            if (ROW0_AHEAD && p == 0) {
+                            if (ROW0_AHEAD) {
                                 rh = row0h;
                                 ru = row0u;
                             } else if (p == 0) {
